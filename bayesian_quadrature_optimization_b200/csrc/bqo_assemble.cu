@@ -1,0 +1,366 @@
+// Hyper-sample preparation and kernel-matrix assembly.
+//   bqo_hyper_prepare, bqo_scale_points, bqo_kernel_assemble_batched,
+//   bqo_kernel_grad_params_batched, bqo_cross_cov_batched, bqo_task_quadrature_weights
+#include "bqo_common.cuh"
+
+extern "C" int bqo_abi_version(void) { return BQO_ABI_VERSION; }
+
+extern "C" int bqo_set_device(int device) { return (int)cudaSetDevice(device); }
+
+extern "C" int64_t bqo_hyper_stride(const bqo_kernel_desc* desc) {
+    if (!desc) return -1;
+    return bqo_hyper_stride_impl(*desc);
+}
+
+static int check_desc(const bqo_kernel_desc* d) {
+    if (!d) return 0;
+    if (d->kind < 0 || d->kind > 2) return 0;
+    if (d->dim_m < 1 || d->dim_m > BQO_MAX_DIM || d->dim < d->dim_m) return 0;
+    if (d->kind == BQO_KIND_PRODUCT_TASKS && (d->n_tasks < 1 || d->dim != d->dim_m + 1)) return 0;
+    if (d->kind != BQO_KIND_PRODUCT_TASKS && d->dim != d->dim_m) return 0;
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// theta -> hyper block.  One CTA per hyper-sample.
+// Task covariance: TasksKernel.compute_cov_matrix (sbo/kernels/tasks_kernel.py:198-239).
+__global__ void hyper_prepare_kernel(bqo_kernel_desc d, const double* __restrict__ theta,
+                                     double* __restrict__ hyp, int64_t stride) {
+    int s = blockIdx.x;
+    const double* th = theta + (int64_t)s * (2 + d.n_params);
+    double* h = hyp + (int64_t)s * stride;
+    int t = threadIdx.x;
+    if (t == 0) {
+        h[BQO_H_VARNOISE] = th[0];
+        h[BQO_H_MEAN] = th[1];
+        h[BQO_H_SIGMA2] = (d.kind == BQO_KIND_SCALED_MATERN52) ? th[2 + d.dim_m] : 1.0;
+        h[3] = 0.0;
+    }
+    for (int l = t; l < BQO_MAX_DIM; l += blockDim.x) {
+        double ls = (l < d.dim_m) ? th[2 + l] : 1.0;
+        h[BQO_H_LS + l] = ls;
+        h[BQO_H_INVLS + l] = 1.0 / ls;
+    }
+    if (d.kind != BQO_KIND_PRODUCT_TASKS) return;
+    const int T = d.n_tasks;
+    const double* p = th + 2 + d.dim_m;
+    double* C = h + BQO_H_TASKC;
+    double* Lt = C + T * T;
+    if (d.same_corr) {
+        double offd = (T > 1) ? exp(p[1]) : 0.0;
+        double diag = (T > 1) ? (exp(p[0]) + offd * (double)(T - 1)) : exp(p[0]);
+        for (int e = t; e < T * T; e += blockDim.x) {
+            int a = e / T, b = e % T;
+            double v = (a == b) ? diag : offd;
+            C[e] = v;
+            Lt[e] = v;
+        }
+        return;
+    }
+    for (int e = t; e < T * T; e += blockDim.x) {
+        int a = e / T, b = e % T;
+        Lt[e] = (b <= a) ? exp(p[a * (a + 1) / 2 + b]) : 0.0;
+    }
+    __syncthreads();
+    for (int e = t; e < T * T; e += blockDim.x) {
+        int a = e / T, b = e % T;
+        int m = a < b ? a : b;
+        double acc = 0.0;
+        for (int j = 0; j <= m; ++j) acc += Lt[a * T + j] * Lt[b * T + j];
+        C[e] = acc;
+    }
+}
+
+extern "C" int bqo_hyper_prepare(const bqo_kernel_desc* desc, const double* theta, int32_t S,
+                                 double* hyp, void* stream) {
+    BQO_CHECK_ARG(check_desc(desc), 1);
+    BQO_CHECK_ARG(theta != nullptr, 2);
+    BQO_CHECK_ARG(S > 0, 3);
+    BQO_CHECK_ARG(hyp != nullptr, 4);
+    hyper_prepare_kernel<<<S, 128, 0, (cudaStream_t)stream>>>(*desc, theta, hyp,
+                                                             bqo_hyper_stride_impl(*desc));
+    BQO_RETURN_LAST_ERROR();
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void scale_points_kernel(bqo_kernel_desc d, const double* __restrict__ hyp,
+                                    int64_t stride, const double* __restrict__ X, int n, int ldx,
+                                    double* __restrict__ Xs, int32_t* __restrict__ tid) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int s = blockIdx.y;
+    if (i >= n) return;
+    const double* h = hyp + (int64_t)s * stride;
+    for (int l = 0; l < d.dim_m; ++l)
+        Xs[((int64_t)s * d.dim_m + l) * n + i] = X[(int64_t)i * ldx + l] / h[BQO_H_LS + l];
+    if (s == 0 && tid != nullptr && d.kind == BQO_KIND_PRODUCT_TASKS)
+        tid[i] = (int32_t)X[(int64_t)i * ldx + d.dim - 1];
+}
+
+extern "C" int bqo_scale_points(const bqo_kernel_desc* desc, const double* hyp, int32_t S,
+                                const double* X, int32_t n, int32_t ldx, double* Xs, int32_t* tid,
+                                void* stream) {
+    BQO_CHECK_ARG(check_desc(desc), 1);
+    BQO_CHECK_ARG(hyp != nullptr, 2);
+    BQO_CHECK_ARG(S > 0, 3);
+    BQO_CHECK_ARG(X != nullptr, 4);
+    BQO_CHECK_ARG(n > 0, 5);
+    BQO_CHECK_ARG(ldx >= desc->dim, 6);
+    BQO_CHECK_ARG(Xs != nullptr, 7);
+    BQO_CHECK_ARG(desc->kind != BQO_KIND_PRODUCT_TASKS || tid != nullptr, 8);
+    dim3 grid((n + 255) / 256, S);
+    scale_points_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        *desc, hyp, bqo_hyper_stride_impl(*desc), X, n, ldx, Xs, tid);
+    BQO_RETURN_LAST_ERROR();
+}
+
+// ---------------------------------------------------------------------------------------------
+// K[s][i][j].  16x16 thread tiles; column reads of the SoA Xs are coalesced, row reads broadcast.
+template <int DM>
+__global__ void assemble_kernel(bqo_kernel_desc d, const double* __restrict__ hyp, int64_t stride,
+                                const double* __restrict__ Xs, const int32_t* __restrict__ tid,
+                                int n, const double* __restrict__ noise_obs, int add_noise,
+                                const double* __restrict__ extra_diag, double* __restrict__ K) {
+    int j = blockIdx.x * 32 + threadIdx.x;
+    int i0 = blockIdx.y * 32 + threadIdx.y * 4;
+    int s = blockIdx.z;
+    if (j >= n) return;
+    const double* h = hyp + (int64_t)s * stride;
+    const double* xs = Xs + (int64_t)s * d.dim_m * n;
+    const int dm = (DM > 0) ? DM : d.dim_m;
+    double xj[(DM > 0) ? DM : BQO_MAX_DIM];
+#pragma unroll
+    for (int l = 0; l < dm; ++l) xj[l] = xs[(int64_t)l * n + j];
+    const double sigma2 = h[BQO_H_SIGMA2];
+    const int tj = (d.kind == BQO_KIND_PRODUCT_TASKS) ? tid[j] : 0;
+    double* Ks = K + (int64_t)s * n * n;
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) {
+        int i = i0 + ii;
+        if (i >= n) break;
+        double r2 = 0.0;
+#pragma unroll
+        for (int l = 0; l < dm; ++l) {
+            double df = xs[(int64_t)l * n + i] - xj[l];
+            r2 = fma(df, df, r2);
+        }
+        double k = bqo_matern52(r2);
+        if (d.kind == BQO_KIND_SCALED_MATERN52) k *= sigma2;
+        if (d.kind == BQO_KIND_PRODUCT_TASKS) k *= bqo_task_cov(h, d.n_tasks, tid[i], tj);
+        if (i == j) {
+            if (add_noise) {
+                if (noise_obs) k += noise_obs[i];
+                k += h[BQO_H_VARNOISE];
+            }
+            if (extra_diag) k += extra_diag[s];
+        }
+        Ks[(int64_t)i * n + j] = k;
+    }
+}
+
+extern "C" int bqo_kernel_assemble_batched(const bqo_kernel_desc* desc, const double* hyp,
+                                           int32_t S, const double* Xs, const int32_t* tid,
+                                           int32_t n, const double* noise_obs, int32_t add_noise,
+                                           const double* extra_diag, double* K, void* stream) {
+    BQO_CHECK_ARG(check_desc(desc), 1);
+    BQO_CHECK_ARG(hyp != nullptr, 2);
+    BQO_CHECK_ARG(S > 0, 3);
+    BQO_CHECK_ARG(Xs != nullptr, 4);
+    BQO_CHECK_ARG(desc->kind != BQO_KIND_PRODUCT_TASKS || tid != nullptr, 5);
+    BQO_CHECK_ARG(n > 0, 6);
+    BQO_CHECK_ARG(K != nullptr, 10);
+    dim3 block(32, 8);
+    dim3 grid((n + 31) / 32, (n + 31) / 32, S);
+    int64_t st = bqo_hyper_stride_impl(*desc);
+    cudaStream_t cs = (cudaStream_t)stream;
+#define LAUNCH_ASM(DMV)                                                                          \
+    assemble_kernel<DMV><<<grid, block, 0, cs>>>(*desc, hyp, st, Xs, tid, n, noise_obs,          \
+                                                 add_noise, extra_diag, K)
+    switch (desc->dim_m) {
+        case 1: LAUNCH_ASM(1); break;
+        case 2: LAUNCH_ASM(2); break;
+        case 3: LAUNCH_ASM(3); break;
+        case 4: LAUNCH_ASM(4); break;
+        case 6: LAUNCH_ASM(6); break;
+        default: LAUNCH_ASM(0); break;
+    }
+#undef LAUNCH_ASM
+    BQO_RETURN_LAST_ERROR();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Derivative of the task covariance with respect to task parameter m, entry (u, v)
+// (GradientTasksKernel.gradient_respect_parameters, sbo/kernels/tasks_kernel.py:580-622).
+__device__ __forceinline__ double bqo_task_dcov(const bqo_kernel_desc& d,
+                                                const double* __restrict__ h, int m, int u, int v) {
+    const int T = d.n_tasks;
+    const double* C = h + BQO_H_TASKC;
+    const double* Lt = C + T * T;
+    if (d.same_corr) {
+        if (T == 1) return (u == v) ? C[0] : 0.0;
+        double value = C[1];  // chol_base_cov_matrix[0, 1]
+        if (m == 0) return (u == v) ? (C[0] - value * (double)(T - 1)) : 0.0;
+        return (u == v) ? value * (double)(T - 1) : C[u * T + v];
+    }
+    // m <-> (a, b), b <= a: tmp_der[a, b] = L[a, b]; M = tmp_der L^T; grad = M + M^T
+    int a = (int)floor((sqrt(8.0 * (double)m + 1.0) - 1.0) * 0.5);
+    while ((a + 1) * (a + 2) / 2 <= m) ++a;
+    while (a * (a + 1) / 2 > m) --a;
+    int b = m - a * (a + 1) / 2;
+    double lab = Lt[a * T + b];
+    double g = 0.0;
+    if (u == a) g += lab * Lt[v * T + b];
+    if (v == a) g += lab * Lt[u * T + b];
+    return g;
+}
+
+// dK[s][p][i][j]
+__global__ void grad_params_kernel(bqo_kernel_desc d, const double* __restrict__ hyp,
+                                   int64_t stride, const double* __restrict__ Xs,
+                                   const int32_t* __restrict__ tid, int n,
+                                   double* __restrict__ dK) {
+    int j = blockIdx.x * 32 + threadIdx.x;
+    int i = blockIdx.y * 8 + threadIdx.y;
+    int s = blockIdx.z;
+    if (i >= n || j >= n) return;
+    const double* h = hyp + (int64_t)s * stride;
+    const double* xs = Xs + (int64_t)s * d.dim_m * n;
+    double df[BQO_MAX_DIM];
+    double r2 = 0.0;
+    for (int l = 0; l < d.dim_m; ++l) {
+        df[l] = xs[(int64_t)l * n + i] - xs[(int64_t)l * n + j];
+        r2 = fma(df[l], df[l], r2);
+    }
+    double km, g;
+    bqo_matern52_kg(r2, km, g);
+    double other = 1.0;  // factor multiplying the Matern derivative
+    if (d.kind == BQO_KIND_SCALED_MATERN52) other = h[BQO_H_SIGMA2];
+    int ti = 0, tj = 0;
+    if (d.kind == BQO_KIND_PRODUCT_TASKS) {
+        ti = tid[i];
+        tj = tid[j];
+        other = bqo_task_cov(h, d.n_tasks, ti, tj);
+    }
+    double* base = dK + ((int64_t)s * d.n_params) * n * n + (int64_t)i * n + j;
+    // d k_M / d ls_l = k'(r) (1/r) delta_l^2 (-1/ls_l^3) = -g(r) (delta_l/ls_l)^2 / ls_l,
+    // diagonal forced to 0 (sbo/lib/distances.py:53-63, sbo/kernels/matern52.py:386-392).
+    for (int l = 0; l < d.dim_m; ++l) {
+        double v = (i == j) ? 0.0 : (-g * df[l] * df[l] * h[BQO_H_INVLS + l]) * other;
+        base[(int64_t)l * n * n] = v;
+    }
+    if (d.kind == BQO_KIND_SCALED_MATERN52) {
+        // d(sigma2 k)/d sigma2 = cov / sigma2 (sbo/kernels/scaled_kernel.py:212)
+        base[(int64_t)d.dim_m * n * n] = (km * h[BQO_H_SIGMA2]) / h[BQO_H_SIGMA2];
+    } else if (d.kind == BQO_KIND_PRODUCT_TASKS) {
+        int pt = d.n_params - d.dim_m;
+        for (int m = 0; m < pt; ++m)
+            base[(int64_t)(d.dim_m + m) * n * n] = km * bqo_task_dcov(d, h, m, ti, tj);
+    }
+}
+
+extern "C" int bqo_kernel_grad_params_batched(const bqo_kernel_desc* desc, const double* hyp,
+                                              int32_t S, const double* Xs, const int32_t* tid,
+                                              int32_t n, double* dK, void* stream) {
+    BQO_CHECK_ARG(check_desc(desc), 1);
+    BQO_CHECK_ARG(hyp != nullptr, 2);
+    BQO_CHECK_ARG(S > 0, 3);
+    BQO_CHECK_ARG(Xs != nullptr, 4);
+    BQO_CHECK_ARG(desc->kind != BQO_KIND_PRODUCT_TASKS || tid != nullptr, 5);
+    BQO_CHECK_ARG(n > 0, 6);
+    BQO_CHECK_ARG(dK != nullptr, 7);
+    dim3 block(32, 8);
+    dim3 grid((n + 31) / 32, (n + 7) / 8, S);
+    grad_params_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
+        *desc, hyp, bqo_hyper_stride_impl(*desc), Xs, tid, n, dK);
+    BQO_RETURN_LAST_ERROR();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cross covariance of m raw points against the training set, and its gradient w.r.t. the point.
+__global__ void cross_cov_kernel(bqo_kernel_desc d, const double* __restrict__ hyp, int64_t stride,
+                                 const double* __restrict__ Xs, const int32_t* __restrict__ tid,
+                                 int n, const double* __restrict__ P, int m, int interleave,
+                                 double* __restrict__ KP, double* __restrict__ dKP) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int q = blockIdx.y;
+    int s = blockIdx.z;
+    if (i >= n) return;
+    const double* h = hyp + (int64_t)s * stride;
+    const double* xs = Xs + (int64_t)s * d.dim_m * n;
+    const double* p = P + (int64_t)q * d.dim;
+    double df[BQO_MAX_DIM];
+    double r2 = 0.0;
+    for (int l = 0; l < d.dim_m; ++l) {
+        df[l] = p[l] / h[BQO_H_LS + l] - xs[(int64_t)l * n + i];
+        r2 = fma(df[l], df[l], r2);
+    }
+    double k, g;
+    bqo_matern52_kg(r2, k, g);
+    double other = 1.0;
+    if (d.kind == BQO_KIND_SCALED_MATERN52) other = h[BQO_H_SIGMA2];
+    if (d.kind == BQO_KIND_PRODUCT_TASKS)
+        other = bqo_task_cov(h, d.n_tasks, (int)p[d.dim - 1], tid[i]);
+    const int rows = 1 + d.dim_m;
+    if (interleave) {
+        double* base = KP + (((int64_t)s * m + q) * rows) * n + i;
+        base[0] = k * other;
+        for (int l = 0; l < d.dim_m; ++l)
+            base[(int64_t)(1 + l) * n] = g * df[l] * h[BQO_H_INVLS + l] * other;
+    } else {
+        KP[((int64_t)s * m + q) * n + i] = k * other;
+        if (dKP) {
+            double* base = dKP + (((int64_t)s * m + q) * d.dim_m) * n + i;
+            for (int l = 0; l < d.dim_m; ++l)
+                base[(int64_t)l * n] = g * df[l] * h[BQO_H_INVLS + l] * other;
+        }
+    }
+}
+
+extern "C" int bqo_cross_cov_batched(const bqo_kernel_desc* desc, const double* hyp, int32_t S,
+                                     const double* Xs, const int32_t* tid, int32_t n,
+                                     const double* P, int32_t m, int32_t interleave, double* KP,
+                                     double* dKP, void* stream) {
+    BQO_CHECK_ARG(check_desc(desc), 1);
+    BQO_CHECK_ARG(hyp != nullptr, 2);
+    BQO_CHECK_ARG(S > 0, 3);
+    BQO_CHECK_ARG(Xs != nullptr, 4);
+    BQO_CHECK_ARG(desc->kind != BQO_KIND_PRODUCT_TASKS || tid != nullptr, 5);
+    BQO_CHECK_ARG(n > 0, 6);
+    BQO_CHECK_ARG(P != nullptr, 7);
+    BQO_CHECK_ARG(m > 0 && m <= 65535, 8);
+    BQO_CHECK_ARG(KP != nullptr, 10);
+    BQO_CHECK_ARG(S <= 65535, 3);
+    dim3 grid((n + 255) / 256, m, S);
+    cross_cov_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        *desc, hyp, bqo_hyper_stride_impl(*desc), Xs, tid, n, P, m, interleave, KP, dKP);
+    BQO_RETURN_LAST_ERROR();
+}
+
+// ---------------------------------------------------------------------------------------------
+// qt[s][t'] = sum_t w_t C_s[t][t'] / sum_t w_t  (np.average over the task axis,
+// sbo/lib/expectations.py:73-74).
+__global__ void task_qweights_kernel(bqo_kernel_desc d, const double* __restrict__ hyp,
+                                     int64_t stride, const double* __restrict__ weights,
+                                     double* __restrict__ qt) {
+    int s = blockIdx.x;
+    const int T = d.n_tasks;
+    const double* C = hyp + (int64_t)s * stride + BQO_H_TASKC;
+    double wsum = 0.0;
+    for (int t = 0; t < T; ++t) wsum += weights ? weights[t] : 1.0;
+    for (int tp = threadIdx.x; tp < T; tp += blockDim.x) {
+        double acc = 0.0;
+        for (int t = 0; t < T; ++t) acc += (weights ? weights[t] : 1.0) * C[t * T + tp];
+        qt[(int64_t)s * T + tp] = acc / wsum;
+    }
+}
+
+extern "C" int bqo_task_quadrature_weights(const bqo_kernel_desc* desc, const double* hyp,
+                                           int32_t S, const double* weights, double* qt,
+                                           void* stream) {
+    BQO_CHECK_ARG(check_desc(desc) && desc->kind == BQO_KIND_PRODUCT_TASKS, 1);
+    BQO_CHECK_ARG(hyp != nullptr, 2);
+    BQO_CHECK_ARG(S > 0, 3);
+    BQO_CHECK_ARG(qt != nullptr, 5);
+    task_qweights_kernel<<<S, 128, 0, (cudaStream_t)stream>>>(
+        *desc, hyp, bqo_hyper_stride_impl(*desc), weights, qt);
+    BQO_RETURN_LAST_ERROR();
+}

@@ -1,0 +1,474 @@
+// Batched FP64 Cholesky, triangular solves, alpha and log marginal likelihood
+// (SURVEY 8a rows a10, a11, a12, a17).
+//
+//   potrf: right-looking blocked factorisation, NB = 64.  Per block column two launches:
+//     (1) panel kernel: every CTA factors the 64x64 diagonal block in shared memory
+//         (redundantly -- it is tiny -- so no inter-CTA dependency exists) and solves its own 64
+//         rows of the panel against it; (2) trailing update A22 -= L21 L21^T on DMMA tiles.
+//   potrs: RHS-major layout Bt[rhs][n].  A CTA owns 64 right-hand sides and walks the block
+//     columns itself (left-looking): tile = B_tile - Y[:, :k0] L[kb, :k0]^T on DMMA, then a
+//     64x64 substitution in shared memory.  No cross-CTA dependency, one launch per direction.
+#include "bqo_gemm.cuh"
+#include <vector>
+
+#define NB BQO_TILE
+#define LDT (NB + 1)
+
+// ---------------------------------------------------------------------------------------------
+// Factor the NB x NB block held in shared memory `Ls` (stride LDT), lower triangle, in place.
+// Left-looking by column; threads 0..NB-1 own one row each.  Returns (to all threads) 0 or the
+// 1-based index of the first non-positive pivot.  `nv` = valid rows/cols (<= NB).
+__device__ int potrf_block_smem(double* Ls, int nv, int* flag_sm) {
+    const int t = threadIdx.x;
+    if (t == 0) *flag_sm = 0;
+    __syncthreads();
+    for (int k = 0; k < nv; ++k) {
+        if (t >= k && t < nv) {
+            double a0 = 0.0, a1 = 0.0;
+            int j = 0;
+            for (; j + 1 < k; j += 2) {
+                a0 = fma(Ls[t * LDT + j], Ls[k * LDT + j], a0);
+                a1 = fma(Ls[t * LDT + j + 1], Ls[k * LDT + j + 1], a1);
+            }
+            if (j < k) a0 = fma(Ls[t * LDT + j], Ls[k * LDT + j], a0);
+            Ls[t * LDT + k] -= (a0 + a1);
+        }
+        __syncthreads();
+        double d = Ls[k * LDT + k];
+        if (!(d > 0.0)) {  // also catches NaN
+            if (t == 0 && *flag_sm == 0) *flag_sm = k + 1;
+            __syncthreads();
+            return *flag_sm;
+        }
+        double sd = sqrt(d);
+        __syncthreads();
+        if (t == k) Ls[k * LDT + k] = sd;
+        if (t > k && t < nv) Ls[t * LDT + k] /= sd;
+        __syncthreads();
+    }
+    return 0;
+}
+
+// Diagonal block kernel: factor the NB x NB block at k0 in place (only launched for k0 = 0; the
+// later diagonal blocks are factored by the trailing-update CTA that finalises them).
+__global__ void __launch_bounds__(128) potrf_diag_kernel(double* __restrict__ A, int n, int k0,
+                                                         int* __restrict__ info) {
+    extern __shared__ double dyn_smem[];
+    double* Ls = dyn_smem;
+    __shared__ int flag;
+    const int s = blockIdx.x;
+    double* As = A + (int64_t)s * n * n;
+    const int nv = (n - k0 < NB) ? n - k0 : NB;
+    const int t = threadIdx.x;
+    for (int e = t; e < NB * NB; e += blockDim.x) {
+        int r = e / NB, c = e % NB;
+        double v = 0.0;
+        if (r < nv && c <= r) v = As[(int64_t)(k0 + r) * n + (k0 + c)];
+        Ls[r * LDT + c] = v;
+    }
+    __syncthreads();
+    int bad = potrf_block_smem(Ls, nv, &flag);
+    if (bad) {
+        if (t == 0) info[s] = k0 + bad;
+        return;
+    }
+    for (int e = t; e < NB * NB; e += blockDim.x) {
+        int r = e / NB, c = e % NB;
+        if (r < nv && c <= r) As[(int64_t)(k0 + r) * n + (k0 + c)] = Ls[r * LDT + c];
+    }
+}
+
+// Panel solve for block column k0: rows below the diagonal block, X L11^T = A21.
+// grid = (row tiles below the diagonal, S); one thread per row, L11 broadcast from smem.
+__global__ void __launch_bounds__(128) potrf_trsm_kernel(double* __restrict__ A, int n, int k0,
+                                                         const int* __restrict__ info) {
+    extern __shared__ double dyn_smem[];
+    double* Ls = dyn_smem;
+    const int s = blockIdx.y;
+    if (info[s] != 0) return;  // this matrix already failed
+    double* As = A + (int64_t)s * n * n;
+    const int t = threadIdx.x;
+    for (int e = t; e < NB * NB; e += blockDim.x) {
+        int r = e / NB, c = e % NB;
+        Ls[r * LDT + c] = (c <= r) ? As[(int64_t)(k0 + r) * n + (k0 + c)] : 0.0;
+    }
+    __syncthreads();
+    const int row = k0 + NB + blockIdx.x * NB + t;
+    if (t < NB && row < n) {
+        double x[NB];
+        double* ap = As + (int64_t)row * n + k0;
+#pragma unroll
+        for (int j = 0; j < NB; ++j) x[j] = ap[j];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            double acc = x[j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) acc = fma(-x[k], Ls[j * LDT + k], acc);
+            x[j] = acc / Ls[j * LDT + j];
+        }
+#pragma unroll
+        for (int j = 0; j < NB; ++j) ap[j] = x[j];
+    }
+}
+
+// Trailing update: A[i][j] -= sum_k L[i][k0+k] L[j][k0+k] for i, j >= k0 + NB, lower tiles only.
+// The CTA of tile (0,0) finalises the next diagonal block and factors it on the spot.
+__global__ void __launch_bounds__(128) potrf_syrk_kernel(double* __restrict__ A, int n, int k0,
+                                                         int* __restrict__ info) {
+    extern __shared__ double dyn_smem[];
+    double* Asm = dyn_smem;
+    double* Bsm = Asm + BQO_OPER_TILE_DOUBLES;
+    double* Ls = Bsm + BQO_OPER_TILE_DOUBLES;
+    __shared__ int flag;
+    const int s = blockIdx.z;
+    if (info[s] != 0) return;
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    if (bj > bi) return;
+    double* As = A + (int64_t)s * n * n;
+    const int base = k0 + NB;
+    const int i0 = base + bi * NB, j0 = base + bj * NB;
+    const int ri = (n - i0 < NB) ? n - i0 : NB;
+    const int rj = (n - j0 < NB) ? n - j0 : NB;
+    BqoAcc acc;
+    acc.zero();
+    bqo_gemm_tile<true, true>(acc, As + (int64_t)i0 * n + k0, n, ri, As + (int64_t)j0 * n + k0, n,
+                              rj, NB, Asm, Bsm);
+    if (bi == 0 && bj == 0) {
+        bqo_acc_foreach(acc, [&](int r, int c, double& v) {
+            double a = (r < ri && c <= r && c < rj) ? As[(int64_t)(i0 + r) * n + (j0 + c)] - v : 0.0;
+            Ls[r * LDT + c] = a;
+        });
+        __syncthreads();
+        int bad = potrf_block_smem(Ls, ri, &flag);
+        if (bad) {
+            if (threadIdx.x == 0) info[s] = i0 + bad;
+            return;
+        }
+        for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
+            int r = e / NB, c = e % NB;
+            if (r < ri && c <= r) As[(int64_t)(i0 + r) * n + (j0 + c)] = Ls[r * LDT + c];
+        }
+        return;
+    }
+    bqo_acc_foreach(acc, [&](int r, int c, double& v) {
+        if (r < ri && c < rj) As[(int64_t)(i0 + r) * n + (j0 + c)] -= v;
+    });
+}
+
+__global__ void zero_upper_kernel(double* __restrict__ A, int n) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = blockIdx.y;
+    int s = blockIdx.z;
+    if (j < n && j > i) A[((int64_t)s * n + i) * n + j] = 0.0;
+}
+
+#define SMEM_LS ((size_t)NB * LDT * sizeof(double))
+#define SMEM_SYRK ((size_t)(2 * BQO_OPER_TILE_DOUBLES + NB * LDT) * sizeof(double))
+#define SMEM_TRSM ((size_t)(2 * BQO_OPER_TILE_DOUBLES + 2 * NB * LDT) * sizeof(double))
+
+static int potrf_launch(double* A, int n, int S, int* info, cudaStream_t cs) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(potrf_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)SMEM_SYRK);
+        attr_done = true;
+    }
+    cudaMemsetAsync(info, 0, sizeof(int) * S, cs);
+    potrf_diag_kernel<<<S, 128, SMEM_LS, cs>>>(A, n, 0, info);
+    for (int k0 = 0; k0 + NB < n; k0 += NB) {
+        int tr = (n - k0 - NB + NB - 1) / NB;  // row tiles below the diagonal block
+        dim3 pg(tr, S);
+        potrf_trsm_kernel<<<pg, 128, SMEM_LS, cs>>>(A, n, k0, info);
+        dim3 sg(tr, tr, S);
+        potrf_syrk_kernel<<<sg, 128, SMEM_SYRK, cs>>>(A, n, k0, info);
+    }
+    dim3 zg((n + 255) / 256, n, S);
+    zero_upper_kernel<<<zg, 256, 0, cs>>>(A, n);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int bqo_potrf_batched(double* A, int32_t n, int32_t S, int32_t* info, void* stream) {
+    BQO_CHECK_ARG(A != nullptr, 1);
+    BQO_CHECK_ARG(n > 0, 2);
+    BQO_CHECK_ARG(S > 0 && S <= 65535, 3);
+    BQO_CHECK_ARG(info != nullptr, 4);
+    return potrf_launch(A, n, S, info, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Triangular solves, RHS-major.  CTA = 64 right-hand sides x all block columns.
+//   forward : L y = b      y[kb] = (b[kb] - sum_{j<kb} L[kb][j] y[j]) / L[kb][kb]
+//   backward: L^T x = y    x[kb] = (y[kb] - sum_{j>kb} L[j][kb]^T x[j]) / L[kb][kb]^T
+// `first_block_is_tile`: the right-hand sides are rows of the identity, so for RHS tile rt the
+// forward solution vanishes before block rt and the walk can start there.
+template <bool FORWARD>
+__global__ void __launch_bounds__(128) trsm_kernel(const double* __restrict__ L, int n,
+                                                   double* __restrict__ Bt, int m,
+                                                   int identity_rhs) {
+    extern __shared__ double dyn_smem[];
+    double* Asm = dyn_smem;
+    double* Bsm = Asm + BQO_OPER_TILE_DOUBLES;
+    double* Ts = Bsm + BQO_OPER_TILE_DOUBLES;
+    double* Ls = Ts + NB * LDT;
+    const int s = blockIdx.y;
+    const double* Lm = L + (int64_t)s * n * n;
+    const int r0 = blockIdx.x * NB;
+    const int rv = (m - r0 < NB) ? m - r0 : NB;
+    double* Bs_ = Bt + ((int64_t)s * m + r0) * n;
+    const int nb = (n + NB - 1) / NB;
+    const int t = threadIdx.x;
+    int kb_begin = FORWARD ? 0 : nb - 1;
+    if (FORWARD && identity_rhs) kb_begin = r0 / NB;
+    for (int kb = kb_begin; FORWARD ? (kb < nb) : (kb >= 0); kb += FORWARD ? 1 : -1) {
+        const int k0 = kb * NB;
+        const int kv = (n - k0 < NB) ? n - k0 : NB;
+        BqoAcc acc;
+        acc.zero();
+        if (FORWARD) {
+            int kstart = identity_rhs ? kb_begin * NB : 0;
+            // acc[r][c] = sum_{k<k0} Y[r][k] L[k0+c][k]
+            if (k0 > kstart)
+                bqo_gemm_tile<true, true>(acc, Bs_ + kstart, n, rv, Lm + (int64_t)k0 * n + kstart,
+                                          n, kv, k0 - kstart, Asm, Bsm);
+        } else {
+            // acc[r][c] = sum_{k>=k0+NB} X[r][k] L[k][k0+c]
+            int kk = k0 + NB;
+            if (kk < n)
+                bqo_gemm_tile<true, false>(acc, Bs_ + kk, n, rv, Lm + (int64_t)kk * n + k0, n, kv,
+                                           n - kk, Asm, Bsm);
+        }
+        __syncthreads();
+        bqo_acc_foreach(acc, [&](int r, int c, double& v) {
+            double b = (r < rv && c < kv) ? Bs_[(int64_t)r * n + k0 + c] : 0.0;
+            Ts[r * LDT + c] = b - v;
+        });
+        for (int e = t; e < NB * NB; e += blockDim.x) {
+            int r = e / NB, c = e % NB;
+            double v = 0.0;
+            if (r < kv && c <= r) v = Lm[(int64_t)(k0 + r) * n + (k0 + c)];
+            if (r >= kv && c == r) v = 1.0;
+            Ls[r * LDT + c] = v;
+        }
+        __syncthreads();
+        if (t < rv) {
+            double* x = Ts + t * LDT;
+            if (FORWARD) {
+                for (int j = 0; j < kv; ++j) {
+                    double a0 = x[j], a1 = 0.0;
+                    int k = 0;
+                    for (; k + 1 < j; k += 2) {
+                        a0 = fma(-x[k], Ls[j * LDT + k], a0);
+                        a1 = fma(-x[k + 1], Ls[j * LDT + k + 1], a1);
+                    }
+                    if (k < j) a0 = fma(-x[k], Ls[j * LDT + k], a0);
+                    x[j] = (a0 + a1) / Ls[j * LDT + j];
+                }
+            } else {
+                for (int j = kv - 1; j >= 0; --j) {
+                    double a0 = x[j], a1 = 0.0;
+                    int k = j + 1;
+                    for (; k + 1 < kv; k += 2) {
+                        a0 = fma(-x[k], Ls[k * LDT + j], a0);
+                        a1 = fma(-x[k + 1], Ls[(k + 1) * LDT + j], a1);
+                    }
+                    if (k < kv) a0 = fma(-x[k], Ls[k * LDT + j], a0);
+                    x[j] = (a0 + a1) / Ls[j * LDT + j];
+                }
+            }
+        }
+        __syncthreads();
+        for (int e = t; e < NB * NB; e += blockDim.x) {
+            int r = e / NB, c = e % NB;
+            if (r < rv && c < kv) Bs_[(int64_t)r * n + k0 + c] = Ts[r * LDT + c];
+        }
+        __syncthreads();
+    }
+}
+
+static int potrs_launch(const double* L, int n, int S, double* Bt, int m, int identity_rhs,
+                        cudaStream_t cs) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(trsm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)SMEM_TRSM);
+        cudaFuncSetAttribute(trsm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)SMEM_TRSM);
+        attr_done = true;
+    }
+    dim3 grid((m + NB - 1) / NB, S);
+    trsm_kernel<true><<<grid, 128, SMEM_TRSM, cs>>>(L, n, Bt, m, identity_rhs);
+    trsm_kernel<false><<<grid, 128, SMEM_TRSM, cs>>>(L, n, Bt, m, 0);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int bqo_potrs_batched(const double* L, int32_t n, int32_t S, double* Bt, int32_t m,
+                                 void* stream) {
+    BQO_CHECK_ARG(L != nullptr, 1);
+    BQO_CHECK_ARG(n > 0, 2);
+    BQO_CHECK_ARG(S > 0 && S <= 65535, 3);
+    BQO_CHECK_ARG(Bt != nullptr, 4);
+    BQO_CHECK_ARG(m > 0, 5);
+    return potrs_launch(L, n, S, Bt, m, 0, (cudaStream_t)stream);
+}
+
+// Internal: Sigma^{-1} via potrs on the identity (used by the log-likelihood gradient).
+int bqo_internal_inverse_from_chol(const double* L, int n, int S, double* Inv, cudaStream_t cs);
+
+__global__ void set_identity_kernel(double* __restrict__ A, int n) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = blockIdx.y;
+    int s = blockIdx.z;
+    if (j < n) A[((int64_t)s * n + i) * n + j] = (i == j) ? 1.0 : 0.0;
+}
+
+int bqo_internal_inverse_from_chol(const double* L, int n, int S, double* Inv, cudaStream_t cs) {
+    dim3 zg((n + 255) / 256, n, S);
+    set_identity_kernel<<<zg, 256, 0, cs>>>(Inv, n);
+    return potrs_launch(L, n, S, Inv, n, 1, cs);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sigma assembly + Cholesky with the reference's jitter policy (sbo/lib/la_functions.py:8-38).
+__global__ void diag_stats_kernel(const double* __restrict__ A, int n, double* __restrict__ mean,
+                                  int* __restrict__ nonpos) {
+    __shared__ double red[32];
+    __shared__ int anyflag;
+    int s = blockIdx.x;
+    if (threadIdx.x == 0) anyflag = 0;
+    __syncthreads();
+    double acc = 0.0;
+    int bad = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double d = A[((int64_t)s * n + i) * n + i];
+        acc += d;
+        if (d <= 0.0) bad = 1;
+    }
+    if (bad) atomicOr(&anyflag, 1);
+    double tot = bqo_block_sum(acc, red);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mean[s] = tot / (double)n;
+        nonpos[s] = anyflag;
+    }
+}
+
+extern "C" int bqo_chol_cov_batched(const bqo_kernel_desc* desc, const double* hyp, int32_t S,
+                                    const double* Xs, const int32_t* tid, int32_t n,
+                                    const double* noise_obs, int32_t max_tries, double* L,
+                                    int32_t* info_host, double* jitter_used_host, void* stream) {
+    BQO_CHECK_ARG(desc != nullptr, 1);
+    BQO_CHECK_ARG(S > 0 && S <= 65535, 3);
+    BQO_CHECK_ARG(L != nullptr, 9);
+    BQO_CHECK_ARG(info_host != nullptr, 10);
+    cudaStream_t cs = (cudaStream_t)stream;
+    int rc = bqo_kernel_assemble_batched(desc, hyp, S, Xs, tid, n, noise_obs, 1, nullptr, L, stream);
+    if (rc) return rc;
+    int* info_d = nullptr;
+    double* mean_d = nullptr;
+    int* nonpos_d = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&info_d, sizeof(int) * S * 2 + sizeof(double) * S * 2, cs);
+    if (e != cudaSuccess) return (int)e;
+    nonpos_d = info_d + S;
+    mean_d = (double*)(info_d + 2 * S);
+    double* extra_d = mean_d + S;
+    // diagonal statistics of Sigma are needed only on failure, but they must be taken before the
+    // in-place factorisation destroys the diagonal.
+    diag_stats_kernel<<<S, 256, 0, cs>>>(L, n, mean_d, nonpos_d);
+    rc = potrf_launch(L, n, S, info_d, cs);
+    std::vector<int> info(S), nonpos(S);
+    std::vector<double> mean(S), jit(S, 0.0), extra(S, 0.0);
+    cudaMemcpyAsync(info.data(), info_d, sizeof(int) * S, cudaMemcpyDeviceToHost, cs);
+    cudaMemcpyAsync(nonpos.data(), nonpos_d, sizeof(int) * S, cudaMemcpyDeviceToHost, cs);
+    cudaMemcpyAsync(mean.data(), mean_d, sizeof(double) * S, cudaMemcpyDeviceToHost, cs);
+    cudaStreamSynchronize(cs);
+    for (int s = 0; s < S; ++s) {
+        info_host[s] = 0;
+        if (info[s] == 0) continue;
+        if (nonpos[s]) {  // "not positive definite matrix"
+            info_host[s] = -1;
+            continue;
+        }
+        double jitter = mean[s] * 1e-6;
+        int n_tries = 1;
+        bool ok = false;
+        // per failed matrix: re-assemble Sigma_s + jitter I into its slot and re-factor it
+        bqo_kernel_desc d1 = *desc;
+        int64_t st = bqo_hyper_stride_impl(d1);
+        while (n_tries <= max_tries && isfinite(jitter)) {
+            cudaMemcpyAsync(extra_d, &jitter, sizeof(double), cudaMemcpyHostToDevice, cs);
+            bqo_kernel_assemble_batched(desc, hyp + (int64_t)s * st, 1,
+                                        Xs + (int64_t)s * desc->dim_m * n, tid, n, noise_obs, 1,
+                                        extra_d, L + (int64_t)s * n * n, stream);
+            potrf_launch(L + (int64_t)s * n * n, n, 1, info_d, cs);
+            int one = 0;
+            cudaMemcpyAsync(&one, info_d, sizeof(int), cudaMemcpyDeviceToHost, cs);
+            cudaStreamSynchronize(cs);
+            if (one == 0) {
+                ok = true;
+                break;
+            }
+            jitter *= 10.0;
+            ++n_tries;
+        }
+        if (ok) jit[s] = jitter;
+        else info_host[s] = -2;
+    }
+    if (jitter_used_host)
+        for (int s = 0; s < S; ++s) jitter_used_host[s] = jit[s];
+    cudaFreeAsync(info_d, cs);
+    e = cudaGetLastError();
+    return rc ? rc : (int)e;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void residual_kernel(const double* __restrict__ hyp, int64_t stride,
+                                const double* __restrict__ y, int n, double* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int s = blockIdx.y;
+    if (i < n) out[(int64_t)s * n + i] = y[i] - hyp[(int64_t)s * stride + BQO_H_MEAN];
+}
+
+extern "C" int bqo_alpha_batched(const double* hyp, int64_t hyp_stride, const double* L, int32_t n,
+                                 int32_t S, const double* y, double* alpha, void* stream) {
+    BQO_CHECK_ARG(hyp != nullptr, 1);
+    BQO_CHECK_ARG(L != nullptr, 3);
+    BQO_CHECK_ARG(n > 0, 4);
+    BQO_CHECK_ARG(S > 0 && S <= 65535, 5);
+    BQO_CHECK_ARG(y != nullptr, 6);
+    BQO_CHECK_ARG(alpha != nullptr, 7);
+    cudaStream_t cs = (cudaStream_t)stream;
+    dim3 grid((n + 255) / 256, S);
+    residual_kernel<<<grid, 256, 0, cs>>>(hyp, hyp_stride, y, n, alpha);
+    // alpha is [S][1][n]: one right-hand side per matrix
+    return potrs_launch(L, n, S, alpha, 1, 0, cs);
+}
+
+__global__ void loglik_kernel(const double* __restrict__ hyp, int64_t stride,
+                              const double* __restrict__ L, const double* __restrict__ alpha,
+                              const double* __restrict__ y, int n, double* __restrict__ llh) {
+    __shared__ double red[32];
+    int s = blockIdx.x;
+    double mean = hyp[(int64_t)s * stride + BQO_H_MEAN];
+    double sl = 0.0, sq = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        sl += log(L[((int64_t)s * n + i) * n + i]);
+        sq = fma(y[i] - mean, alpha[(int64_t)s * n + i], sq);
+    }
+    double a = bqo_block_sum(sl, red);
+    double b = bqo_block_sum(sq, red);
+    if (threadIdx.x == 0) llh[s] = -a - 0.5 * b;
+}
+
+extern "C" int bqo_loglik_batched(const double* hyp, int64_t hyp_stride, const double* L,
+                                  const double* alpha, const double* y, int32_t n, int32_t S,
+                                  double* llh, void* stream) {
+    BQO_CHECK_ARG(hyp != nullptr, 1);
+    BQO_CHECK_ARG(L != nullptr, 3);
+    BQO_CHECK_ARG(alpha != nullptr, 4);
+    BQO_CHECK_ARG(y != nullptr, 5);
+    BQO_CHECK_ARG(n > 0, 6);
+    BQO_CHECK_ARG(S > 0, 7);
+    BQO_CHECK_ARG(llh != nullptr, 8);
+    loglik_kernel<<<S, 256, 0, (cudaStream_t)stream>>>(hyp, hyp_stride, L, alpha, y, n, llh);
+    BQO_RETURN_LAST_ERROR();
+}

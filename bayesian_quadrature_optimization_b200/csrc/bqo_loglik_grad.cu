@@ -1,0 +1,188 @@
+// Gradient of the log marginal likelihood for S hyper-samples at once.
+//
+// Reference: grad_log_likelihood_dict + GradientGPFittingGaussian
+// (sbo/models/gp_fitting_gaussian.py:832-897, 1654-1697):
+//     d llh / d theta_j = 0.5 trace(alpha alpha^T dK_j - Sigma^-1 dK_j)
+// which the reference evaluates with one n x n dpotrs and one n x n x n product PER parameter.
+// Here Sigma^-1 is formed once per hyper-sample (potrs on the identity) and every parameter
+// derivative is the Frobenius product <alpha alpha^T - Sigma^-1, dK_j>, with dK_j generated on the
+// fly in registers from the same pairwise distance (never stored).  Partial sums are written
+// per CTA and added in a fixed order, so the result is bit-reproducible.
+#include "bqo_common.cuh"
+
+int bqo_internal_inverse_from_chol(const double* L, int n, int S, double* Inv, cudaStream_t cs);
+
+#define LG_MAX_ACC (BQO_MAX_DIM + 4)
+// accumulator slots: [0..dim_m) length scales, then
+#define LG_SLOT_KM(dm) (dm)        // sum M_ij k_M(i,j) other-free  (sigma2 derivative)
+#define LG_SLOT_SAME(dm) ((dm) + 1) // sum over pairs with equal tasks of M_ij k_M
+#define LG_SLOT_DIFF(dm) ((dm) + 2) // sum over pairs with different tasks of M_ij k_M
+#define LG_SLOT_TRACE(dm) ((dm) + 3) // sum_i M_ii
+
+__global__ void __launch_bounds__(256)
+    loglik_grad_partial_kernel(bqo_kernel_desc d, const double* __restrict__ hyp, int64_t stride,
+                               const double* __restrict__ Xs, const int32_t* __restrict__ tid,
+                               int n, const double* __restrict__ Inv,
+                               const double* __restrict__ alpha, double* __restrict__ partial,
+                               double* __restrict__ Wtask) {
+    __shared__ double red[32];
+    const int s = blockIdx.z;
+    const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int i0 = blockIdx.y * 32 + (threadIdx.x >> 5) * 4;
+    const double* h = hyp + (int64_t)s * stride;
+    const double* xs = Xs + (int64_t)s * d.dim_m * n;
+    const double* inv = Inv + (int64_t)s * n * n;
+    const double* al = alpha + (int64_t)s * n;
+    const int dm = d.dim_m;
+    const int nacc = dm + 4;
+    double acc[LG_MAX_ACC];
+    for (int q = 0; q < nacc; ++q) acc[q] = 0.0;
+    const bool general_tasks = (d.kind == BQO_KIND_PRODUCT_TASKS) && !d.same_corr;
+    if (j < n) {
+        double xj[BQO_MAX_DIM];
+        for (int l = 0; l < dm; ++l) xj[l] = xs[(int64_t)l * n + j];
+        const double aj = al[j];
+        const int tj = (d.kind == BQO_KIND_PRODUCT_TASKS) ? tid[j] : 0;
+        for (int ii = 0; ii < 4; ++ii) {
+            const int i = i0 + ii;
+            if (i >= n) break;
+            const double Mij = al[i] * aj - inv[(int64_t)i * n + j];
+            double df[BQO_MAX_DIM];
+            double r2 = 0.0;
+            for (int l = 0; l < dm; ++l) {
+                df[l] = xs[(int64_t)l * n + i] - xj[l];
+                r2 = fma(df[l], df[l], r2);
+            }
+            double km, g;
+            bqo_matern52_kg(r2, km, g);
+            double other = 1.0;
+            int ti = 0;
+            if (d.kind == BQO_KIND_SCALED_MATERN52) other = h[BQO_H_SIGMA2];
+            if (d.kind == BQO_KIND_PRODUCT_TASKS) {
+                ti = tid[i];
+                other = bqo_task_cov(h, d.n_tasks, ti, tj);
+            }
+            if (i != j) {
+                const double w = -Mij * g * other;
+                for (int l = 0; l < dm; ++l)
+                    acc[l] = fma(w * df[l] * df[l], h[BQO_H_INVLS + l], acc[l]);
+            } else {
+                acc[LG_SLOT_TRACE(dm)] += Mij;
+            }
+            const double mk = Mij * km;
+            acc[LG_SLOT_KM(dm)] += mk;
+            if (d.kind == BQO_KIND_PRODUCT_TASKS) {
+                if (general_tasks) atomicAdd(Wtask + ((int64_t)s * d.n_tasks + ti) * d.n_tasks + tj, mk);
+                else if (ti == tj) acc[LG_SLOT_SAME(dm)] += mk;
+                else acc[LG_SLOT_DIFF(dm)] += mk;
+            }
+        }
+    }
+    const int nblk = gridDim.x * gridDim.y;
+    const int blk = blockIdx.y * gridDim.x + blockIdx.x;
+    for (int q = 0; q < nacc; ++q) {
+        double tot = bqo_block_sum(acc[q], red);
+        if (threadIdx.x == 0) partial[((int64_t)s * nacc + q) * nblk + blk] = tot;
+    }
+}
+
+__global__ void loglik_grad_final_kernel(bqo_kernel_desc d, const double* __restrict__ hyp,
+                                         int64_t stride, const double* __restrict__ partial,
+                                         int nblk, const double* __restrict__ alpha, int n,
+                                         const double* __restrict__ Wtask,
+                                         double* __restrict__ grad) {
+    __shared__ double red[32];
+    __shared__ double tot[LG_MAX_ACC];
+    const int s = blockIdx.x;
+    const int dm = d.dim_m;
+    const int nacc = dm + 4;
+    const double* h = hyp + (int64_t)s * stride;
+    for (int q = 0; q < nacc; ++q) {
+        // fixed-order tree: each thread a strided serial sum, then the block tree
+        double a = 0.0;
+        for (int b = threadIdx.x; b < nblk; b += blockDim.x)
+            a += partial[((int64_t)s * nacc + q) * nblk + b];
+        a = bqo_block_sum(a, red);
+        if (threadIdx.x == 0) tot[q] = a;
+    }
+    double sa = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sa += alpha[(int64_t)s * n + i];
+    sa = bqo_block_sum(sa, red);
+    __syncthreads();
+    double* g = grad + (int64_t)s * (2 + d.n_params);
+    if (threadIdx.x == 0) {
+        g[0] = 0.5 * tot[LG_SLOT_TRACE(dm)];  // dK = I
+        g[1] = sa;                            // 1^T Sigma^-1 (y - mean)
+        for (int l = 0; l < dm; ++l) g[2 + l] = 0.5 * tot[l];
+        if (d.kind == BQO_KIND_SCALED_MATERN52) g[2 + dm] = 0.5 * tot[LG_SLOT_KM(dm)];
+        if (d.kind == BQO_KIND_PRODUCT_TASKS && d.same_corr) {
+            const int T = d.n_tasks;
+            const double* C = h + BQO_H_TASKC;
+            if (T == 1) {
+                g[2 + dm] = 0.5 * C[0] * tot[LG_SLOT_SAME(dm)];
+            } else {
+                double value = C[1];
+                g[2 + dm] = 0.5 * (C[0] - value * (double)(T - 1)) * tot[LG_SLOT_SAME(dm)];
+                g[2 + dm + 1] = 0.5 * (value * (double)(T - 1) * tot[LG_SLOT_SAME(dm)] +
+                                       value * tot[LG_SLOT_DIFF(dm)]);
+            }
+        }
+    }
+    if (d.kind == BQO_KIND_PRODUCT_TASKS && !d.same_corr) {
+        // grad_m = 0.5 sum_{u,v} dC_m[u][v] W[u][v],  dC_m = E + E^T, E[a][v] = L[a][b] L[v][b]
+        const int T = d.n_tasks;
+        const double* Lt = h + BQO_H_TASKC + T * T;
+        const double* W = Wtask + (int64_t)s * T * T;
+        const int pt = d.n_params - dm;
+        for (int m = threadIdx.x; m < pt; m += blockDim.x) {
+            int a = (int)floor((sqrt(8.0 * (double)m + 1.0) - 1.0) * 0.5);
+            while ((a + 1) * (a + 2) / 2 <= m) ++a;
+            while (a * (a + 1) / 2 > m) --a;
+            int b = m - a * (a + 1) / 2;
+            double lab = Lt[a * T + b];
+            double accm = 0.0;
+            for (int v = 0; v < T; ++v) accm += lab * Lt[v * T + b] * (W[a * T + v] + W[v * T + a]);
+            g[2 + dm + m] = 0.5 * accm;
+        }
+    }
+}
+
+extern "C" int64_t bqo_loglik_grad_workspace_bytes(int32_t n, int32_t S) {
+    int64_t nblk = (int64_t)((n + 31) / 32) * ((n + 31) / 32);
+    int64_t d = (int64_t)S * n * n + (int64_t)S * LG_MAX_ACC * nblk + (int64_t)S * 128 * 128;
+    return d * (int64_t)sizeof(double);
+}
+
+extern "C" int bqo_loglik_grad_batched(const bqo_kernel_desc* desc, const double* hyp, int32_t S,
+                                       const double* Xs, const int32_t* tid, int32_t n,
+                                       const double* L, const double* alpha, const double* y,
+                                       double* grad, void* workspace, void* stream) {
+    BQO_CHECK_ARG(desc != nullptr, 1);
+    BQO_CHECK_ARG(hyp != nullptr, 2);
+    BQO_CHECK_ARG(S > 0 && S <= 65535, 3);
+    BQO_CHECK_ARG(Xs != nullptr, 4);
+    BQO_CHECK_ARG(n > 0, 6);
+    BQO_CHECK_ARG(L != nullptr, 7);
+    BQO_CHECK_ARG(alpha != nullptr, 8);
+    BQO_CHECK_ARG(grad != nullptr, 10);
+    BQO_CHECK_ARG(workspace != nullptr, 11);
+    BQO_CHECK_ARG(desc->n_tasks <= 128, 1);
+    (void)y;
+    cudaStream_t cs = (cudaStream_t)stream;
+    const int nb = (n + 31) / 32;
+    const int64_t nblk = (int64_t)nb * nb;
+    double* Inv = (double*)workspace;
+    double* partial = Inv + (int64_t)S * n * n;
+    double* Wtask = partial + (int64_t)S * LG_MAX_ACC * nblk;
+    int rc = bqo_internal_inverse_from_chol(L, n, S, Inv, cs);
+    if (rc) return rc;
+    if (desc->kind == BQO_KIND_PRODUCT_TASKS && !desc->same_corr)
+        cudaMemsetAsync(Wtask, 0, sizeof(double) * S * desc->n_tasks * desc->n_tasks, cs);
+    dim3 grid(nb, nb, S);
+    const int64_t st = bqo_hyper_stride_impl(*desc);
+    loglik_grad_partial_kernel<<<grid, 256, 0, cs>>>(*desc, hyp, st, Xs, tid, n, Inv, alpha, partial,
+                                                     Wtask);
+    loglik_grad_final_kernel<<<S, 256, 0, cs>>>(*desc, hyp, st, partial, (int)nblk, alpha, n, Wtask,
+                                                grad);
+    BQO_RETURN_LAST_ERROR();
+}
