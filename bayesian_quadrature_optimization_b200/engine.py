@@ -1,0 +1,395 @@
+"""Device engine: owns the HBM-resident state of one GP model and drives libbqo_sm100.so.
+
+PyTorch is used for buffer ownership, pinned host<->device copies and the CUDA stream only;
+every numerical step is a call into the C ABI (include/bqo_sm100.h).  There is no CPU path:
+constructing an engine without CUDA raises.
+
+Layout in HBM (all FP64, row-major):
+    X      [n][dim]           raw training inputs (x columns, then w / task column)
+    y      [n]                evaluations
+    theta  [S][2+p]           hyper-samples (var_noise, mean, kernel parameters)
+    hyp    [S][stride]        prepared hyper blocks (ls, 1/ls, sigma2, task covariance tables)
+    Xs     [S][dim_m][n]      X / ls per hyper-sample, structure of arrays
+    L      [S][n][n]          Cholesky factors of Sigma_s (lower, strict upper zeroed)
+    alpha  [S][n]             Sigma_s^-1 (y - mean_s)
+    per candidate batch: G, R [S][C*(1+dim_m)][n]  (gamma | grad gamma rows, unsolved / solved)
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import KernelDesc, StageC, InnerOpt, check, ptr
+
+F64 = torch.float64
+I32 = torch.int32
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def kernel_desc(kind: int, dim: int, n_tasks: int = 0, same_correlation: bool = False) -> KernelDesc:
+    dim_m = dim - 1 if kind == _cabi.KIND_PRODUCT_TASKS else dim
+    if kind == _cabi.KIND_MATERN52:
+        n_params = dim
+    elif kind == _cabi.KIND_SCALED_MATERN52:
+        n_params = dim + 1
+    else:
+        nt = min(n_tasks, 2) if same_correlation else n_tasks * (n_tasks + 1) // 2
+        n_params = dim_m + nt
+    return KernelDesc(kind, dim, dim_m, n_tasks, int(bool(same_correlation)), n_params)
+
+
+class GPEngine(object):
+    """Training data of one GP on one GPU."""
+
+    def __init__(self, kind, dim, n_tasks=0, same_correlation=False, device=None):
+        if not torch.cuda.is_available():
+            raise _cabi.BqoLibraryError(
+                "CUDA device required: bayesian_quadrature_optimization_b200 has no CPU path")
+        self.lib = _cabi.load()
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        torch.cuda.set_device(self.device)
+        check(self.lib.bqo_set_device(self.device.index or 0), "bqo_set_device")
+        self.desc = kernel_desc(kind, dim, n_tasks, same_correlation)
+        self.hyp_stride = int(self.lib.bqo_hyper_stride(C.byref(self.desc)))
+        self.n = 0
+        self.X = self.y = self.noise_obs = None
+
+    # -- data ---------------------------------------------------------------------------------
+    def to_device(self, a, dtype=F64):
+        if isinstance(a, torch.Tensor):
+            return a.to(device=self.device, dtype=dtype).contiguous()
+        arr = np.ascontiguousarray(np.asarray(a, dtype=np.float64 if dtype == F64 else np.int32))
+        return torch.from_numpy(arr).to(self.device, non_blocking=False)
+
+    def set_data(self, points, evaluations, var_noise_obs=None):
+        self.X = self.to_device(points).reshape(-1, self.desc.dim)
+        self.y = self.to_device(evaluations).reshape(-1)
+        self.n = int(self.X.shape[0])
+        self.noise_obs = None if var_noise_obs is None else self.to_device(var_noise_obs).reshape(-1)
+
+    def empty(self, *shape, dtype=F64):
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    def hypers(self, thetas) -> "HyperBatch":
+        return HyperBatch(self, thetas)
+
+
+class HyperBatch(object):
+    """S hyper-samples resident on the device with their prepared blocks and factors."""
+
+    def __init__(self, eng: GPEngine, thetas):
+        self.eng = eng
+        lib, d = eng.lib, eng.desc
+        self.theta = eng.to_device(thetas).reshape(-1, 2 + d.n_params)
+        self.S = int(self.theta.shape[0])
+        self.hyp = eng.empty(self.S, eng.hyp_stride)
+        check(lib.bqo_hyper_prepare(C.byref(d), ptr(self.theta), self.S, ptr(self.hyp), _stream()),
+              "bqo_hyper_prepare")
+        self.Xs = eng.empty(self.S, d.dim_m, eng.n)
+        self.tid = eng.empty(eng.n, dtype=I32) if d.kind == _cabi.KIND_PRODUCT_TASKS else None
+        check(lib.bqo_scale_points(C.byref(d), ptr(self.hyp), self.S, ptr(eng.X), eng.n, d.dim,
+                                   ptr(self.Xs), ptr(self.tid), _stream()), "bqo_scale_points")
+        self.L = None
+        self.alpha = None
+        self.info = None
+        self.jitter = None
+
+    # -- kernel matrices ------------------------------------------------------------------------
+    def cov(self, add_noise=False):
+        eng = self.eng
+        K = eng.empty(self.S, eng.n, eng.n)
+        check(eng.lib.bqo_kernel_assemble_batched(
+            C.byref(eng.desc), ptr(self.hyp), self.S, ptr(self.Xs), ptr(self.tid), eng.n,
+            ptr(eng.noise_obs) if add_noise else None, int(add_noise), None, ptr(K), _stream()),
+            "bqo_kernel_assemble_batched")
+        return K
+
+    def grad_cov(self):
+        eng = self.eng
+        dK = eng.empty(self.S, eng.desc.n_params, eng.n, eng.n)
+        check(eng.lib.bqo_kernel_grad_params_batched(
+            C.byref(eng.desc), ptr(self.hyp), self.S, ptr(self.Xs), ptr(self.tid), eng.n, ptr(dK),
+            _stream()), "bqo_kernel_grad_params_batched")
+        return dK
+
+    def cross_cov(self, P, grad=False):
+        """k(P, X) [S][m][n] (and d/dP [S][m][dim_m][n])."""
+        eng = self.eng
+        P = eng.to_device(P).reshape(-1, eng.desc.dim)
+        m = int(P.shape[0])
+        KP = eng.empty(self.S, m, eng.n)
+        dKP = eng.empty(self.S, m, eng.desc.dim_m, eng.n) if grad else None
+        check(eng.lib.bqo_cross_cov_batched(
+            C.byref(eng.desc), ptr(self.hyp), self.S, ptr(self.Xs), ptr(self.tid), eng.n, ptr(P), m,
+            0, ptr(KP), ptr(dKP), _stream()), "bqo_cross_cov_batched")
+        return (KP, dKP) if grad else KP
+
+    # -- factorisation ----------------------------------------------------------------------------
+    def factorize(self, max_tries=7):
+        """Sigma_s = K_s + noise; L_s with the reference's jitter policy; alpha_s."""
+        if self.L is not None:
+            return self
+        eng = self.eng
+        self.L = eng.empty(self.S, eng.n, eng.n)
+        info = (C.c_int32 * self.S)()
+        jit = (C.c_double * self.S)()
+        check(eng.lib.bqo_chol_cov_batched(
+            C.byref(eng.desc), ptr(self.hyp), self.S, ptr(self.Xs), ptr(self.tid), eng.n,
+            ptr(eng.noise_obs), int(max_tries), ptr(self.L), info, jit, _stream()),
+            "bqo_chol_cov_batched")
+        self.info = np.array(list(info), dtype=np.int32)
+        self.jitter = np.array(list(jit), dtype=np.float64)
+        self.alpha = eng.empty(self.S, eng.n)
+        check(eng.lib.bqo_alpha_batched(ptr(self.hyp), eng.hyp_stride, ptr(self.L), eng.n, self.S,
+                                        ptr(eng.y), ptr(self.alpha), _stream()), "bqo_alpha_batched")
+        return self
+
+    def solve(self, Bt):
+        """Sigma_s^-1 applied to Bt[S][m][n] in place."""
+        eng = self.eng
+        self.factorize()
+        m = int(Bt.shape[1])
+        check(eng.lib.bqo_potrs_batched(ptr(self.L), eng.n, self.S, ptr(Bt), m, _stream()),
+              "bqo_potrs_batched")
+        return Bt
+
+    def log_likelihood(self):
+        eng = self.eng
+        self.factorize()
+        llh = eng.empty(self.S)
+        check(eng.lib.bqo_loglik_batched(ptr(self.hyp), eng.hyp_stride, ptr(self.L), ptr(self.alpha),
+                                         ptr(eng.y), eng.n, self.S, ptr(llh), _stream()),
+              "bqo_loglik_batched")
+        return llh
+
+    def grad_log_likelihood(self):
+        eng = self.eng
+        self.factorize()
+        nbytes = int(eng.lib.bqo_loglik_grad_workspace_bytes(eng.n, self.S))
+        work = torch.empty(nbytes // 8 + 1, dtype=F64, device=eng.device)
+        grad = eng.empty(self.S, 2 + eng.desc.n_params)
+        check(eng.lib.bqo_loglik_grad_batched(
+            C.byref(eng.desc), ptr(self.hyp), self.S, ptr(self.Xs), ptr(self.tid), eng.n,
+            ptr(self.L), ptr(self.alpha), ptr(eng.y), ptr(grad), ptr(work), _stream()),
+            "bqo_loglik_grad_batched")
+        return grad
+
+    # -- posterior / EI ------------------------------------------------------------------------------
+    def posterior(self, P, var=True, grad=False):
+        eng = self.eng
+        self.factorize()
+        d = eng.desc
+        P = eng.to_device(P).reshape(-1, d.dim)
+        m = int(P.shape[0])
+        mean = eng.empty(self.S, m)
+        v = eng.empty(self.S, m) if var else None
+        gm = eng.empty(self.S, m, d.dim_m) if grad else None
+        gv = eng.empty(self.S, m, d.dim_m) if (grad and var) else None
+        work = eng.empty(self.S * m * (2 + d.dim_m) * eng.n)
+        check(eng.lib.bqo_posterior_batched(
+            C.byref(d), ptr(self.hyp), self.S, ptr(self.Xs), ptr(self.tid), eng.n, ptr(self.L),
+            ptr(self.alpha), ptr(P), m, ptr(mean), ptr(v), ptr(gm), ptr(gv), ptr(work), _stream()),
+            "bqo_posterior_batched")
+        return {"mean": mean, "var": v, "grad_mean": gm, "grad_var": gv}
+
+    def ei(self, P, best, grad=False):
+        eng = self.eng
+        post = self.posterior(P, var=True, grad=grad)
+        best = eng.to_device(best).reshape(-1)
+        m = int(post["mean"].shape[1])
+        ei = eng.empty(self.S, m)
+        gei = eng.empty(self.S, m, eng.desc.dim_m) if grad else None
+        check(eng.lib.bqo_ei_batched(ptr(post["mean"]), ptr(post["var"]), ptr(post["grad_mean"]),
+                                     ptr(post["grad_var"]), ptr(best), self.S, m, eng.desc.dim_m,
+                                     ptr(ei), ptr(gei), _stream()), "bqo_ei_batched")
+        return ei, gei
+
+
+class UnitBatch(object):
+    """(candidate, hyper-sample) units of one candidate batch, ordered u = c * S + k."""
+
+    def __init__(self):
+        self.cand = self.G = self.R = self.den = self.beta4 = None
+        self.unit_k = self.unit_c = None
+        self.C = 0
+
+
+class BQEngine(object):
+    """Bayesian-quadrature stage B/C on top of a factorised HyperBatch."""
+
+    def __init__(self, hb: HyperBatch, dx: int, weights=None, wsets=None, lower=None, upper=None,
+                 bq_var_noise=None):
+        self.hb = hb.factorize()
+        self.eng = eng = hb.eng
+        d = eng.desc
+        self.dx = int(dx)
+        self.dw = d.dim_m - self.dx
+        self.is_product = d.kind == _cabi.KIND_PRODUCT_TASKS
+        if self.is_product and self.dw != 0:
+            raise ValueError("finite-W models integrate the task column only")
+        self.qt = None
+        if self.is_product:
+            self.weights = None if weights is None else eng.to_device(weights).reshape(-1)
+            self.qt = eng.empty(hb.S, d.n_tasks)
+            check(eng.lib.bqo_task_quadrature_weights(C.byref(d), ptr(hb.hyp), hb.S,
+                                                      ptr(self.weights), ptr(self.qt), _stream()),
+                  "bqo_task_quadrature_weights")
+        self.alpha_q = eng.empty(hb.S, eng.n)
+        check(eng.lib.bqo_weight_alpha(C.byref(d), ptr(hb.alpha), ptr(self.qt), ptr(hb.tid), hb.S,
+                                       eng.n, ptr(self.alpha_q), _stream()), "bqo_weight_alpha")
+        if self.dw > 0:
+            if wsets is None:
+                raise ValueError("Monte-Carlo W models need pre-drawn W sample sets")
+            ws = eng.to_device(wsets)
+            if ws.dim() == 2:
+                ws = ws.unsqueeze(0)
+            if ws.dim() != 3 or int(ws.shape[2]) != self.dw:
+                raise ValueError("wsets must be [n_wsets][M][d_w]")
+            self.wsets = ws.contiguous()
+            self.n_wsets, self.M = int(ws.shape[0]), int(ws.shape[1])
+        else:
+            self.wsets, self.n_wsets, self.M = None, 0, 1
+        self.lower = None if lower is None else eng.to_device(lower).reshape(-1)
+        self.upper = None if upper is None else eng.to_device(upper).reshape(-1)
+        # noise term of the denominator: mean observed noise if any, else var_noise_s
+        if bq_var_noise is not None:
+            self.add_noise = torch.full((hb.S,), float(bq_var_noise), dtype=F64, device=eng.device)
+        else:
+            self.add_noise = hb.theta[:, 0].contiguous()
+
+    # -- stage B ---------------------------------------------------------------------------------------
+    def setup(self, cands) -> UnitBatch:
+        eng, hb, d = self.eng, self.hb, self.eng.desc
+        ub = UnitBatch()
+        ub.cand = eng.to_device(cands).reshape(-1, d.dim)
+        Cn = ub.C = int(ub.cand.shape[0])
+        rows = 1 + d.dim_m
+        ub.G = eng.empty(hb.S, Cn * rows, eng.n)
+        check(eng.lib.bqo_cross_cov_batched(
+            C.byref(d), ptr(hb.hyp), hb.S, ptr(hb.Xs), ptr(hb.tid), eng.n, ptr(ub.cand), Cn, 1,
+            ptr(ub.G), None, _stream()), "bqo_cross_cov_batched")
+        ub.R = ub.G.clone()
+        check(eng.lib.bqo_potrs_batched(ptr(hb.L), eng.n, hb.S, ptr(ub.R), Cn * rows, _stream()),
+              "bqo_potrs_batched")
+        ub.den = eng.empty(hb.S, Cn)
+        ub.beta4 = eng.empty(hb.S, Cn, d.dim_m)
+        check(eng.lib.bqo_candidate_setup_batched(
+            C.byref(d), ptr(hb.hyp), hb.S, ptr(ub.G), ptr(ub.R), eng.n, Cn, ptr(ub.cand),
+            ptr(self.add_noise), ptr(self.qt), ptr(hb.tid), ptr(ub.den), ptr(ub.beta4), _stream()),
+            "bqo_candidate_setup_batched")
+        u = torch.arange(Cn * hb.S, device=eng.device, dtype=torch.int64)
+        ub.unit_c = (u // hb.S).to(I32).contiguous()
+        ub.unit_k = (u % hb.S).to(I32).contiguous()
+        return ub
+
+    def _stage_c(self, ub: UnitBatch) -> StageC:
+        eng, hb = self.eng, self.hb
+        pb = StageC()
+        pb.desc = eng.desc
+        pb.n, pb.S, pb.dx, pb.dw = eng.n, hb.S, self.dx, self.dw
+        pb.n_units, pb.C = int(ub.unit_k.shape[0]), ub.C
+        pb.M, pb.n_wsets = self.M, self.n_wsets
+        pb.hyp, pb.Xs, pb.tid = ptr(hb.hyp), ptr(hb.Xs), ptr(hb.tid)
+        pb.alpha, pb.qt = ptr(self.alpha_q), ptr(self.qt)
+        pb.R, pb.den, pb.beta4, pb.cand = ptr(ub.R), ptr(ub.den), ptr(ub.beta4), ptr(ub.cand)
+        pb.unit_k, pb.unit_c = ptr(ub.unit_k), ptr(ub.unit_c)
+        pb.wsets, pb.lower, pb.upper = ptr(self.wsets), ptr(self.lower), ptr(self.upper)
+        return pb
+
+    # -- stage C ---------------------------------------------------------------------------------------
+    def sample_ab(self, ub, pts, pt_unit, pt_wset=None):
+        """[P][2+2dx]: a, b, grad a, grad b at P points (unit and W set per point)."""
+        eng = self.eng
+        pts = eng.to_device(pts).reshape(-1, self.dx)
+        P = int(pts.shape[0])
+        pt_unit = eng.to_device(pt_unit, I32).reshape(-1)
+        pt_wset = None if pt_wset is None else eng.to_device(pt_wset, I32).reshape(-1)
+        out = eng.empty(P, 2 + 2 * self.dx)
+        pb = self._stage_c(ub)
+        check(eng.lib.bqo_sample_ab_batched(C.byref(pb), ptr(pts), ptr(pt_unit), ptr(pt_wset), P,
+                                            ptr(out), _stream()), "bqo_sample_ab_batched")
+        return out
+
+    def inner_maximize(self, ub, z, starts, maxiter=10, factr=1e12, pgtol=1e-5, max_ls=20,
+                       use_vertices=True, z_per_cta=None, count_evals=False):
+        eng = self.eng
+        z = eng.to_device(z).reshape(-1)
+        starts = eng.to_device(starts)
+        per_hyper = starts.dim() == 3
+        n_starts = int(starts.shape[-2])
+        n_units = int(ub.unit_k.shape[0])
+        n_z = int(z.shape[0])
+        if z_per_cta is None:
+            z_per_cta = n_z
+        opt = InnerOpt(n_z, n_starts, int(maxiter), int(max_ls), float(factr), float(pgtol),
+                       int(bool(use_vertices)), int(z_per_cta), int(per_hyper))
+        out_max = eng.empty(n_units, n_z)
+        out_arg = eng.empty(n_units, n_z, self.dx)
+        n_evals = torch.zeros(n_units, dtype=torch.int64, device=eng.device) if count_evals else None
+        pb = self._stage_c(ub)
+        check(eng.lib.bqo_inner_maximize_batched(C.byref(pb), C.byref(opt), ptr(z), ptr(starts),
+                                                 ptr(out_max), ptr(out_arg), ptr(n_evals), _stream()),
+              "bqo_inner_maximize_batched")
+        return out_max, out_arg, n_evals
+
+    def grad_vector_b(self, ub, pts, pt_wset=None):
+        """pts [n_units][npts][dx] -> grad_c b [n_units][npts][dim_m], nan flags [n_units]."""
+        eng = self.eng
+        n_units = int(ub.unit_k.shape[0])
+        pts = eng.to_device(pts).reshape(n_units, -1, self.dx)
+        npts = int(pts.shape[1])
+        pt_wset = None if pt_wset is None else eng.to_device(pt_wset, I32).reshape(-1)
+        out = eng.empty(n_units, npts, eng.desc.dim_m)
+        is_nan = torch.zeros(n_units, dtype=I32, device=eng.device)
+        pb = self._stage_c(ub)
+        check(eng.lib.bqo_grad_vector_b_batched(C.byref(pb), ptr(pts), npts, ptr(pt_wset), ptr(out),
+                                                ptr(is_nan), _stream()), "bqo_grad_vector_b_batched")
+        return out, is_nan
+
+    def acq_reduce(self, ub, out_max, gvb, is_nan, z, max_mean=None):
+        eng, hb = self.eng, self.hb
+        z = eng.to_device(z).reshape(-1)
+        n_z = int(z.shape[0])
+        dim_g = eng.desc.dim_m if gvb is not None else 0
+        value = eng.empty(ub.C)
+        grad = eng.empty(ub.C, dim_g) if gvb is not None else None
+        mm = None if max_mean is None else eng.to_device(max_mean).reshape(-1)
+        check(eng.lib.bqo_acq_reduce(ptr(out_max), ptr(gvb), ptr(is_nan), ptr(z), ptr(mm), ub.C,
+                                     hb.S, n_z, dim_g, ptr(value), ptr(grad), _stream()),
+              "bqo_acq_reduce")
+        return value, grad
+
+    def evaluate_candidates(self, cands, z, starts, max_mean=None, compute_gradient=True, **opt):
+        """One pass of the hot path over a batch of candidates: stage B, inner maximisation for
+        every (candidate, hyper-sample, Z), gradient of b at the maximisers, MC reduction."""
+        ub = self.setup(cands)
+        out_max, out_arg, n_evals = self.inner_maximize(ub, z, starts, **opt)
+        gvb = is_nan = None
+        if compute_gradient:
+            gvb, is_nan = self.grad_vector_b(ub, out_arg)
+        value, grad = self.acq_reduce(ub, out_max, gvb, is_nan, z, max_mean)
+        return {"evaluations": value, "gradient": grad, "max": out_max, "optimum": out_arg,
+                "n_evals": n_evals, "units": ub}
+
+
+def kg_discretized(eng: GPEngine, a, b):
+    """KG values and envelope indices for B problems sharing `a` (discretised SBO)."""
+    a = eng.to_device(a).reshape(-1)
+    b = eng.to_device(b).reshape(-1, a.shape[0])
+    m, B = int(a.shape[0]), int(b.shape[0])
+    nbytes = int(eng.lib.bqo_kg_workspace_bytes(m, B))
+    work = torch.empty(nbytes // 8 + 1, dtype=F64, device=eng.device)
+    kg = eng.empty(B)
+    cnt = torch.zeros(B, dtype=I32, device=eng.device)
+    idx = torch.zeros(B, m, dtype=I32, device=eng.device)
+    c_out = torch.zeros(B, m, dtype=F64, device=eng.device)
+    check(eng.lib.bqo_kg_discretized_batched(ptr(a), ptr(b), m, B, ptr(kg), ptr(cnt), ptr(idx),
+                                             ptr(c_out), ptr(work), _stream()),
+          "bqo_kg_discretized_batched")
+    return kg, cnt, idx, c_out

@@ -45,3 +45,16 @@ def oracle_from_golden(g):
     else:
         bq = orc.OracleBQ(gp, list(range(dx)), orc.GAMMA)
     return spec, gp, bq
+
+
+def cond_rtol(g, s, base=1e-9):
+    """Tolerance for quantities that pass through Sigma^-1: two correct factorisations of the
+    same matrix differ by about cond(Sigma) * eps, so the 1e-9 bar applies while
+    cond(Sigma) * eps stays below it (true for every fixture except the reference's own
+    test vector theta = [1, 5, 50, 9.6, -3, -0.1], whose Sigma has cond = 2.3e9)."""
+    th = g["thetas"][s]
+    cov = g["cov"][s].copy()
+    if "var_noise_obs" in g:
+        cov += np.diag(g["var_noise_obs"])
+    cov += th[0] * np.eye(cov.shape[0])
+    return max(base, 8.0 * np.linalg.cond(cov) * np.finfo(float).eps)

@@ -1,0 +1,352 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the fixtures generated from the
+unmodified reference and against the numpy oracle on seeded inputs.
+
+Tolerance: north star = 1e-9 relative in FP64 for posterior mean/variance, log-likelihood and
+acquisition values; each assertion states its own (tighter where the arithmetic allows).
+"""
+import numpy as np
+import pytest
+
+from oracle import bqo_oracle as orc
+from oracle import inner_opt
+from tests.helpers import assert_close, cond_rtol, oracle_from_golden
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["product_uniform", "product_weighted", "scaled_gamma"]
+
+
+def _engine(g):
+    from bayesian_quadrature_optimization_b200 import engine as E
+    eng = E.GPEngine(int(g["kind"]), g["points"].shape[1], int(g["n_tasks"]),
+                     bool(int(g["same_correlation"])))
+    eng.set_data(g["points"], g["evaluations"], g["var_noise_obs"] if "var_noise_obs" in g else None)
+    return eng
+
+
+def _bq(g, hb):
+    from bayesian_quadrature_optimization_b200 import engine as E
+    dx = int(g["dx"])
+    lo = np.zeros(dx)
+    up = np.ones(dx) * (100.0 if g["points"][:, 0].max() > 2 else 1.0)
+    bqv = float(np.mean(g["var_noise_obs"])) if "var_noise_obs" in g else None
+    return E.BQEngine(hb, dx, weights=g["weights"] if "weights" in g else None,
+                      wsets=g["wset"] if "wset" in g else None, lower=lo, upper=up,
+                      bq_var_noise=bqv), lo, up
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_cov_and_param_gradients(golden, name):
+    g = golden(name)
+    eng = _engine(g)
+    hb = eng.hypers(g["thetas"])
+    assert_close(hb.cov().cpu().numpy(), g["cov"], rtol=1e-13, what="cov")
+    assert_close(hb.grad_cov().cpu().numpy(), g["grad_cov"], rtol=1e-10, atol=1e-15, what="grad_cov")
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_cholesky_loglik_and_gradient(golden, name):
+    g = golden(name)
+    eng = _engine(g)
+    hb = eng.hypers(g["thetas"]).factorize()
+    assert np.all(hb.info == 0) and np.all(hb.jitter == 0.0)
+    assert_close(hb.L.cpu().numpy(), g["chol"], rtol=1e-10, atol=1e-14, what="chol")
+    assert_close(hb.log_likelihood().cpu().numpy(), g["llh"], rtol=1e-11, what="llh")
+    assert_close(hb.grad_log_likelihood().cpu().numpy(), g["grad_llh"], rtol=1e-8, atol=1e-9,
+                 what="grad llh")
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_posterior_and_ei(golden, name):
+    g = golden(name)
+    eng = _engine(g)
+    hb = eng.hypers(g["thetas"])
+    post = hb.posterior(g["query"], var=True, grad=True)
+    dm = eng.desc.dim_m
+    assert_close(post["mean"].cpu().numpy(), g["post_mean"], rtol=1e-10, what="post mean")
+    want_var = np.stack([np.diag(c) for c in g["post_cov"]])
+    assert_close(post["var"].cpu().numpy(), want_var, rtol=1e-9, atol=1e-12, what="post var")
+    assert_close(post["grad_mean"].cpu().numpy(), g["grad_post_mean"][:, :, :dm], rtol=1e-9,
+                 atol=1e-13, what="grad mean")
+    assert_close(post["grad_var"].cpu().numpy(), g["grad_post_cov"][:, :, :dm], rtol=1e-8,
+                 atol=1e-12, what="grad var")
+    best = np.full(len(g["thetas"]), np.max(g["evaluations"]))
+    ei, gei = hb.ei(g["query"], best, grad=True)
+    assert_close(ei.cpu().numpy(), g["ei"], rtol=1e-8, atol=1e-300, what="ei")
+    assert_close(gei.cpu().numpy(), g["grad_ei"][:, :, :dm], rtol=1e-7, atol=1e-300, what="grad ei")
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_stage_b_and_sample_ab(golden, name):
+    g = golden(name)
+    eng = _engine(g)
+    hb = eng.hypers(g["thetas"])
+    bq, lo, up = _bq(g, hb)
+    ub = bq.setup(g["cands"])
+    S, Cn, n = hb.S, ub.C, eng.n
+    rows = 1 + eng.desc.dim_m
+    G = ub.G.cpu().numpy().reshape(S, Cn, rows, n)
+    R = ub.R.cpu().numpy().reshape(S, Cn, rows, n)
+    assert_close(G[:, :, 0, :], g["gamma"], rtol=1e-13, what="gamma")
+    s2 = R[:, :, 0, :]
+    if bq.is_product:
+        q = bq.qt.cpu().numpy()[:, g["points"][:, -1].astype(int)]  # [S][n]
+        s2 = s2 / q[:, None, :]
+    assert_close(s2, g["solve_2"], rtol=1e-8, atol=1e-12, what="solve_2")
+    assert_close(ub.den.cpu().numpy(), g["den"], rtol=1e-9, what="den")
+    # a, b, grad a, grad b at every (hyper, candidate, point)
+    P = g["xq"].shape[0]
+    pts, units = [], []
+    for s in range(S):
+        for c in range(Cn):
+            for p in range(P):
+                pts.append(g["xq"][p])
+                units.append(c * S + s)
+    out = bq.sample_ab(ub, np.array(pts), np.array(units, dtype=np.int32))
+    got = out.cpu().numpy().reshape(S, Cn, P, -1)
+    for s in range(S):
+        assert_close(got[s], g["ab"][s], rtol=cond_rtol(g, s), atol=1e-11, what="ab[%d]" % s)
+    # gradient_vector_b at the same points
+    upts = np.zeros((Cn * S, P, int(g["dx"])))
+    upts[:] = g["xq"][None, :, :]
+    gvb, is_nan = bq.grad_vector_b(ub, upts)
+    gvb = gvb.cpu().numpy().reshape(Cn, S, P, -1).transpose(1, 0, 2, 3)
+    assert not is_nan.cpu().numpy().any()
+    for s in range(S):
+        assert_close(gvb[s], g["gvb"][s][:, :, :eng.desc.dim_m], rtol=10 * cond_rtol(g, s),
+                     atol=1e-11, what="gvb[%d]" % s)
+
+
+@pytest.mark.parametrize("name", ["product_uniform", "product_weighted"])
+def test_discretised_kg(golden, name):
+    from bayesian_quadrature_optimization_b200 import engine as E
+    from scipy.stats import norm
+    g = golden(name)
+    eng = _engine(g)
+    hb = eng.hypers(g["thetas"])
+    bq, lo, up = _bq(g, hb)
+    ub = bq.setup(g["cands"])
+    S, Cn = hb.S, ub.C
+    disc = g["discretization"]
+    m = disc.shape[0]
+    for s in range(S):
+        for c in range(Cn):
+            u = c * S + s
+            ab = bq.sample_ab(ub, disc, np.full(m, u, dtype=np.int32)).cpu().numpy()
+            kg, cnt, idx, c_out = E.kg_discretized(eng, ab[:, 0], ab[None, :, 1])
+            assert_close(kg.cpu().numpy()[0], g["kg"][s, c], rtol=1e-8, atol=1e-13, what="kg")
+            M = int(cnt.cpu().numpy()[0])
+            if M <= 1:
+                assert_close(np.zeros(eng.desc.dim_m), g["grad_kg"][s, c][:eng.desc.dim_m], atol=0)
+                continue
+            keep = idx.cpu().numpy()[0, :M]
+            cc = np.abs(c_out.cpu().numpy()[0, :M - 1])
+            upts = np.zeros((Cn * S, M, int(g["dx"])))
+            upts[u] = disc[keep]
+            gv, _ = bq.grad_vector_b(ub, upts)
+            gv = gv.cpu().numpy()[u]
+            grad = np.array([np.dot(np.diff(gv[:, l]), norm.pdf(cc)) for l in range(gv.shape[1])])
+            assert_close(grad, g["grad_kg"][s, c][:eng.desc.dim_m], rtol=1e-7, atol=1e-12,
+                         what="grad kg")
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_inner_maximize_matches_cpu_restatement(golden, name):
+    g = golden(name)
+    eng = _engine(g)
+    hb = eng.hypers(g["thetas"])
+    bq, lo, up = _bq(g, hb)
+    ub = bq.setup(g["cands"])
+    spec, ogp, obq = oracle_from_golden(g)
+    rng = np.random.RandomState(11)
+    dx = int(g["dx"])
+    zs = rng.normal(0, 1, 5)
+    starts = rng.uniform(lo, up, (3, dx))
+    out_max, out_arg, n_evals = bq.inner_maximize(ub, zs, starts, count_evals=True)
+    out_max = out_max.cpu().numpy()
+    out_arg = out_arg.cpu().numpy()
+    w = g["wset"] if "wset" in g else None
+    S = hb.S
+    total = 0
+    for c in range(ub.C):
+        cand = g["cands"][c:c + 1, :]
+        for s in (0, S - 1):
+            th = g["thetas"][s]
+            u = c * S + s
+
+            def ab(x, wset):
+                v = obq.compute_parameters_for_sample(x, cand, th[0], th[1], th[2:], w=w)
+                gr = obq.compute_gradient_parameters_for_sample(x, cand, th[0], th[1], th[2:], w=w)
+                return v["a"][0], np.asarray(v["b"]).reshape(-1)[0], gr["a"], gr["b"]
+
+            for i, z in enumerate(zs):
+                best, arg, ne = inner_opt.inner_maximize(ab, z, starts, lo, up)
+                total += ne
+                # the value is the acquisition ingredient: 1e-9 relative
+                assert_close(out_max[u, i], best, rtol=1e-9, atol=1e-12, what="inner max")
+                # the device argmax evaluated by the oracle reproduces the device value
+                a, b, _, _ = ab(out_arg[u, i], 0)
+                assert_close(a + z * b, out_max[u, i], rtol=1e-9, atol=1e-12, what="value at argmax")
+                assert np.all(out_arg[u, i] >= lo - 1e-15) and np.all(out_arg[u, i] <= up + 1e-15)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_full_candidate_evaluation_against_oracle_pipeline(golden, name):
+    """evaluate_mc_bayesian_candidate_points_no_restarts: device pipeline vs the same
+    ingredients assembled on the CPU (inner maxima from the CPU restatement of the optimiser,
+    gradient_vector_b and the means from the oracle)."""
+    g = golden(name)
+    eng = _engine(g)
+    hb = eng.hypers(g["thetas"])
+    bq, lo, up = _bq(g, hb)
+    spec, ogp, obq = oracle_from_golden(g)
+    rng = np.random.RandomState(3)
+    dx = int(g["dx"])
+    zs = rng.normal(0, 1, 4)
+    starts = rng.uniform(lo, up, (2, dx))
+    max_mean = rng.normal(0, 1, hb.S)
+    res = bq.evaluate_candidates(g["cands"], zs, starts, max_mean=max_mean)
+    w = g["wset"] if "wset" in g else None
+    vals = np.zeros(len(g["cands"]))
+    grads = np.zeros((len(g["cands"]), eng.desc.dim_m))
+    for c in range(len(g["cands"])):
+        cand = g["cands"][c:c + 1, :]
+        vk, gk = [], []
+        for s, th in enumerate(g["thetas"]):
+            def ab(x, wset):
+                v = obq.compute_parameters_for_sample(x, cand, th[0], th[1], th[2:], w=w)
+                gr = obq.compute_gradient_parameters_for_sample(x, cand, th[0], th[1], th[2:], w=w)
+                return v["a"][0], np.asarray(v["b"]).reshape(-1)[0], gr["a"], gr["b"]
+            mx, args = [], []
+            for z in zs:
+                best, arg, _ = inner_opt.inner_maximize(ab, z, starts, lo, up)
+                mx.append(best)
+                args.append(arg)
+            vk.append(np.mean(mx) - max_mean[s])
+            gb = obq.gradient_vector_b(cand, np.array(args), th[0], th[1], th[2:], w=w)
+            gk.append(np.mean(gb * zs.reshape(-1, 1), axis=0)[:eng.desc.dim_m])
+        vals[c] = np.mean(vk)
+        grads[c] = np.mean(gk, axis=0)
+    assert_close(res["evaluations"].cpu().numpy(), vals, rtol=1e-9, atol=1e-12, what="acq value")
+    assert_close(res["gradient"].cpu().numpy(), grads, rtol=1e-6, atol=1e-9, what="acq gradient")
+    # argmax candidate index is exact
+    assert int(np.argmax(res["evaluations"].cpu().numpy())) == int(np.argmax(vals))
+
+
+def test_cholesky_solve_random_sizes():
+    """Non-multiple-of-64 sizes, several right-hand sides, against LAPACK."""
+    import torch
+    from bayesian_quadrature_optimization_b200 import engine as E, _cabi
+    import ctypes as C
+    rng = np.random.RandomState(0)
+    eng = E.GPEngine(_cabi.KIND_MATERN52, 1)
+    for n, S, m in [(1, 2, 1), (63, 2, 3), (64, 1, 65), (65, 3, 7), (300, 2, 130), (517, 2, 5)]:
+        A = rng.normal(0, 1, (S, n, n + 5))
+        A = A @ A.transpose(0, 2, 1) + 1e-3 * np.eye(n)
+        Ad = eng.to_device(A.copy())
+        info = torch.zeros(S, dtype=torch.int32, device=eng.device)
+        _cabi.check(eng.lib.bqo_potrf_batched(_cabi.ptr(Ad), n, S, _cabi.ptr(info),
+                                              torch.cuda.current_stream().cuda_stream), "potrf")
+        assert not info.cpu().numpy().any()
+        L = np.stack([np.linalg.cholesky(a) for a in A])
+        assert_close(Ad.cpu().numpy(), L, rtol=1e-9, atol=1e-11, what="potrf n=%d" % n)
+        B = rng.normal(0, 1, (S, m, n))
+        Bd = eng.to_device(B.copy())
+        _cabi.check(eng.lib.bqo_potrs_batched(_cabi.ptr(Ad), n, S, _cabi.ptr(Bd), m,
+                                              torch.cuda.current_stream().cuda_stream), "potrs")
+        X = np.stack([np.linalg.solve(A[s], B[s].T).T for s in range(S)])
+        assert_close(Bd.cpu().numpy(), X, rtol=1e-7, atol=1e-9, what="potrs n=%d" % n)
+
+
+def test_cholesky_not_positive_definite_and_jitter():
+    """sbo/lib/la_functions.py:19-38: diag <= 0 -> error; otherwise jitter escalation."""
+    import torch
+    from bayesian_quadrature_optimization_b200 import engine as E, _cabi
+    # duplicate training points and zero noise make Sigma singular: jitter must rescue it
+    pts = np.array([[0.1], [0.1], [0.5], [0.9], [0.9]])
+    y = np.array([1.0, 1.0, 2.0, 3.0, 3.0])
+    eng = E.GPEngine(_cabi.KIND_MATERN52, 1)
+    eng.set_data(pts, y)
+    thetas = np.array([[0.0, 0.0, 0.3], [1e-3, 0.0, 0.3]])
+    hb = eng.hypers(thetas).factorize()
+    assert hb.info[1] == 0 and hb.jitter[1] == 0.0
+    assert hb.info[0] == 0 and hb.jitter[0] > 0.0
+    spec = orc.KernelSpec(orc.MATERN52, 1)
+    cov = spec.cov(thetas[0][2:], pts)
+    want = orc.cholesky(cov, max_tries=7)
+    # same jitter level as the reference picked (mean(diag) * 1e-6 * 10^t)
+    t = np.log10(hb.jitter[0] / (np.mean(np.diag(cov)) * 1e-6))
+    assert abs(t - round(t)) < 1e-9
+    ref_j = None
+    for tt in range(8):
+        j = np.mean(np.diag(cov)) * 1e-6 * 10 ** tt
+        try:
+            np.linalg.cholesky(cov + j * np.eye(5))
+            ref_j = j
+            break
+        except np.linalg.LinAlgError:
+            pass
+    assert ref_j is not None
+    if abs(ref_j - hb.jitter[0]) <= 1e-12 * ref_j:
+        assert_close(hb.L.cpu().numpy()[0], want, rtol=1e-6, atol=1e-9, what="jittered chol")
+    # a matrix with a non-positive diagonal entry reports the reference's first error
+    A = eng.to_device(np.array([[[1.0, 2.0], [2.0, -1.0]]]))
+    info = torch.zeros(1, dtype=torch.int32, device=eng.device)
+    _cabi.check(eng.lib.bqo_potrf_batched(_cabi.ptr(A), 2, 1, _cabi.ptr(info),
+                                          torch.cuda.current_stream().cuda_stream), "potrf")
+    assert info.cpu().numpy()[0] == 2
+
+
+def test_large_size_properties():
+    """n = 2048 (BASELINE size): L L^T reproduces Sigma, potrs residual, log-likelihood vs LAPACK."""
+    from bayesian_quadrature_optimization_b200 import engine as E, _cabi
+    rng = np.random.RandomState(0)
+    n, d = 2048, 6
+    pts = np.concatenate([rng.uniform(0, 1, (n, 4)), rng.gamma(2.0, 1.0, (n, 2))], 1)
+    y = np.sin(pts.sum(1)) + 0.01 * rng.normal(0, 1, n)
+    thetas = np.array([[1e-4, 0.0, 0.3, 0.3, 0.3, 0.3, 2.0, 2.0, 1.0],
+                       [2e-4, 0.05, 0.35, 0.25, 0.3, 0.4, 1.8, 2.2, 1.2]])
+    eng = E.GPEngine(_cabi.KIND_SCALED_MATERN52, d)
+    eng.set_data(pts, y)
+    hb = eng.hypers(thetas)
+    Sigma = hb.cov(add_noise=True)
+    hb.factorize()
+    assert np.all(hb.info == 0)
+    L = hb.L
+    rec = L @ L.transpose(1, 2)
+    err = ((rec - Sigma).norm() / Sigma.norm()).item()
+    assert err < 1e-13, err
+    spec = orc.KernelSpec(orc.SCALED_MATERN52, d)
+    ogp = orc.OracleGP(spec, pts, y)
+    llh = hb.log_likelihood().cpu().numpy()
+    want = [ogp.log_likelihood(t[0], t[1], t[2:]) for t in thetas]
+    assert_close(llh, want, rtol=1e-9, what="llh n=2048")
+    res = (Sigma @ hb.alpha.unsqueeze(2)).squeeze(2) - (eng.y.unsqueeze(0) - hb.theta[:, 1:2])
+    assert (res.norm() / eng.y.norm()).item() < 1e-9
+
+
+def test_adam_step_matches_reference_sgd():
+    import torch
+    from bayesian_quadrature_optimization_b200 import engine as E, _cabi
+    eng = E.GPEngine(_cabi.KIND_MATERN52, 1)
+    rng = np.random.RandomState(2)
+    R, dim = 5, 3
+    target = rng.uniform(0.2, 0.8, (R, dim))
+    start = rng.uniform(0, 1, (R, dim))
+    bounds = [(0.0, 1.0)] * dim
+    want = np.stack([orc.sgd_adam(start[r], lambda x, r=r: 2 * (x - target[r]), 1, bounds=bounds,
+                                  maxepoch=25) for r in range(R)])
+    pt = eng.to_device(start.copy())
+    m0 = torch.zeros_like(pt)
+    v0 = torch.zeros_like(pt)
+    active = torch.ones(R, dtype=torch.int32, device=eng.device)
+    lo = eng.to_device(np.zeros(dim))
+    up = eng.to_device(np.ones(dim))
+    tgt = eng.to_device(target)
+    for t in range(1, 26):
+        grad = (2 * (pt - tgt)).contiguous()
+        _cabi.check(eng.lib.bqo_adam_step_batched(
+            _cabi.ptr(pt), _cabi.ptr(grad), _cabi.ptr(m0), _cabi.ptr(v0), _cabi.ptr(active),
+            _cabi.ptr(lo), _cabi.ptr(up), R, dim, t, 0.1, 0.9, 0.999, 1e-8,
+            torch.cuda.current_stream().cuda_stream), "adam")
+    assert_close(pt.cpu().numpy(), want, rtol=1e-12, atol=1e-14, what="adam")
