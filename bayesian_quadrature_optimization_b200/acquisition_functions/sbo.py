@@ -1,0 +1,232 @@
+"""SBO: host-side mirror of sbo/acquisition_functions/sbo.py (the BQO acquisition function).
+
+Every (candidate, hyper-sample, Z sample) tuple is evaluated on the GPU: stage B (gamma,
+Sigma^-1 gamma, denominator), the inner maximisation of a(x) + Z b(x) over x, the gradient of b
+with respect to the candidate at the maximisers, and the Monte-Carlo means.
+"""
+from __future__ import annotations
+
+import itertools
+from copy import deepcopy
+
+import numpy as np
+import torch
+from scipy.stats import norm
+
+from ..engine import kg_discretized
+from ..lib.constant import UNIFORM_FINITE, LBFGS_NAME, DEFAULT_N_PARAMETERS, DEFAULT_N_SAMPLES
+from ..services.domain import DomainService
+
+
+class SBO(object):
+
+    def __init__(self, bayesian_quadrature, discretization_domain=None):
+        self.bq = bayesian_quadrature
+        self.discretization = discretization_domain
+        self.bounds_opt = deepcopy(self.bq.bounds)
+        if self.bq.separate_tasks and not self.bq.task_continue:
+            self.bounds_opt.append([None, None])
+        elif self.bq.separate_tasks:
+            for i in self.bq.w_domain:
+                bound = self.bounds_opt[i]
+                self.bounds_opt[i] = [bound[0], bound[-1]]
+        self.opt_separing_domain = self.bq.distribution == UNIFORM_FINITE
+        self.domain_w = [self.bq.gp.bounds[i] for i in self.bq.w_domain]
+        self.optimization_results = []
+        self.samples = None
+        self.starting_points_sbo = None
+        self.optimal_samples = {}
+        self.mc_bayesian = {}
+        self.args_handler = ()
+        # device-side inner maximiser settings (bgo defaults: sbo/services/bgo.py:43-44)
+        self.inner_pgtol = 1e-5
+        self.inner_max_ls = 20
+        self.last_n_evals = None
+
+    # -- one sample path ------------------------------------------------------------------------------
+    def evaluate_sample(self, point, candidate_point, sample, var_noise=None, mean=None,
+                        parameters_kernel=None, cache=True, n_threads=0, clear_cache=True, w_set=0):
+        """:140-165 -> float: a_{n+1}(point) for the standard normal draw `sample`."""
+        point = np.asarray(point, dtype=float)
+        if len(point.shape) == 1:
+            point = point.reshape((1, len(point)))
+        vectors = self.bq.compute_parameters_for_sample(
+            point, candidate_point, var_noise=var_noise, mean=mean,
+            parameters_kernel=parameters_kernel, w_set=w_set)
+        value = vectors['a'] + sample * vectors['b']
+        return value[0, 0]
+
+    def evaluate_gradient_sample(self, point, candidate_point, sample, var_noise=None, mean=None,
+                                 parameters_kernel=None, cache=True, w_set=0):
+        """:167-194 -> np.array(n)."""
+        point = np.asarray(point, dtype=float)
+        if len(point.shape) == 1:
+            point = point.reshape((1, len(point)))
+        g = self.bq.compute_gradient_parameters_for_sample(
+            point, candidate_point, var_noise=var_noise, mean=mean,
+            parameters_kernel=parameters_kernel, w_set=w_set)
+        return g['a'] + sample * g['b']
+
+    def _bounds_x(self):
+        return [self.bounds_opt[i] for i in range(len(self.bounds_opt)) if i in self.bq.x_domain]
+
+    def generate_starting_points_evaluate_mc(self, n_restarts, cache=True):
+        """:378-399."""
+        bounds_x = self._bounds_x()
+        start = np.array(DomainService.get_points_domain(n_restarts + 1, bounds_x,
+                                                         type_bounds=len(bounds_x) * [0]))
+        if cache:
+            self.starting_points_sbo = start
+        return start
+
+    def generate_samples_starting_points_evaluate_mc(self, n_samples, n_restarts, cache=True):
+        """:368-376: Z samples first, then the start points (RNG call order of the reference)."""
+        samples = np.random.normal(0, 1, n_samples)
+        if cache:
+            self.samples = samples
+        start = self.generate_starting_points_evaluate_mc(n_restarts, cache=cache)
+        return samples, start
+
+    def evaluate_sbo_by_sample(self, candidate_point, sample, start=None, var_noise=None, mean=None,
+                               parameters_kernel=None, n_restarts=5, parallel=True, n_threads=0,
+                               method_opt=None, tol=None, **opt_params_mc):
+        """:237-366 -> {'max': float, 'optimum': np.array(n)}: max_x a(x) + Z b(x) from
+        n_restarts + 1 starts (the previous posterior-mean optimum first, when cached) and the box
+        vertices, all on the device."""
+        theta = self.bq._theta(var_noise, mean, parameters_kernel)
+        bounds_x = self._bounds_x()
+        index_cache = 'mc_mean' if var_noise is None else (theta[0], theta[1], tuple(theta[2:]))
+        if start is None:
+            start_points = DomainService.get_points_domain(n_restarts + 1, bounds_x,
+                                                           type_bounds=len(bounds_x) * [0])
+            prev = self.bq.optimal_solutions.get(index_cache)
+            if prev is not None and len(prev) > 0:
+                start = np.array([prev[-1]['solution']] + start_points[0:-1])
+            else:
+                start = np.array(start_points)
+        else:
+            start = np.asarray(start, dtype=float).reshape(1, -1)
+        bq = self.bq.engine_for(theta)
+        ub = bq.setup(np.asarray(candidate_point, dtype=float).reshape(1, -1))
+        mx, arg, _ = bq.inner_maximize(
+            ub, np.array([sample], dtype=float), start, maxiter=opt_params_mc.get('maxiter', 15000),
+            factr=opt_params_mc.get('factr', 1e7), pgtol=self.inner_pgtol, max_ls=self.inner_max_ls,
+            use_vertices=len(bounds_x) < 7)
+        return {'max': float(mx.cpu().numpy()[0, 0]), 'optimum': arg.cpu().numpy()[0, 0]}
+
+    # -- Monte-Carlo Bayesian estimate over many candidates -----------------------------------------------
+    def _max_posterior_mean(self, bq, parameters, n_restarts=100):
+        """max_x E[G(x)] per hyper-sample (optimize_posterior_mean, bayesian_quadrature.py:693-910,
+        called from sbo.py:597-620): the same device maximiser with Z = 0, i.e. the objective a(x)."""
+        missing = [k for k, p in enumerate(parameters)
+                   if (p[0], p[1], tuple(p[2:])) not in self.bq.max_mean]
+        if missing:
+            bounds_x = self._bounds_x()
+            starts = np.array(DomainService.get_points_domain(
+                n_restarts + 1, bounds_x, type_bounds=len(bounds_x) * [0]))
+            ub = bq.setup(self.bq._dummy_candidate())
+            mx, arg, _ = bq.inner_maximize(ub, np.zeros(1), starts, maxiter=15000, factr=1e7,
+                                           pgtol=self.inner_pgtol, max_ls=self.inner_max_ls,
+                                           use_vertices=len(bounds_x) < 7)
+            mx = mx.cpu().numpy()[:, 0]
+            arg = arg.cpu().numpy()[:, 0]
+            for k in missing:
+                p = parameters[k]
+                index_cache = (p[0], p[1], tuple(p[2:]))
+                self.bq.max_mean[index_cache] = mx[k]
+                self.bq.optimal_solutions.setdefault(index_cache, []).append(
+                    {'solution': arg[k], 'optimal_value': mx[k]})
+        return np.array([self.bq.max_mean[(p[0], p[1], tuple(p[2:]))] for p in parameters])
+
+    def evaluate_mc_bayesian_candidate_points_no_restarts(
+            self, candidate_points, n_samples_parameters, n_samples, n_restarts=10, n_threads=0,
+            compute_max_mean=False, compute_gradient=False, method_opt=None, **opt_params_mc):
+        """:523-670 -> {'evaluations': np.array(n), 'gradient': np.array(n x k)}.
+
+        Same argument meaning as the reference; the C x S x Z inner maximisations the reference
+        farms out to a process pool run as one kernel launch."""
+        gp = self.bq.gp
+        if n_samples_parameters == 0:
+            parameters = [gp.get_value_parameters_model]
+        else:
+            parameters = gp.samples_parameters[-n_samples_parameters:]
+        samples, start = self.generate_samples_starting_points_evaluate_mc(
+            n_samples, n_restarts, cache=False)
+        candidate_points = np.asarray(candidate_points, dtype=float)
+        bq = self.bq.engine_for(np.array(parameters))
+        max_mean = None
+        if compute_max_mean:
+            max_mean = self._max_posterior_mean(bq, parameters)
+        else:
+            mm = [self.bq.max_mean.get((p[0], p[1], tuple(p[2:])), 0) for p in parameters]
+            if any(m != 0 for m in mm):
+                max_mean = np.array(mm, dtype=float)
+        res = bq.evaluate_candidates(
+            candidate_points, samples, start, max_mean=max_mean, compute_gradient=compute_gradient,
+            maxiter=opt_params_mc.get('maxiter', 15000), factr=opt_params_mc.get('factr', 1e7),
+            pgtol=self.inner_pgtol, max_ls=self.inner_max_ls,
+            use_vertices=len(self._bounds_x()) < 7)
+        evaluations = res['evaluations'].cpu().numpy()
+        gradient = None
+        if compute_gradient:
+            g = res['gradient'].cpu().numpy()
+            pad = candidate_points.shape[1] - g.shape[1]
+            if pad > 0:  # task coordinate: zero gradient (NaN rows stay NaN)
+                extra = np.where(np.isnan(g[:, :1]), np.nan, 0.0)
+                g = np.concatenate([g] + pad * [extra], axis=1)
+            gradient = g
+        return {'evaluations': evaluations, 'gradient': gradient}
+
+    # -- discretised SBO (closed-form knowledge gradient) -------------------------------------------------
+    def evaluate(self, point, var_noise=None, mean=None, parameters_kernel=None, cache=True,
+                 n_threads=0):
+        """:1394-1425 -> float."""
+        vectors = self.bq.compute_posterior_parameters_kg(
+            self.discretization, point, var_noise=var_noise, mean=mean,
+            parameters_kernel=parameters_kernel)
+        a, b = vectors['a'], vectors['b']
+        if not np.all(np.isfinite(b)):
+            return 0.0
+        kg, _, _, _ = kg_discretized(self.bq.gp._engine(), a, b[None, :])
+        return float(kg.cpu().numpy()[0])
+
+    def evaluate_gradient(self, point, var_noise=None, mean=None, parameters_kernel=None,
+                          cache=True, n_threads=0):
+        """:1428-1474 -> np.array(n)."""
+        point = np.asarray(point, dtype=float).reshape(1, -1)
+        vectors = self.bq.compute_posterior_parameters_kg(
+            self.discretization, point, var_noise=var_noise, mean=mean,
+            parameters_kernel=parameters_kernel)
+        a, b = vectors['a'], vectors['b']
+        _, cnt, idx, c_out = kg_discretized(self.bq.gp._engine(), a, b[None, :])
+        M = int(cnt.cpu().numpy()[0])
+        if M <= 1:
+            return np.zeros(point.shape[1])
+        keep = idx.cpu().numpy()[0, :M]
+        c2 = np.abs(c_out.cpu().numpy()[0, :M - 1])
+        evalC = norm.pdf(c2)
+        gradients = self.bq.gradient_vector_b(point, self.discretization[keep, :],
+                                              var_noise=var_noise, mean=mean,
+                                              parameters_kernel=parameters_kernel)
+        gradient = np.zeros(point.shape[1])
+        for i in range(point.shape[1]):
+            gradient[i] = np.dot(np.diff(gradients[:, i]), evalC)
+        return gradient
+
+    @staticmethod
+    def hvoi(b, c, keep):
+        """:1952-1961 (host helper kept for API parity)."""
+        M = len(keep)
+        if M > 1:
+            c = c[keep + 1]
+            c2 = -np.abs(c[0:M - 1])
+            tmp = norm.pdf(c2) + c2 * norm.cdf(c2)
+            return np.sum(np.diff(b[keep]) * tmp)
+        return 0
+
+    def clean_cache(self):
+        self.samples = None
+        self.starting_points_sbo = None
+        self.optimal_samples = {}
+        self.mc_bayesian = {}
+        self.bq.clean_cache()

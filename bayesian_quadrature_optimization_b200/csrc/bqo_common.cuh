@@ -70,6 +70,80 @@ __device__ __forceinline__ double bqo_matern52_dr(double r, double r2) {
     return part_1 + part_2;
 }
 
+// ---- fast path of the streaming stage (stage C) ---------------------------------------------
+// Every FP64 instruction counts there (64 DFMA lanes per SM per clock is the roof), so sqrt and
+// exp are open-coded:
+//   sqrt : MUFU.RSQ64H seed (SFU pipe), one Goldschmidt step and one Newton correction;
+//   exp  : exp(-sqrt5 r) = 2^(n/32), n = round(-32 sqrt5 log2(e) r); 2^(n/32) = 2^k T[j] P(f)
+//          with a 32-entry table T[j] = 2^(j/32) in shared memory, a degree-6 Taylor
+//          polynomial P on |f| <= 1/2 (argument <= ln2/64, truncation error 3e-18) and the
+//          power of two applied to the exponent field with integer adds (ALU pipe).
+// Both are accurate to about 1.5 ulp (checked against libm in tests/test_gpu_parity.py).
+#define BQO_EXP_TABLE 32
+
+// Constants of the fast path live in constant memory so that DFMA/DMUL read them as c[bank][off]
+// operands; as literals ptxas re-materialises each 64-bit constant with two UMOVs inside the loop
+// (27% of all issued instructions in the first profile, profiles/r01_inner_maximize_v0.md).
+static __constant__ double BQO_FC[10] = {
+    2.23606797749978969640917366873128,   // 0 sqrt(5)
+    -46.16624130844683,                   // 1 -32/ln2
+    -0.02166084938653512,                 // 2 -(ln2/32) high 32 bits
+    -5.9631716539705866e-12,              // 3 -(ln2/32) low part
+    1.0 / 720.0,                          // 4
+    1.0 / 120.0,                          // 5
+    1.0 / 24.0,                           // 6
+    1.0 / 6.0,                            // 7
+    5.0 / 3.0,                            // 8
+    -5.0 / 3.0,                           // 9
+};
+
+__device__ __forceinline__ void bqo_exp_table_init(double* tab) {
+    for (int j = threadIdx.x; j < BQO_EXP_TABLE; j += blockDim.x)
+        tab[j] = exp2((double)j / (double)BQO_EXP_TABLE);
+}
+
+// sqrt(x) for normal x > 0.
+__device__ __forceinline__ double bqo_fast_sqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double g = x * y;        // ~ sqrt(x)
+    double h = 0.5 * y;      // ~ 1 / (2 sqrt(x))
+    double r = fma(-h, g, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    double d = fma(-g, g, x);
+    return fma(d, h, g);
+}
+
+// k(r) and g(r) = k'(r)/r from the squared scaled distance r2 (must be a normal number > 0:
+// callers start the accumulation of r2 at 1e-300).
+__device__ __forceinline__ void bqo_matern52_kg_fast(double r2, const double* __restrict__ tab,
+                                                     double& k, double& g) {
+    const double r = bqo_fast_sqrt(r2);
+    const double s = BQO_FC[0] * r;  // the reference's np.sqrt(5) * r, same rounding
+    // n = round(-s * 32 / ln2); Cody-Waite reduction fr = -s - n ln2/32 with a two-part constant
+    const double magic = 6755399441055744.0;  // 1.5 * 2^52
+    const double tk = fma(s, BQO_FC[1], magic);
+    int n = __double2loint(tk);
+    const double kf = tk - magic;
+    double fr = fma(kf, BQO_FC[2], -s);   // ln2/32, high 32 bits
+    fr = fma(kf, BQO_FC[3], fr);          // ln2/32, low part
+    // exp(fr), |fr| <= ln2/64: Taylor degree 6 (truncation error < 3e-18)
+    double p = fma(BQO_FC[4], fr, BQO_FC[5]);
+    p = fma(p, fr, BQO_FC[6]);
+    p = fma(p, fr, BQO_FC[7]);
+    p = fma(p, fr, 0.5);
+    p = fma(p, fr, 1.0);
+    p = fma(p, fr, 1.0);
+    n = max(n, -32000);  // exp underflow: keep the exponent arithmetic in the normal range
+    double e = p * tab[n & (BQO_EXP_TABLE - 1)];
+    e = __hiloint2double(__double2hiint(e) + ((n >> 5) << 20), __double2loint(e));
+    // k = (1 + sqrt5 r + 5/3 r^2) e,  g = -(5/3)(1 + sqrt5 r) e
+    const double t1 = 1.0 + s;
+    k = fma(BQO_FC[8], r2, t1) * e;
+    g = (t1 * e) * BQO_FC[9];
+}
+
 __device__ __forceinline__ double bqo_warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

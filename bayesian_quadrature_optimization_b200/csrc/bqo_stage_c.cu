@@ -129,6 +129,7 @@ struct UnitCtx {
     const double* xs;   // [(DX+DW)][ldx] scaled training coordinates (global or shared)
     const double* wa;   // [n] weights of a (alpha, q-weighted for PRODUCT)
     const double* wb;   // [n] weights of b (s2, q-weighted for PRODUCT)
+    const double* tab;  // shared-memory table 2^(j/32) of the fast exp
     int ldx;            // stride between coordinate rows of xs
     int n;
     int M;
@@ -194,7 +195,7 @@ __device__ __forceinline__ void eval_ab_warp(const UnitCtx<DX, DW>& u, const dou
     const int M = u.M;
     for (int j = lane; j < u.n; j += 32) {
         double dxl[DX];
-        double Dx = 0.0;
+        double Dx = 1e-300;  // keeps r2 a normal positive number for the fast sqrt (k(0) = 1)
 #pragma unroll
         for (int l = 0; l < DX; ++l) {
             dxl[l] = xsc[l] - u.xs[l * u.ldx + j];
@@ -214,12 +215,12 @@ __device__ __forceinline__ void eval_ab_warp(const UnitCtx<DX, DW>& u, const dou
                     r2 = fma(dw, dw, r2);
                 }
                 double k, g;
-                bqo_matern52_kg(r2, k, g);
+                bqo_matern52_kg_fast(r2, u.tab, k, g);
                 ksum += k;
                 gsum += g;
             }
         } else {
-            bqo_matern52_kg(Dx, ksum, gsum);
+            bqo_matern52_kg_fast(Dx, u.tab, ksum, gsum);
         }
         const double wa = u.wa[j], wb = u.wb[j];
         Sa = fma(ksum, wa, Sa);
@@ -237,7 +238,7 @@ __device__ __forceinline__ void eval_ab_warp(const UnitCtx<DX, DW>& u, const dou
     for (int l = 0; l < DX; ++l) GC[l] = 0.0;
     for (int m = lane; m < M; m += 32) {
         double dxl[DX];
-        double r2 = 0.0;
+        double r2 = 1e-300;
 #pragma unroll
         for (int l = 0; l < DX; ++l) {
             dxl[l] = xsc[l] - u.cs[l];
@@ -249,7 +250,7 @@ __device__ __forceinline__ void eval_ab_warp(const UnitCtx<DX, DW>& u, const dou
             r2 = fma(dw, dw, r2);
         }
         double k, g;
-        bqo_matern52_kg(r2, k, g);
+        bqo_matern52_kg_fast(r2, u.tab, k, g);
         Kc += k;
 #pragma unroll
         for (int l = 0; l < DX; ++l) GC[l] = fma(g, dxl[l], GC[l]);
@@ -290,10 +291,13 @@ __global__ void __launch_bounds__(AB_WARPS * 32) sample_ab_kernel(bqo_stage_c pb
     extern __shared__ double dyn_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = blockIdx.x * AB_WARPS + warp;
+    bqo_exp_table_init(dyn_smem);
+    __syncthreads();
     if (q >= P) return;
-    double* ws = dyn_smem + warp * (pb.M * (DW > 0 ? DW : 1));
+    double* ws = dyn_smem + BQO_EXP_TABLE + warp * (pb.M * (DW > 0 ? DW : 1));
     UnitCtx<DX, DW> u;
     unit_ctx_init<DX, DW>(u, pb, pt_unit[q]);
+    u.tab = dyn_smem;
     if (DW > 0) {
         int wsi = pt_wset ? pt_wset[q] : 0;
         scale_wset<DX, DW>(u, pb.wsets + (int64_t)wsi * pb.M * DW, ws);
@@ -377,7 +381,7 @@ extern "C" int bqo_sample_ab_batched(const bqo_stage_c* pb, const double* pts,
     BQO_CHECK_ARG(out != nullptr, 6);
     cudaStream_t cs = (cudaStream_t)stream;
     int grid = (P + AB_WARPS - 1) / AB_WARPS;
-    size_t smem = sizeof(double) * AB_WARPS * (size_t)(pb->M > 0 ? pb->M : 1) * (pb->dw > 0 ? pb->dw : 1);
+    size_t smem = sizeof(double) * (BQO_EXP_TABLE + AB_WARPS * (size_t)(pb->M > 0 ? pb->M : 1) * (pb->dw > 0 ? pb->dw : 1));
 #define LAUNCH_AB(DXV, DWV) \
     sample_ab_kernel<DXV, DWV><<<grid, AB_WARPS * 32, smem, cs>>>(*pb, pts, pt_unit, pt_wset, P, out)
     SC_DISPATCH(pb, LAUNCH_AB);
@@ -421,12 +425,13 @@ __global__ void __launch_bounds__(IM_WARPS * 32, 1)
     const int n_pre = n_starts + (opt.use_vertices ? NV : 0);
 
     // ---- shared memory carve-up -------------------------------------------------------------
-    double* sm = dyn_smem;
+    double* s_tab = dyn_smem;                // [32] exp table
+    double* sm = dyn_smem + BQO_EXP_TABLE;
     double* s_xs = sm;                       // STAGE: [D][n]
     double* s_wa = s_xs + (STAGE ? (size_t)D * n : 0);
     double* s_wb = s_wa + (STAGE ? n : 0);
-    double* s_ws = s_wb + (STAGE ? n : 0);   // [n_wsets][M][DW] scaled W sets
-    double* s_pre = s_ws + (size_t)pb.n_wsets * M * (DW > 0 ? DW : 0);  // [n_pre][2+2DX]
+    double* s_ws = s_wb + (STAGE ? n : 0);   // [M][DW] the unit's W set, scaled
+    double* s_pre = s_ws + (size_t)M * (DW > 0 ? DW : 0);  // [n_pre][2+2DX]
     double* s_prex = s_pre + (size_t)n_pre * (2 + 2 * DX);              // [n_pre][DX]
     double* s_run = s_prex + (size_t)n_pre * DX;  // [nz][n_starts][1+DX] run results
     RunState<DX>* s_state =
@@ -435,6 +440,8 @@ __global__ void __launch_bounds__(IM_WARPS * 32, 1)
 
     UnitCtx<DX, DW> u;
     unit_ctx_init<DX, DW>(u, pb, unit);
+    u.tab = s_tab;
+    bqo_exp_table_init(s_tab);
     if (STAGE) {
         for (int e = threadIdx.x; e < D * n; e += blockDim.x) s_xs[e] = u.xs[e];
         for (int e = threadIdx.x; e < n; e += blockDim.x) {
@@ -445,9 +452,13 @@ __global__ void __launch_bounds__(IM_WARPS * 32, 1)
         u.wa = s_wa;
         u.wb = s_wb;
     }
-    if (DW > 0)
-        for (int e = threadIdx.x; e < pb.n_wsets * M * DW; e += blockDim.x)
-            s_ws[e] = pb.wsets[e] / u.ls[DX + (e % (DW > 0 ? DW : 1))];
+    if (DW > 0) {
+        // every evaluation of this unit uses the W set of its candidate (sample-average
+        // approximation: the objective of a run is a fixed smooth function)
+        const double* wsrc = pb.wsets + (size_t)(pb.unit_c[unit] % pb.n_wsets) * M * DW;
+        for (int e = threadIdx.x; e < M * DW; e += blockDim.x)
+            s_ws[e] = wsrc[e] / u.ls[DX + (e % (DW > 0 ? DW : 1))];
+    }
     if (threadIdx.x == 0) *s_counter = 0;
     const double* st = starts + (opt.starts_per_hyper ? (int64_t)pb.unit_k[unit] * n_starts * DX : 0);
     __syncthreads();
@@ -470,7 +481,7 @@ __global__ void __launch_bounds__(IM_WARPS * 32, 1)
             for (int l = 0; l < DX; ++l) x[l] = ((v >> (DX - 1 - l)) & 1) ? pb.upper[l] : pb.lower[l];
         }
         AbOut<DX> o;
-        eval_ab_warp<DX, DW>(u, x, s_ws /* W set 0 */, o);
+        eval_ab_warp<DX, DW>(u, x, s_ws, o);
         ++evals;
         if (lane == 0) {
             double* op = s_pre + (size_t)p * (2 + 2 * DX);
@@ -497,7 +508,6 @@ __global__ void __launch_bounds__(IM_WARPS * 32, 1)
         if (run >= n_runs) break;
         const int zi = run / n_starts, sidx = run % n_starts;
         const double Z = z[z0 + zi];
-        int eval_idx = 1;  // evaluation 0 (the start point) used W set 0
         // phi = -(a + Z b)
         if (lane == 0) {
             const double* op = s_pre + (size_t)sidx * (2 + 2 * DX);
@@ -572,9 +582,7 @@ __global__ void __launch_bounds__(IM_WARPS * 32, 1)
                     decr = fma(S.g[l], t - S.x[l], decr);
                 }
                 AbOut<DX> o;
-                const double* wsp = (DW > 0) ? s_ws + (size_t)(eval_idx % pb.n_wsets) * M * DW : s_ws;
-                eval_ab_warp<DX, DW>(u, xn, wsp, o);
-                ++eval_idx;
+                eval_ab_warp<DX, DW>(u, xn, s_ws, o);
                 ++evals;
                 phin = -(o.a + Z * o.b);
                 if (phin <= S.phi + c1 * decr) {
@@ -590,7 +598,14 @@ __global__ void __launch_bounds__(IM_WARPS * 32, 1)
                     __syncwarp();
                     break;
                 }
-                step *= 0.5;
+                // safeguarded quadratic interpolation through phi(0), phi'(0) = decr/step * step..., phi(step):
+                // minimiser of q(t) = phi + decr_t t + c t^2 along the projected path, kept in
+                // [0.1, 0.5] of the current step
+                double denom_q = 2.0 * (phin - S.phi - decr);
+                double shrink = (denom_q > 0.0) ? (-decr / denom_q) : 0.5;
+                shrink = fmin(fmax(shrink, 0.1), 0.5);
+                if (!(shrink == shrink)) shrink = 0.5;
+                step *= shrink;
             }
             if (!accepted) break;
             // BFGS update of the inverse Hessian approximation
@@ -711,9 +726,9 @@ static size_t inner_smem_bytes(const bqo_stage_c* pb, const bqo_inner_opt* opt, 
     const int M = pb->dw > 0 ? pb->M : 1;
     const int NV = 1 << pb->dx;
     const int n_pre = opt->n_starts + (opt->use_vertices ? NV : 0);
-    size_t d = 0;
+    size_t d = BQO_EXP_TABLE;
     if (stage) d += (size_t)(D + 2) * pb->n;
-    d += (size_t)pb->n_wsets * M * pb->dw;
+    d += (size_t)M * pb->dw;
     d += (size_t)n_pre * (2 + 2 * pb->dx) + (size_t)n_pre * pb->dx;
     d += (size_t)opt->z_per_cta * opt->n_starts * (1 + pb->dx);
     return d * sizeof(double) + state_bytes * IM_WARPS + 16;
@@ -792,7 +807,8 @@ __global__ void __launch_bounds__(AB_WARPS * 32)
     }
     if (lane == 0 && gp % npts == 0) is_nan[unit] = 0;
     if (DW > 0) {
-        int wsi = pt_wset ? pt_wset[gp] : 0;
+        // default: the W set of the unit's candidate, like the inner maximiser
+        int wsi = pt_wset ? pt_wset[gp] : (c % pb.n_wsets);
         scale_wset<DX, DW>(u, pb.wsets + (int64_t)wsi * pb.M * DW, ws);
         __syncwarp();
     }

@@ -1,0 +1,409 @@
+"""GPFittingGaussian: host-side mirror of sbo/models/gp_fitting_gaussian.py over the CUDA engine.
+
+Same method names, argument meaning, return types (numpy float64 / Python floats / dicts) and
+error behaviour as the reference for the GP hot path; every number is produced by
+libbqo_sm100.so on the GPU.  Methods taking (var_noise, mean, parameters_kernel) evaluate ONE
+hyper-sample like the reference; the `*_batch` methods are the batched extension (all
+slice-sampled hyper-samples in one launch) the acquisition functions use.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import numpy as np
+from scipy import linalg
+
+from .. import _cabi
+from ..engine import GPEngine
+from ..lib.constant import (
+    MATERN52_NAME, TASKS_KERNEL_NAME, PRODUCT_KERNELS_SEPARABLE, SCALED_KERNEL, SAME_CORRELATION,
+    MEAN_NAME, VAR_NOISE_NAME,
+)
+
+
+class ParameterEntity(object):
+    """sbo/entities/parameter.py: name, value (np.array), prior, bounds."""
+
+    def __init__(self, name, value, prior=None, bounds=None):
+        self.name = name
+        self.value = np.asarray(value, dtype=float)
+        self.prior = prior
+        self.dimension = len(self.value)
+        self.bounds = bounds
+
+    def set_value(self, value):
+        self.value = np.asarray(value, dtype=float)
+
+    def log_prior(self, value=None):
+        if self.prior is None:
+            return 0.0
+        return self.prior.logprob(self.value if value is None else value)
+
+
+class _KernelParameters(object):
+    """The part of the reference's kernel objects the GP model exposes."""
+
+    def __init__(self, values, dimension):
+        self._values = np.asarray(values, dtype=float)
+        self.dimension = dimension
+        self.dimension_parameters = len(self._values)
+
+    @property
+    def hypers_values_as_array(self):
+        return self._values
+
+    def update_value_parameters(self, params):
+        self._values = np.asarray(params, dtype=float)
+
+
+def kernel_kind(type_kernel, dimensions, **kernel_parameters):
+    """(kind, dim, n_tasks, same_correlation) from the reference's (type_kernel, dimensions)
+    convention (sbo/models/gp_fitting_gaussian.py:88-97; sbo/services/bgo.py:155-165)."""
+    same_corr = bool(kernel_parameters.get(SAME_CORRELATION, False))
+    if type_kernel[0] == PRODUCT_KERNELS_SEPARABLE:
+        if list(type_kernel[1:]) != [MATERN52_NAME, TASKS_KERNEL_NAME]:
+            raise NameError("only Matern52 x Tasks_Kernel products are on the accelerated path")
+        return _cabi.KIND_PRODUCT_TASKS, int(dimensions[1]) + 1, int(dimensions[2]), same_corr
+    if type_kernel[0] == SCALED_KERNEL:
+        if type_kernel[1] != MATERN52_NAME:
+            raise NameError("only a scaled Matern52 is on the accelerated path")
+        return _cabi.KIND_SCALED_MATERN52, int(dimensions[0]), 0, False
+    if type_kernel[0] == MATERN52_NAME:
+        return _cabi.KIND_MATERN52, int(dimensions[0]), 0, False
+    raise NameError(type_kernel[0] + " doesn't exist")
+
+
+class GPFittingGaussian(object):
+
+    _possible_kernels_ = [MATERN52_NAME, TASKS_KERNEL_NAME, PRODUCT_KERNELS_SEPARABLE]
+
+    def __init__(self, type_kernel, training_data, dimensions=None, bounds_domain=None,
+                 kernel_values=None, mean_value=None, var_noise_value=None, thinning=0, n_burning=0,
+                 start_point_sampler=None, max_steps_out=1, data=None, random_seed=None,
+                 type_bounds=None, training_name=None, problem_name=None,
+                 name_model='gp_fitting_gaussian', samples_parameters=None, noise=False,
+                 simplex_domain=None, define_samplers=True, device=None, **kernel_parameters):
+        if random_seed is not None:
+            np.random.seed(random_seed)
+        if bounds_domain is None:
+            raise TypeError("bounds_domain is required")  # reference: len(None) at :151
+        if type_bounds is None:
+            type_bounds = len(bounds_domain) * [0]
+        self.name_model = name_model
+        self.training_name = training_name
+        self.problem_name = problem_name
+        self.noise = noise
+        self.type_kernel = type_kernel
+        self.additional_kernel_parameters = kernel_parameters
+        self.simplex_domain = simplex_domain
+        self.bounds = bounds_domain
+        self.training_data = training_data
+        self.dimension_domain = len(bounds_domain)
+        self.dimensions = dimensions
+        self.type_bounds = type_bounds
+        self.data = self.convert_from_list_to_numpy(training_data if data is None else data)
+        self.thinning = thinning
+        self.max_steps_out = max_steps_out
+        self.n_burning = n_burning
+        self.samples_parameters = []
+        if samples_parameters is not None:
+            self.samples_parameters = [np.array(sample) for sample in samples_parameters]
+        self.start_point_sampler = start_point_sampler
+
+        self._kind, self._dim, self._n_tasks, self._same_corr = kernel_kind(
+            type_kernel, dimensions, **kernel_parameters)
+        if self.data['points'].shape[1] != self._dim:
+            raise ValueError("points have %d columns, kernel expects %d"
+                             % (self.data['points'].shape[1], self._dim))
+        self._device = device
+        self._eng = None
+        self._hb_cache = OrderedDict()
+        self._hb_cache_size = 64
+        self.best_solution = {}
+
+        # model values (reference: set_parameters_kernel, :355-422).  When the data carries
+        # observation noise, or the model is noise free, var_noise = mean = 0 (:363-365).
+        n_params = self._engine().desc.n_params
+        if kernel_values is None or len(kernel_values) == 0:
+            kernel_values = self._default_kernel_values()
+        if len(kernel_values) != n_params:
+            raise ValueError("kernel_values must have %d entries" % n_params)
+        if not self.noise or self.data.get('var_noise') is not None:
+            mean_value = [0.0]
+            var_noise_value = [0.0]
+        if mean_value is None or len(mean_value) == 0:
+            mean_value = [np.mean(self.data['evaluations'])]
+        if var_noise_value is None or len(var_noise_value) == 0:
+            ev = self.data['evaluations']
+            var_noise_value = [np.var(ev)] if len(ev) > 1 else [0.1]
+        self.kernel = _KernelParameters(kernel_values, self._dim)
+        self.mean = ParameterEntity(MEAN_NAME, np.array(mean_value, dtype=float))
+        self.var_noise = ParameterEntity(VAR_NOISE_NAME, np.array(var_noise_value, dtype=float))
+        self.dimension_parameters = n_params + 2
+        self.kernel_values = list(kernel_values)
+        self.mean_value = list(mean_value)
+        self.var_noise_value = list(var_noise_value)
+
+        if type_bounds is not None and len(type_bounds) > 0 and type_bounds[-1] == 1:
+            self.separate_tasks = True
+            self.tasks = self.bounds[-1]
+        else:
+            self.separate_tasks = False
+        self.model_only_x = False
+        if len(self.samples_parameters) == 0:
+            self.samples_parameters.append(self.get_value_parameters_model)
+
+    # -- data plumbing ----------------------------------------------------------------------------
+    @staticmethod
+    def convert_from_list_to_numpy(data_as_list):
+        """:513-535."""
+        data = {}
+        data['points'] = np.array(data_as_list['points'], dtype=float)
+        data['evaluations'] = np.array(data_as_list['evaluations'], dtype=float)
+        vn = data_as_list.get('var_noise')
+        data['var_noise'] = np.array(vn, dtype=float) if vn is not None and len(vn) > 0 else None
+        return data
+
+    def _default_kernel_values(self):
+        """Data-driven defaults in the spirit of define_prior_parameters (kernels/matern52.py:
+        298-326: mean |x - y| / 0.324 per coordinate); tasks / sigma2 defaults as in
+        lib/util_gp_fitting.py:161-240."""
+        pts = self.data['points']
+        dm = self._dim - 1 if self._kind == _cabi.KIND_PRODUCT_TASKS else self._dim
+        ls = []
+        for l in range(dm):
+            x = np.sort(pts[:, l])
+            n = len(x)
+            if n > 1:
+                k = np.arange(n)
+                mean_abs = 2.0 * np.sum((2 * k - n + 1) * x) / (n * n)
+                ls.append(max(mean_abs / 0.324, 1e-10))
+            else:
+                ls.append(1.0)
+        if self._kind == _cabi.KIND_MATERN52:
+            return ls
+        if self._kind == _cabi.KIND_SCALED_MATERN52:
+            ev = self.data['evaluations']
+            return ls + [float(np.var(ev)) if len(ev) > 1 else 1.0]
+        T = self._n_tasks
+        nt = min(T, 2) if self._same_corr else T * (T + 1) // 2
+        return ls + nt * [0.0]
+
+    def _engine(self) -> GPEngine:
+        if self._eng is None:
+            self._eng = GPEngine(self._kind, self._dim, self._n_tasks, self._same_corr,
+                                 device=self._device)
+            self._eng.set_data(self.data['points'], self.data['evaluations'], self.data.get('var_noise'))
+        return self._eng
+
+    def _temp_engine(self, points):
+        eng = GPEngine(self._kind, self._dim, self._n_tasks, self._same_corr, device=self._device)
+        points = np.asarray(points, dtype=float)
+        eng.set_data(points, np.zeros(points.shape[0]))
+        return eng
+
+    def _defaults(self, var_noise, mean, parameters_kernel):
+        if var_noise is None:
+            var_noise = self.var_noise.value[0]
+        if parameters_kernel is None:
+            parameters_kernel = self.kernel.hypers_values_as_array
+        if mean is None:
+            mean = self.mean.value[0]
+        return float(var_noise), float(mean), np.asarray(parameters_kernel, dtype=float)
+
+    def hyper_batch(self, thetas):
+        """Device-resident batch of hyper-samples (cached by value)."""
+        thetas = np.ascontiguousarray(np.asarray(thetas, dtype=float).reshape(
+            -1, self.dimension_parameters))
+        key = thetas.tobytes()
+        hb = self._hb_cache.get(key)
+        if hb is None:
+            hb = self._engine().hypers(thetas)
+            self._hb_cache[key] = hb
+            while len(self._hb_cache) > self._hb_cache_size:
+                self._hb_cache.popitem(last=False)
+        else:
+            self._hb_cache.move_to_end(key)
+        return hb
+
+    def _hb1(self, var_noise, mean, parameters_kernel):
+        return self.hyper_batch(np.concatenate([[var_noise, mean], parameters_kernel]))
+
+    @staticmethod
+    def _raise_info(info):
+        if info == -1:
+            raise linalg.LinAlgError("not positive definite matrix")
+        if info != 0:
+            raise linalg.LinAlgError("not positive definite, even with jitter.")
+
+    # -- model parameters -------------------------------------------------------------------------
+    @property
+    def get_value_parameters_model(self):
+        """:645-655."""
+        return np.concatenate([self.var_noise.value, self.mean.value,
+                               self.kernel.hypers_values_as_array])
+
+    def update_value_parameters(self, vector):
+        """:1040-1051."""
+        self.var_noise.set_value(vector[0:1])
+        self.mean.set_value(vector[1:2])
+        self.kernel.update_value_parameters(vector[2:])
+
+    def add_points_evaluations(self, point, evaluation, var_noise_eval=None):
+        """:492-511: append data, invalidate every cached factor."""
+        self.data['points'] = np.append(self.data['points'], point, axis=0)
+        self.data['evaluations'] = np.append(self.data['evaluations'], evaluation)
+        if var_noise_eval is not None:
+            self.data['var_noise'] = np.append(self.data['var_noise'], var_noise_eval)
+        self.clean_cache()
+        self._eng = None
+
+    def clean_cache(self):
+        self._hb_cache = OrderedDict()
+        self.best_solution = {}
+
+    # -- kernel matrices ---------------------------------------------------------------------------
+    def evaluate_cov(self, points, parameters_kernel):
+        """:701-731 -> np.array(n x n)."""
+        eng = self._temp_engine(points)
+        hb = eng.hypers(np.concatenate([[0.0, 0.0], np.asarray(parameters_kernel, dtype=float)]))
+        return hb.cov().cpu().numpy()[0]
+
+    def evaluate_grad_cov(self, parameters_kernel, points):
+        """:800-829 -> {i: np.array(n x n)}."""
+        eng = self._temp_engine(points)
+        hb = eng.hypers(np.concatenate([[0.0, 0.0], np.asarray(parameters_kernel, dtype=float)]))
+        dK = hb.grad_cov().cpu().numpy()[0]
+        return {i: dK[i] for i in range(dK.shape[0])}
+
+    def evaluate_cross_cov(self, points_1, points_2, parameters_kernel):
+        """:1107-1143 -> np.array(n x m)."""
+        eng = self._temp_engine(points_2)
+        hb = eng.hypers(np.concatenate([[0.0, 0.0], np.asarray(parameters_kernel, dtype=float)]))
+        return hb.cross_cov(points_1).cpu().numpy()[0]
+
+    def evaluate_grad_cross_cov_respect_point(self, points_1, points_2, parameters_kernel):
+        """:1145-1170 -> np.array(m x k) (zero column for a task coordinate)."""
+        eng = self._temp_engine(points_2)
+        hb = eng.hypers(np.concatenate([[0.0, 0.0], np.asarray(parameters_kernel, dtype=float)]))
+        _, dKP = hb.cross_cov(points_1, grad=True)
+        g = dKP.cpu().numpy()[0, 0].T  # m x dim_m
+        if g.shape[1] < self._dim:
+            g = np.concatenate([g, np.zeros((g.shape[0], self._dim - g.shape[1]))], axis=1)
+        return g
+
+    # -- factorisation, likelihood ------------------------------------------------------------------
+    def _chol_cov_including_noise(self, var_noise, parameters_kernel, historical_points=None,
+                                  cache=True, clear_cache=True):
+        """:733-770 -> (chol, cov)."""
+        hb = self._hb1(var_noise, 0.0 if self.mean is None else self.mean.value[0], parameters_kernel)
+        cov = hb.cov(add_noise=True).cpu().numpy()[0]
+        hb.factorize(max_tries=7)
+        self._raise_info(int(hb.info[0]))
+        return hb.L.cpu().numpy()[0], cov
+
+    def log_likelihood(self, var_noise, mean, parameters_kernel):
+        """:772-798 -> float."""
+        hb = self._hb1(var_noise, mean, parameters_kernel)
+        hb.factorize(max_tries=7)
+        self._raise_info(int(hb.info[0]))
+        return float(hb.log_likelihood().cpu().numpy()[0])
+
+    def grad_log_likelihood(self, var_noise, mean, parameters_kernel):
+        """:876-897 -> np.array(2 + p): [d var_noise, d mean, d kernel params]."""
+        hb = self._hb1(var_noise, mean, parameters_kernel)
+        hb.factorize(max_tries=7)
+        self._raise_info(int(hb.info[0]))
+        return hb.grad_log_likelihood().cpu().numpy()[0]
+
+    def grad_log_likelihood_dict(self, var_noise, mean, parameters_kernel):
+        g = self.grad_log_likelihood(var_noise, mean, parameters_kernel)
+        return {'var_noise': g[0], 'mean': g[1], 'kernel_params': g[2:]}
+
+    def log_likelihood_batch(self, thetas):
+        """Batched extension: log-likelihood of S hyper-samples -> np.array(S); -inf where the
+        factorisation failed (objective_llh convention, :946-960)."""
+        hb = self.hyper_batch(thetas)
+        hb.factorize(max_tries=7)
+        llh = hb.log_likelihood().cpu().numpy()
+        llh[hb.info != 0] = -np.inf
+        return llh
+
+    def grad_log_likelihood_batch(self, thetas):
+        hb = self.hyper_batch(thetas)
+        hb.factorize(max_tries=7)
+        return hb.grad_log_likelihood().cpu().numpy()
+
+    def _cholesky_solve_vectors_for_posterior(self, var_noise, mean, parameters_kernel,
+                                              historical_points=None, historical_evaluations=None,
+                                              cache=True, clear_cache=True):
+        """:1202-1251 -> {'chol', 'solve'}."""
+        hb = self._hb1(var_noise, mean, parameters_kernel)
+        hb.factorize(max_tries=7)
+        self._raise_info(int(hb.info[0]))
+        return {'chol': hb.L.cpu().numpy()[0], 'solve': hb.alpha.cpu().numpy()[0]}
+
+    # -- posterior ------------------------------------------------------------------------------------
+    def compute_posterior_parameters(self, points, var_noise=None, mean=None,
+                                     parameters_kernel=None, only_mean=False):
+        """:1253-1311 -> {'mean': np.array(n), 'cov': np.array(n x n)}."""
+        var_noise, mean, parameters_kernel = self._defaults(var_noise, mean, parameters_kernel)
+        hb = self._hb1(var_noise, mean, parameters_kernel)
+        hb.factorize(max_tries=7)
+        self._raise_info(int(hb.info[0]))
+        points = np.asarray(points, dtype=float)
+        if only_mean:
+            post = hb.posterior(points, var=False)
+            return {'mean': post['mean'].cpu().numpy()[0], 'cov': None}
+        if points.shape[0] == 1:
+            post = hb.posterior(points, var=True)
+            return {'mean': post['mean'].cpu().numpy()[0],
+                    'cov': post['var'].cpu().numpy()[0].reshape(1, 1)}
+        # full posterior covariance: k(P,P) - k* Sigma^-1 k*^T
+        KP = hb.cross_cov(points)
+        sol = hb.solve(KP.clone())
+        mean_v = hb.posterior(points, var=False)['mean'].cpu().numpy()[0]
+        kpp = self.evaluate_cov(points, parameters_kernel)
+        cov = kpp - (KP[0] @ sol[0].T).cpu().numpy()
+        return {'mean': mean_v, 'cov': cov}
+
+    def gradient_posterior_parameters(self, point, var_noise=None, mean=None,
+                                      parameters_kernel=None, parallel=True, only_mean=False):
+        """:1313-1353 -> {'mean': np.array(k), 'cov': np.array(1 x k)}."""
+        var_noise, mean, parameters_kernel = self._defaults(var_noise, mean, parameters_kernel)
+        hb = self._hb1(var_noise, mean, parameters_kernel)
+        hb.factorize(max_tries=7)
+        self._raise_info(int(hb.info[0]))
+        post = hb.posterior(np.asarray(point, dtype=float), var=True, grad=True)
+        gm = post['grad_mean'].cpu().numpy()[0, 0]
+        gv = post['grad_var'].cpu().numpy()[0, 0]
+        pad = self._dim - gm.shape[0]
+        if pad > 0:
+            gm = np.concatenate([gm, np.zeros(pad)])
+            gv = np.concatenate([gv, np.zeros(pad)])
+        return {'mean': gm, 'cov': gv.reshape(1, -1)}
+
+    def get_historical_best_solution(self, var_noise=None, mean=None, parameters_kernel=None,
+                                     noisy_evaluations=False):
+        """:1590-1626."""
+        var_noise, mean, parameters_kernel = self._defaults(var_noise, mean, parameters_kernel)
+        index = (var_noise, mean, tuple(parameters_kernel))
+        if index in self.best_solution:
+            return self.best_solution[index]
+        if not noisy_evaluations:
+            evaluations = self.data['evaluations']
+        else:
+            evaluations = self.compute_posterior_parameters(
+                self.data['points'], var_noise, mean, parameters_kernel, only_mean=True)['mean']
+        best = np.max(evaluations)
+        self.best_solution[index] = best
+        return best
+
+    def log_prob_parameters(self, parameters):
+        """:1543-1567 (priors are host-side; without priors this is the log-likelihood)."""
+        lp = 0.0
+        for par, sl in ((self.var_noise, slice(0, 1)), (self.mean, slice(1, 2))):
+            lp += par.log_prior(parameters[sl])
+        if not np.isinf(lp):
+            lp += self.log_likelihood(parameters[0], parameters[1], parameters[2:])
+        return lp

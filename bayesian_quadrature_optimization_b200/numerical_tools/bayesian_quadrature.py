@@ -1,0 +1,332 @@
+"""BayesianQuadrature: host-side mirror of sbo/numerical_tools/bayesian_quadrature.py.
+
+GP on G(x) = E_W[F(x, W)].  The expectation over W is a finite (optionally weighted) sum over
+tasks or a Monte-Carlo mean over M = 10 W samples.  The reference draws fresh `gamma.rvs` inside
+every call (sbo/lib/expectations.py:105); here the samples are drawn ONCE per object with the
+same scipy call (`resample_w`), kept as `w_sets[n_wsets][M][d_w]`, uploaded to the GPU, and every
+evaluation names the set it uses -- the explicit-randomness contract of SURVEY.md section 7.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import numpy as np
+import torch
+from scipy.stats import gamma
+
+from .. import _cabi
+from ..engine import BQEngine
+from ..lib.constant import (
+    UNIFORM_FINITE, WEIGHTED_UNIFORM_FINITE, GAMMA, EXPONENTIAL, TASKS, BAYESIAN_QUADRATURE,
+    N_SAMPLES_W,
+)
+
+
+class BayesianQuadrature(object):
+
+    def __init__(self, gp_model, x_domain, distribution, parameters_distribution=None,
+                 model_only_x=False, tasks=None, n_w_sets=1):
+        self.gp = gp_model
+        self.simplex_domain = self.gp.simplex_domain
+        self.name_model = BAYESIAN_QUADRATURE
+        if parameters_distribution == {}:
+            parameters_distribution = None
+        if parameters_distribution is None and distribution == UNIFORM_FINITE:
+            parameters_distribution = {TASKS: self.gp._n_tasks}
+        self.parameters_distribution = parameters_distribution
+        self.dimension_domain = self.gp.dimension_domain
+        self.x_domain = list(x_domain)
+        if self.x_domain != list(range(len(self.x_domain))):
+            raise ValueError("the accelerated path needs x_domain = [0, ..., d_x - 1]")
+        self.w_domain = [i for i in range(self.gp.dimension_domain) if i not in self.x_domain]
+        self.distribution = distribution
+        self.weights = None
+        self.task_continue = False
+        if distribution == UNIFORM_FINITE:
+            self.n_tasks = self.parameters_distribution.get(TASKS)
+        elif distribution == WEIGHTED_UNIFORM_FINITE:
+            self.weights = np.array(self.parameters_distribution['weights'], dtype=float)
+            self.n_tasks = len(self.weights)
+            self.task_continue = True
+            if self.parameters_distribution.get('n_samples'):
+                raise NotImplementedError("sub-sampled finite expectations are not accelerated")
+        elif distribution in (GAMMA, EXPONENTIAL):
+            pass
+        else:
+            raise NameError("distribution %s is not on the accelerated path" % distribution)
+        finite = distribution in (UNIFORM_FINITE, WEIGHTED_UNIFORM_FINITE)
+        if finite != (self.gp._kind == _cabi.KIND_PRODUCT_TASKS):
+            raise ValueError("finite W needs the Matern52 x Tasks product kernel and vice versa")
+
+        self.var_noise = None
+        if self.gp.noise and self.gp.data.get('var_noise') is not None:
+            self.var_noise = np.mean(self.gp.data.get('var_noise'))  # :153-155
+
+        self.separate_tasks = False
+        if self.gp.type_bounds != [] and self.gp.type_bounds[-1] == 1 and not model_only_x:
+            self.separate_tasks = True
+        self.model_only_x = model_only_x
+        if model_only_x or self.separate_tasks:
+            self.type_bounds = [self.gp.type_bounds[i] for i in self.x_domain]
+            self.bounds = [self.gp.bounds[i] for i in self.x_domain]
+        else:
+            self.type_bounds = list(self.gp.type_bounds)
+            self.bounds = [list(b) for b in self.gp.bounds]
+        if not model_only_x and self.task_continue:
+            self.type_bounds = list(self.gp.type_bounds)
+            self.bounds = [list(b) for b in self.gp.bounds]
+        self.tasks = self.gp.bounds[-1] if (self.gp.bounds != [] and self.separate_tasks) else []
+        self.type_kernel = self.gp.type_kernel
+
+        self.w_sets = None
+        if not finite:
+            self.resample_w(n_w_sets)
+        self._bq_cache = OrderedDict()
+        self.optimal_solutions = {}
+        self.max_mean = {}
+        self.best_solution = {}
+        self.args_handler = ()
+
+    # -- explicit W samples ------------------------------------------------------------------------
+    def resample_w(self, n_w_sets=1, n_samples=N_SAMPLES_W):
+        """Draw the W sample sets with the reference's own sampler call
+        (gamma.rvs(a, scale=scale, size=(n_samples, dim_w)), sbo/lib/expectations.py:93-105)."""
+        a = self.parameters_distribution['a'][0]
+        scale = self.parameters_distribution['scale'][0]
+        dim_w = len(self.w_domain)
+        self.w_sets = np.stack([gamma.rvs(a, scale=scale, size=(n_samples, dim_w))
+                                for _ in range(n_w_sets)])
+        self._bq_cache = OrderedDict()
+
+    def set_w_sets(self, w_sets):
+        w_sets = np.asarray(w_sets, dtype=float)
+        self.w_sets = w_sets[None] if w_sets.ndim == 2 else w_sets
+        self._bq_cache = OrderedDict()
+
+    # -- device objects ------------------------------------------------------------------------------
+    def bounds_x(self):
+        return [self.gp.bounds[i] for i in self.x_domain]
+
+    def engine_for(self, thetas) -> BQEngine:
+        hb = self.gp.hyper_batch(thetas)
+        key = id(hb)
+        bq = self._bq_cache.get(key)
+        if bq is None or bq.hb is not hb:
+            hb.factorize(max_tries=7)
+            for s in range(hb.S):
+                self.gp._raise_info(int(hb.info[s]))
+            bx = self.bounds_x()
+            lower = np.array([b[0] for b in bx], dtype=float)
+            upper = np.array([b[-1] for b in bx], dtype=float)
+            bq = BQEngine(hb, len(self.x_domain), weights=self.weights, wsets=self.w_sets,
+                          lower=lower, upper=upper, bq_var_noise=self.var_noise)
+            self._bq_cache[key] = bq
+            while len(self._bq_cache) > 8:
+                self._bq_cache.popitem(last=False)
+        return bq
+
+    def _theta(self, var_noise, mean, parameters_kernel):
+        var_noise, mean, parameters_kernel = self.gp._defaults(var_noise, mean, parameters_kernel)
+        return np.concatenate([[var_noise, mean], parameters_kernel])
+
+    def clean_cache(self):
+        self._bq_cache = OrderedDict()
+        self.gp.clean_cache()
+
+    # -- expectations of the kernel ------------------------------------------------------------------
+    def _new_points(self, point, w_set=0):
+        """(x, W values): uniform_finite / gamma_expect build the same array
+        (sbo/lib/expectations.py:44-50, 100-106)."""
+        point = np.asarray(point, dtype=float).reshape(1, -1)
+        if self.w_sets is not None:
+            random = self.w_sets[w_set]
+        else:
+            random = np.arange(self.n_tasks, dtype=float).reshape(-1, 1)
+        m = random.shape[0]
+        new_points = np.zeros((m, len(self.w_domain) + point.shape[1]))
+        new_points[:, self.x_domain] = np.repeat(point, m, axis=0)
+        new_points[:, self.w_domain] = random
+        return new_points
+
+    def _average(self, values):
+        """np.average(values, axis=0, weights) / np.mean(values, axis=0) on the device."""
+        if self.weights is None:
+            return values.mean(dim=0)
+        w = torch.as_tensor(self.weights, dtype=values.dtype, device=values.device)
+        shape = [-1] + [1] * (values.dim() - 1)
+        return (values * w.reshape(shape)).sum(dim=0) / w.sum()
+
+    def evaluate_quadrature_cross_cov(self, point, points_2, parameters_kernel, w_set=0):
+        """B(x, z_j): :308-334 -> np.array(m)."""
+        eng = self.gp._temp_engine(points_2)
+        hb = eng.hypers(np.concatenate([[0.0, 0.0], np.asarray(parameters_kernel, dtype=float)]))
+        vals = hb.cross_cov(self._new_points(point, w_set))[0]
+        return self._average(vals).cpu().numpy()
+
+    def evaluate_grad_quadrature_cross_cov(self, point, points_2, parameters_kernel, w_set=0):
+        """grad_x B(x, z_j): :336-362 -> np.array(k x m)."""
+        eng = self.gp._temp_engine(points_2)
+        hb = eng.hypers(np.concatenate([[0.0, 0.0], np.asarray(parameters_kernel, dtype=float)]))
+        _, dKP = hb.cross_cov(self._new_points(point, w_set), grad=True)
+        return self._average(dKP[0])[: len(self.x_domain)].cpu().numpy()
+
+    def evaluate_grad_quadrature_cross_cov_resp_candidate(self, candidate_point, points,
+                                                          parameters_kernel, w_set=0):
+        """grad_c B(x_p, c): :388-415 -> np.array(k x m)."""
+        candidate_point = np.asarray(candidate_point, dtype=float).reshape(1, -1)
+        points = np.asarray(points, dtype=float)
+        out = np.zeros((candidate_point.shape[1], points.shape[0]))
+        for i in range(points.shape[0]):
+            new_points = self._new_points(points[i:i + 1, :], w_set)
+            eng = self.gp._temp_engine(new_points)
+            hb = eng.hypers(np.concatenate([[0.0, 0.0], np.asarray(parameters_kernel, dtype=float)]))
+            _, dKP = hb.cross_cov(candidate_point, grad=True)  # [1][1][dim_m][M]
+            g = self._average(dKP[0, 0].T).cpu().numpy()
+            out[: g.shape[0], i] = g
+        return out
+
+    def evaluate_quadrate_cov(self, point, parameters_kernel, w_set=0, w_set_2=0):
+        """E_W E_W' k: :282-306 -> float (finite W: exact weighted double sum)."""
+        p1 = self._new_points(point, w_set)
+        p2 = self._new_points(point, w_set_2)
+        vals = torch.as_tensor(self.gp.evaluate_cross_cov(p1, p2, parameters_kernel))
+        if self.weights is None:
+            return float(vals.mean())
+        w = torch.as_tensor(self.weights, dtype=vals.dtype)
+        return float((vals * torch.outer(w, w)).sum() / (w.sum() ** 2))
+
+    # -- posterior of G ------------------------------------------------------------------------------
+    def _dummy_candidate(self):
+        return self.gp.data['points'][0:1, :]
+
+    def compute_posterior_parameters(self, points, var_noise=None, mean=None,
+                                     parameters_kernel=None, historical_points=None,
+                                     historical_evaluations=None, only_mean=False, cache=True,
+                                     parallel=False, w_set=0):
+        """:449-537 -> {'mean': np.array(t), 'cov': float}."""
+        theta = self._theta(var_noise, mean, parameters_kernel)
+        points = np.asarray(points, dtype=float).reshape(-1, len(self.x_domain))
+        bq = self.engine_for(theta)
+        ub = bq.setup(self._dummy_candidate())
+        t = points.shape[0]
+        out = bq.sample_ab(ub, points, np.zeros(t, dtype=np.int32),
+                           np.full(t, w_set, dtype=np.int32) if self.w_sets is not None else None)
+        mu_n = out[:, 0].cpu().numpy()
+        if only_mean:
+            return {'mean': mu_n, 'cov': None}
+        B = torch.as_tensor(self.evaluate_quadrature_cross_cov(
+            points[0:1, :], self.gp.data['points'], theta[2:], w_set), device=bq.eng.device)
+        sol = bq.hb.solve(B.reshape(1, 1, -1).clone())
+        cov = self.evaluate_quadrate_cov(points[0:1, :], theta[2:], w_set, w_set) - \
+            float((B * sol[0, 0]).sum())
+        return {'mean': mu_n, 'cov': cov}
+
+    def gradient_posterior_mean(self, point, var_noise=None, mean=None, parameters_kernel=None,
+                                historical_points=None, historical_evaluations=None, cache=True,
+                                w_set=0):
+        """:539-579 -> np.array(k)."""
+        theta = self._theta(var_noise, mean, parameters_kernel)
+        bq = self.engine_for(theta)
+        ub = bq.setup(self._dummy_candidate())
+        dx = len(self.x_domain)
+        out = bq.sample_ab(ub, np.asarray(point, dtype=float).reshape(1, dx),
+                           np.zeros(1, dtype=np.int32),
+                           np.full(1, w_set, dtype=np.int32) if self.w_sets is not None else None)
+        return out[0, 2:2 + dx].cpu().numpy()
+
+    def objective_posterior_mean(self, point, var_noise=None, mean=None, parameters_kernel=None):
+        point = np.asarray(point, dtype=float).reshape((1, -1))
+        return self.compute_posterior_parameters(point, var_noise=var_noise, mean=mean,
+                                                 parameters_kernel=parameters_kernel,
+                                                 only_mean=True)['mean']
+
+    def grad_posterior_mean(self, point, var_noise=None, mean=None, parameters_kernel=None):
+        point = np.asarray(point, dtype=float).reshape((1, -1))
+        return self.gradient_posterior_mean(point, var_noise=var_noise, mean=mean,
+                                            parameters_kernel=parameters_kernel)
+
+    # -- per-candidate quantities --------------------------------------------------------------------
+    def get_parameters_for_samples(self, cache, candidate_point, parameters_kernel, var_noise, mean,
+                                   clear_cache=True):
+        """:1074-1145."""
+        theta = self._theta(var_noise, mean, parameters_kernel)
+        bq = self.engine_for(theta)
+        ub = bq.setup(np.asarray(candidate_point, dtype=float).reshape(1, -1))
+        n = self.gp.data['points'].shape[0]
+        rows = 1 + bq.eng.desc.dim_m
+        gamma_v = ub.G.reshape(1, 1, rows, n)[0, 0, 0].cpu().numpy().reshape(n, 1)
+        s2 = ub.R.reshape(1, 1, rows, n)[0, 0, 0]
+        if bq.is_product:
+            s2 = s2 / bq.qt[0][bq.hb.tid.long()]
+        return {
+            'gamma': gamma_v, 'solve_2': s2.cpu().numpy().reshape(n, 1),
+            'denominator': ub.den.cpu().numpy().reshape(1),
+            'chol': bq.hb.L.cpu().numpy()[0], 'solve': bq.hb.alpha.cpu().numpy()[0],
+            'parameters_kernel': theta[2:], 'var_noise': theta[0], 'mean': theta[1],
+        }
+
+    def _ab(self, point, candidate_point, theta, w_set=0):
+        bq = self.engine_for(theta)
+        ub = bq.setup(np.asarray(candidate_point, dtype=float).reshape(1, -1))
+        dx = len(self.x_domain)
+        pts = np.asarray(point, dtype=float).reshape(-1, dx)
+        t = pts.shape[0]
+        out = bq.sample_ab(ub, pts, np.zeros(t, dtype=np.int32),
+                           np.full(t, w_set, dtype=np.int32) if self.w_sets is not None else None)
+        return out.cpu().numpy()
+
+    def compute_parameters_for_sample(self, point, candidate_point, var_noise=None, mean=None,
+                                      parameters_kernel=None, cache=True, n_threads=0,
+                                      clear_cache=True, w_set=0):
+        """:1148-1191 -> {'a': np.array(1), 'b': np.array(1x1)}."""
+        out = self._ab(point, candidate_point, self._theta(var_noise, mean, parameters_kernel), w_set)
+        return {'a': out[0:1, 0], 'b': out[0:1, 1:2]}
+
+    def compute_gradient_parameters_for_sample(self, point, candidate_point, var_noise=None,
+                                               mean=None, parameters_kernel=None, cache=True,
+                                               w_set=0):
+        """:1193-1239 -> {'a': np.array(n), 'b': np.array(n)}."""
+        out = self._ab(point, candidate_point, self._theta(var_noise, mean, parameters_kernel), w_set)
+        dx = len(self.x_domain)
+        return {'a': out[0, 2:2 + dx], 'b': out[0, 2 + dx:2 + 2 * dx]}
+
+    def gradient_vector_b(self, candidate_point, points, var_noise=None, mean=None,
+                          parameters_kernel=None, cache=True, keep_indexes=None, parallel=True,
+                          monte_carlo=False, n_threads=0, w_set=0):
+        """:1447-1519 -> np.array(n x m), or the object np.nan when den^2 == 0."""
+        theta = self._theta(var_noise, mean, parameters_kernel)
+        bq = self.engine_for(theta)
+        cand = np.asarray(candidate_point, dtype=float).reshape(1, -1)
+        ub = bq.setup(cand)
+        pts = np.asarray(points, dtype=float).reshape(1, -1, len(self.x_domain))
+        ws = None
+        if self.w_sets is not None:
+            ws = np.full(pts.shape[1], w_set, dtype=np.int32)
+        out, is_nan = bq.grad_vector_b(ub, pts, ws)
+        if int(is_nan.cpu().numpy()[0]):
+            return np.nan
+        g = out[0].cpu().numpy()
+        pad = cand.shape[1] - g.shape[1]
+        if pad > 0:
+            g = np.concatenate([g, np.zeros((g.shape[0], pad))], axis=1)
+        return g
+
+    def compute_posterior_parameters_kg(self, points, candidate_point, var_noise=None, mean=None,
+                                        parameters_kernel=None, cache=True, parallel=True,
+                                        n_threads=0, w_set=0):
+        """:1376-1445 -> {'a': np.array(n), 'b': np.array(n)}."""
+        out = self._ab(points, candidate_point, self._theta(var_noise, mean, parameters_kernel), w_set)
+        return {'a': out[:, 0], 'b': out[:, 1]}
+
+    def get_historical_best_solution(self, var_noise=None, mean=None, parameters_kernel=None,
+                                     noisy_evaluations=False):
+        """:1542-1577: max posterior mean of G over the x of the training points."""
+        theta = self._theta(var_noise, mean, parameters_kernel)
+        index = (theta[0], theta[1], tuple(theta[2:]))
+        if index in self.best_solution:
+            return self.best_solution[index]
+        pts = self.gp.data['points'][:, self.x_domain]
+        best = np.max(self.compute_posterior_parameters(pts, theta[0], theta[1], theta[2:],
+                                                        only_mean=True)['mean'])
+        self.best_solution[index] = best
+        return best

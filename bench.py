@@ -1,0 +1,481 @@
+#!/usr/bin/env python
+"""bench.py -- BQO acquisition-plus-gradient throughput on the north-star configuration.
+
+Workload (SURVEY.md section 8d, config C3 = BASELINE.json configs[2], the one the metric is
+quoted on): synthetic GP, Scaled(Matern52) over d = 6 columns (d_x = 4, d_w = 2), n = 2048
+training points, S = 20 hyper-samples, Z = 100 standard-normal samples, M_W = 10 gamma W samples
+per quadrature, 10 000 candidates processed in batches.
+
+A "step" is one pass of the hot path over one batch of CAND_PER_STEP candidates: stage B
+(gamma / grad gamma rows, triangular solves against the 20 resident factors, denominators),
+stage C (inner maximisation of a(x) + Z b(x) for every (candidate, hyper-sample, Z), gradient
+of b at the maximisers) and the Monte-Carlo reduction -> acquisition value and gradient per
+candidate.  Unit = one (candidate, hyper-sample) pair including all Z samples.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle port (the reference is
+pure Python and cannot travel to the GPU box) on the host cores with a process pool, like the
+reference's own mp.Pool.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_TRAIN, DX, DW = 2048, 4, 2
+N_HYPER, N_Z, M_W, N_WSETS = 20, 100, 10, 8
+N_CAND_TOTAL = 10000
+CAND_PER_STEP = 37          # 37 x 20 = 740 units = 5 per SM
+N_RESTARTS_MC, MAXITER_MC, FACTR_MC = 5, 10, 1e12  # bgo() defaults, sbo/services/bgo.py:43-44
+Z_PER_CTA = 25
+
+
+def make_workload(seed_shift=0):
+    """seeds fixed so CPU and GPU arms see identical arrays."""
+    rng = np.random.RandomState(0)
+    x = rng.uniform(0, 1, (N_TRAIN, DX))
+    w = rng.gamma(2.0, 1.0, (N_TRAIN, DW))
+    pts = np.concatenate([x, w], 1)
+    y = np.sin(pts.sum(1)) + 0.01 * rng.normal(0, 1, N_TRAIN)
+    r2 = np.random.RandomState(2)
+    base = np.array([1e-4, 0.0] + DX * [0.3] + DW * [2.0] + [1.0])
+    thetas = base[None, :] * (1.0 + 0.05 * r2.normal(0, 1, (N_HYPER, base.size)))
+    thetas[:, 1] = 0.05 * r2.normal(0, 1, N_HYPER)
+    zs = np.random.RandomState(3).normal(0, 1, N_Z)
+    wsets = np.random.RandomState(4).gamma(2.0, 1.0, (N_WSETS, M_W, DW))
+    r5 = np.random.RandomState(5 + seed_shift)
+    cands = np.concatenate([r5.uniform(0, 1, (N_CAND_TOTAL, DX)),
+                            r5.gamma(2.0, 1.0, (N_CAND_TOTAL, DW))], 1)
+    starts = np.random.RandomState(6).uniform(0, 1, (N_RESTARTS_MC + 1, DX))
+    return dict(pts=pts, y=y, thetas=thetas, zs=zs, wsets=wsets, cands=cands, starts=starts,
+                lower=np.zeros(DX), upper=np.ones(DX))
+
+
+def f_eval_flops():
+    """Algorithmic FP64 flops of one evaluation of (a, b, grad a, grad b), SURVEY 8d stage C:
+    M_W n (2d+10) + M_W n (3 d_x + 8) + 4 n (1 + d_x)."""
+    d = DX + DW
+    return M_W * N_TRAIN * (2 * d + 10) + M_W * N_TRAIN * (3 * DX + 8) + 4 * N_TRAIN * (1 + DX)
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [t.strip() for t in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    smax.append(float(f[2]))
+                except ValueError:
+                    continue
+                for nm, val in zip(names, f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(np.max(smax))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+def _cpu_unit_worker(args):
+    """One (candidate, hyper-sample) unit on the CPU oracle with z_cpu Z samples."""
+    os.environ["OMP_NUM_THREADS"] = "1"
+    cand_idx, hyper_idx, z_cpu = args
+    from oracle import bqo_oracle as orc
+    wl = _WL
+    spec = orc.KernelSpec(orc.SCALED_MATERN52, DX + DW)
+    gp = orc.OracleGP(spec, wl["pts"], wl["y"])
+    bq = orc.OracleBQ(gp, list(range(DX)), orc.GAMMA)
+    sbo = orc.OracleSBO(bq, [(0.0, 1.0)] * DX)
+    th = wl["thetas"][hyper_idx]
+    t0 = time.time()
+    gp.chol_solve(th[0], th[1], th[2:])  # factor cached per theta, as in the reference
+    t_factor = time.time() - t0
+    t0 = time.time()
+    res = sbo.evaluate_mc_bayesian_candidate_points_no_restarts(
+        wl["cands"][cand_idx:cand_idx + 1], [th], wl["zs"][:z_cpu], wl["starts"], w=wl["wsets"][0],
+        compute_gradient=True, factr=FACTR_MC, maxiter=MAXITER_MC)
+    return time.time() - t0, t_factor, float(res["evaluations"][0])
+
+
+_WL = None
+
+
+def cpu_baseline(wl, z_cpu=2, units=None, cores=None):
+    """CPU oracle timed on the host cores: `units` independent units in a process pool (the
+    reference's own parallelism is an mp.Pool over units, sbo/lib/parallel.py:42-47), each with
+    z_cpu of the Z = 100 samples; value is extrapolated linearly in Z to Z = 100."""
+    import multiprocessing as mp
+    global _WL
+    _WL = wl
+    if cores is None:
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except Exception:
+            cores = os.cpu_count() or 1
+    cores = max(1, min(cores, 32))
+    if units is None:
+        units = cores
+    jobs = [(i % 4, i % N_HYPER, z_cpu) for i in range(units)]
+    t0 = time.time()
+    if cores > 1:
+        ctx = mp.get_context("fork")
+        with ctx.Pool(processes=cores) as pool:
+            res = pool.map(_cpu_unit_worker, jobs)
+    else:
+        res = [_cpu_unit_worker(j) for j in jobs]
+    wall = time.time() - t0
+    units_per_s_zcpu = units / wall
+    value = units_per_s_zcpu * z_cpu / float(N_Z)
+    return {
+        "value": value, "unit": "units/s", "cores": cores, "kind": "port",
+        "sample": "%d units (1 candidate x 1 hyper-sample each) with Z=%d of %d Z samples, n=%d, "
+                  "R=%d starts + 16 vertices, scipy L-BFGS-B maxiter=%d; %.1f s wall; value = "
+                  "units/s extrapolated linearly in Z to Z=%d (raw %.4f units/s at Z=%d)"
+                  % (units, z_cpu, N_Z, N_TRAIN, N_RESTARTS_MC + 1, MAXITER_MC, wall, N_Z,
+                     units_per_s_zcpu, z_cpu),
+        "wall_s": wall,
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = make_workload()
+    total_steps = args.warmup + args.steps
+    vals = []
+    t_all = time.time()
+    base = None
+    for s in range(total_steps):
+        base = cpu_baseline(wl, z_cpu=1)
+        if s >= args.warmup:
+            vals.append(base)
+        if time.time() - t_all > 240:
+            break
+    if not vals:
+        vals = [base]
+    value = float(np.mean([v["value"] for v in vals]))
+    ms = float(np.mean([v["wall_s"] for v in vals])) * 1e3
+    cb = dict(vals[-1])
+    cb["value"] = value
+    cb.pop("wall_s", None)
+    line = {
+        "impl": "reference", "metric": "bqo_acq_grad_units_per_s", "value": value, "unit": "units/s",
+        "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": workload_config(),
+        "cpu_baseline": cb,
+        "e2e": {"value": value, "unit": "units/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config():
+    return {
+        "workload": "C3 synthetic GP: Scaled(Matern52) d=6 (d_x=4, d_w=2, gamma W), n=2048, "
+                    "S=20 hyper-samples, Z=100, M_W=10, 10k candidates in batches",
+        "n_training": N_TRAIN, "d_x": DX, "d_w": DW, "hyper_samples": N_HYPER, "z_samples": N_Z,
+        "w_samples": M_W, "candidates_per_step": CAND_PER_STEP,
+        "units_per_step": CAND_PER_STEP * N_HYPER,
+        "inner_maximiser": "R=%d starts + 16 vertices, maxiter=%d, factr=%g"
+                           % (N_RESTARTS_MC + 1, MAXITER_MC, FACTR_MC),
+        "l2": "256 MiB buffer rewritten between steps (L2 flush); per-step inputs (20 factors, "
+              "640 MB) exceed L2 as well",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+
+    from bayesian_quadrature_optimization_b200 import _cabi, engine as E
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    wl = make_workload()
+    # weak scaling: every rank owns its own slice of the candidate list and a full copy of the
+    # training data and of the S factors; the only exchange is the final argmax (one all_gather).
+    eng = E.GPEngine(_cabi.KIND_SCALED_MATERN52, DX + DW, device=dev)
+    eng.set_data(wl["pts"], wl["y"])
+
+    # FP64 peak of this GPU, measured now (MEASURED_PEAKS.json has no FP64 entry)
+    lib = eng.lib
+    ms, fl = C.c_double(), C.c_double()
+    _cabi.check(lib.bqo_fp64_peak_probe(0, 100000, C.byref(ms), C.byref(fl)), "probe")
+    dfma_peak = fl.value / (ms.value * 1e-3) / 1e12
+    _cabi.check(lib.bqo_fp64_peak_probe(1, 100000, C.byref(ms), C.byref(fl)), "probe")
+    dmma_peak = fl.value / (ms.value * 1e-3) / 1e12
+
+    # ---- stage A (once per BO iteration; secondary metric: log-likelihood + gradient per s) ----
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage_a_ms = []
+    for rep in range(3):
+        hb = eng.hypers(wl["thetas"])
+        torch.cuda.synchronize()
+        ev0.record()
+        hb.factorize()
+        llh = hb.log_likelihood()
+        gll = hb.grad_log_likelihood()
+        ev1.record()
+        torch.cuda.synchronize()
+        stage_a_ms.append(ev0.elapsed_time(ev1))
+    stage_a = float(np.min(stage_a_ms[1:]))
+    assert np.all(hb.info == 0)
+    n = N_TRAIN
+    p = DX + DW + 1
+    f_ll = n * n * (2 * (DX + DW) + 10) + n ** 3 / 3.0 + 2 * n * n + 2 * n ** 3 / 3.0 \
+        + p * n * n * (2 * (DX + DW) + 12)
+
+    bq = E.BQEngine(hb, DX, wsets=wl["wsets"], lower=wl["lower"], upper=wl["upper"])
+    zs = eng.to_device(wl["zs"])
+    starts = eng.to_device(wl["starts"])
+    cands_all = eng.to_device(wl["cands"])
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    per_rank = N_CAND_TOTAL // world
+    opt = dict(maxiter=MAXITER_MC, factr=FACTR_MC, z_per_cta=Z_PER_CTA)
+
+    def batch(step):
+        lo = rank * per_rank + (step * CAND_PER_STEP) % max(1, per_rank - CAND_PER_STEP)
+        return cands_all[lo:lo + CAND_PER_STEP]
+
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kern_ms = []
+    evals_total = [0]
+    best = [None]
+
+    def step(i, timed):
+        cb = batch(i)
+        ub = bq.setup(cb)
+        k0.record()
+        out_max, out_arg, n_evals = bq.inner_maximize(ub, zs, starts, count_evals=True, **opt)
+        k1.record()
+        gvb, is_nan = bq.grad_vector_b(ub, out_arg)
+        value, grad = bq.acq_reduce(ub, out_max, gvb, is_nan, zs)
+        v, idx = torch.max(value, dim=0)
+        best[0] = (v, idx + 0)
+        flush.fill_(i & 0xFF)
+        return n_evals
+
+    # launches of this library per step: cross_cov 1, trsm 2, candidate_setup 1,
+    # inner_maximize 1, grad_vector_b 1, acq_reduce 1
+    launches_per_step = 7
+
+    for i in range(args.warmup):
+        step(i, False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    counts = []
+    kevs = []
+    for i in range(args.steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0, k1 = a, b
+        counts.append(step(args.warmup + i, True))
+        kevs.append((a, b))
+    t1.record()
+    torch.cuda.synchronize()
+    elapsed_ms = t0.elapsed_time(t1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+        # the one exchange of the path: every rank's best (value, global index) -> argmax
+        v, idx = best[0]
+        mine = torch.stack([v, (idx + rank * per_rank).to(torch.float64)])
+        allv = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+    kern_ms = [a.elapsed_time(b) for a, b in kevs]
+    evals = float(sum(int(c.sum().item()) for c in counts))
+    units_per_step = CAND_PER_STEP * N_HYPER
+    value = world * units_per_step * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- end to end through the public API (host numpy in, numpy out) ---------------------------
+    e2e = None
+    if True:
+        from bayesian_quadrature_optimization_b200.models.gp_fitting_gaussian import GPFittingGaussian
+        from bayesian_quadrature_optimization_b200.numerical_tools.bayesian_quadrature import \
+            BayesianQuadrature
+        from bayesian_quadrature_optimization_b200.acquisition_functions.sbo import SBO
+        from bayesian_quadrature_optimization_b200.lib.constant import SCALED_KERNEL, MATERN52_NAME, GAMMA
+        td = {"points": wl["pts"], "evaluations": wl["y"], "var_noise": []}
+        bounds = [[0, 1]] * DX + [[0, 20]] * DW
+        gp = GPFittingGaussian([SCALED_KERNEL, MATERN52_NAME], td, [DX + DW], bounds_domain=bounds,
+                               noise=True, kernel_values=list(wl["thetas"][0][2:]),
+                               mean_value=[0.0], var_noise_value=[1e-4], device=dev)
+        gp.samples_parameters = [t.copy() for t in wl["thetas"]]
+        quad = BayesianQuadrature(gp, list(range(DX)), GAMMA,
+                                  parameters_distribution={"a": [2.0], "scale": [1.0]})
+        quad.set_w_sets(wl["wsets"])
+        sbo = SBO(quad)
+        np.random.seed(7 + rank)
+        host_cands = wl["cands"]
+
+        def e2e_step(i):
+            lo = rank * per_rank + (i * CAND_PER_STEP) % max(1, per_rank - CAND_PER_STEP)
+            r = sbo.evaluate_mc_bayesian_candidate_points_no_restarts(
+                host_cands[lo:lo + CAND_PER_STEP], N_HYPER, N_Z, n_restarts=N_RESTARTS_MC,
+                compute_gradient=True, factr=FACTR_MC, maxiter=MAXITER_MC)
+            return r
+
+        for i in range(max(1, min(args.warmup, 2))):
+            e2e_step(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        w0 = time.perf_counter()
+        n_e2e = max(1, min(args.steps, 3))
+        for i in range(n_e2e):
+            r = e2e_step(10 + i)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - w0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        h2d = CAND_PER_STEP * (DX + DW) * 8 + N_Z * 8 + (N_RESTARTS_MC + 1) * DX * 8
+        d2h = CAND_PER_STEP * 8 + CAND_PER_STEP * (DX + DW) * 8
+        e2e = {"value": world * units_per_step * n_e2e / dt, "unit": "units/s",
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_e2e}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    kern_avg_ms = float(np.mean(kern_ms))
+    flops_per_launch = evals / args.steps * f_eval_flops()
+    achieved = flops_per_launch / (kern_avg_ms * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "inner_maximize_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(wl, z_cpu=2)
+        cpu.pop("wall_s", None)
+    line = {
+        "metric": "bqo_acq_grad_units_per_s", "value": value, "unit": "units/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(),
+        "roofline": {
+            "bound": "fp64", "kernel": "inner_maximize_kernel<4,2>", "achieved": achieved,
+            "peak": dfma_peak, "unit": "TFLOP/s", "frac": achieved / dfma_peak,
+            "traffic": traffic,
+            "peak_source": "FP64 DFMA rate measured in this run by bqo_fp64_peak_probe "
+                           "(MEASURED_PEAKS.json holds no FP64 figure); DMMA m8n8k4 probe: %.1f TF/s"
+                           % dmma_peak,
+            "flops_per_eval": f_eval_flops(), "evals_per_launch": evals / args.steps,
+            "evals_per_unit_per_z": evals / args.steps / (units_per_step * N_Z),
+            "kernel_ms": kern_avg_ms, "kernel_share_of_step": kern_avg_ms / (elapsed_ms / args.steps),
+        },
+        "secondary": {
+            "metric": "gp_loglik_grad_per_s", "value": N_HYPER / (stage_a * 1e-3), "unit": "evals/s",
+            "ms_for_%d_hyper_samples" % N_HYPER: stage_a,
+            "achieved_tflops": N_HYPER * f_ll / (stage_a * 1e-3) / 1e12, "peak_tflops": dmma_peak,
+            "frac": N_HYPER * f_ll / (stage_a * 1e-3) / 1e12 / dmma_peak,
+            "bound": "fp64 tensor (DMMA)", "flops_per_eval": f_ll,
+        },
+        "cpu_baseline": cpu,
+        "e2e": e2e,
+        "gpu_launches": launches_per_step * args.steps,
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

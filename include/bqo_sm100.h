@@ -188,7 +188,9 @@ typedef struct bqo_stage_c {
     int32_t n_units;    /* (candidate, hyper-sample) units in this batch */
     int32_t C;          /* candidates in R/den/beta4 (unit u -> candidate unit_c[u]) */
     int32_t M;          /* W samples per quadrature evaluation (N_SAMPLES=10, expectations.py:7) */
-    int32_t n_wsets;    /* pre-drawn W sample sets; evaluation e of a run uses set e % n_wsets */
+    int32_t n_wsets;    /* pre-drawn W sample sets; the inner maximiser and (by default) the
+                           candidate gradient use set (candidate index % n_wsets) for every
+                           evaluation of a unit, so each run optimises a fixed smooth function */
     const double* hyp;      /* [S][stride] */
     const double* Xs;       /* [S][dim_m][n] */
     const int32_t* tid;     /* [n] or NULL */

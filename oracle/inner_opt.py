@@ -76,7 +76,12 @@ def pbfgs_maximize(fg, x0, lower, upper, maxiter=10, max_ls=20, factr=1e12, pgto
                 accepted = True
                 gn = -np.asarray(gFn, dtype=float)
                 break
-            step *= 0.5
+            denom_q = 2.0 * (phin - phi - decr)
+            shrink = (-decr / denom_q) if denom_q > 0.0 else 0.5
+            shrink = min(max(shrink, 0.1), 0.5)
+            if shrink != shrink:
+                shrink = 0.5
+            step *= shrink
         if not accepted:
             break
         sv = xn - x
@@ -108,11 +113,11 @@ def box_vertices(lower, upper):
     return [np.array(p, dtype=float) for p in itertools.product(*zip(lower, upper))]
 
 
-def inner_maximize(ab, z, starts, lower, upper, n_wsets=1, use_vertices=True, **opt):
+def inner_maximize(ab, z, starts, lower, upper, wset=0, use_vertices=True, **opt):
     """max over starts (+ vertices) of a(x) + z b(x).
 
-    ab(x, wset) -> (a, b, grad_a, grad_b).  Mirrors the three phases of the CUDA kernel:
-    start/vertex evaluations use W set 0, evaluation e of a run uses set e % n_wsets.
+    ab(x, wset) -> (a, b, grad_a, grad_b).  Mirrors the three phases of the CUDA kernel; every
+    evaluation of a unit uses the W set of its candidate (`wset` = candidate index % n_wsets).
     Returns (max, argmax, n_evals).
     """
     best = None
@@ -120,10 +125,10 @@ def inner_maximize(ab, z, starts, lower, upper, n_wsets=1, use_vertices=True, **
     n_evals = 0
     for x0 in np.asarray(starts, dtype=float):
         x0c = np.minimum(np.maximum(x0, lower), upper)
-        a0, b0, ga0, gb0 = ab(x0c, 0)
+        a0, b0, ga0, gb0 = ab(x0c, wset)
 
         def fg(x, e):
-            a, b, ga, gb = ab(x, e % n_wsets)
+            a, b, ga, gb = ab(x, wset)
             return a + z * b, ga + z * gb
 
         F, x, ne = pbfgs_maximize(fg, x0c, lower, upper, f0g0=(a0 + z * b0, ga0 + z * gb0), **opt)
@@ -133,7 +138,7 @@ def inner_maximize(ab, z, starts, lower, upper, n_wsets=1, use_vertices=True, **
     if use_vertices:
         vb, vx = None, None
         for v in box_vertices(lower, upper):
-            a, b, _, _ = ab(v, 0)
+            a, b, _, _ = ab(v, wset)
             val = a + z * b
             if vb is None or val > vb:
                 vb, vx = val, v
