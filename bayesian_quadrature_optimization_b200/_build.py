@@ -81,5 +81,35 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB_PATH
 
 
+def build_variant(tag: str, defines: dict) -> Path:
+    """Tuning aid: build libbqo_sm100_<tag>.so with extra -D macros (e.g. IM_WARPS, EVAL_NV).
+    Select it at run time with the environment variable BQO_LIB_PATH."""
+    LIB_DIR.mkdir(exist_ok=True)
+    nvcc = _nvcc()
+    out = LIB_DIR / ("libbqo_sm100_%s.so" % tag)
+    objs = []
+    for src in SOURCES:
+        obj = LIB_DIR / (src[:-3] + ".o")
+        if src == "bqo_stage_c.cu":
+            obj = LIB_DIR / ("bqo_stage_c_%s.o" % tag)
+            flags = ["-D%s=%s" % kv for kv in defines.items()]
+            cmd = [nvcc, *NVCC_FLAGS, *flags, "-c", str(CSRC / src), "-o", str(obj)]
+            r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+            if r.returncode != 0:
+                raise RuntimeError(r.stdout.decode())
+        objs.append(str(obj))
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(out), *objs]
+    r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    if r.returncode != 0:
+        raise RuntimeError(r.stdout.decode())
+    return out
+
+
 if __name__ == "__main__":
-    print(build(force=True, verbose=True))
+    import sys
+    if len(sys.argv) > 2 and sys.argv[1] == "--variant":
+        # python _build.py --variant w20n2 IM_WARPS=20 EVAL_NV=2
+        build(force=False)
+        print(build_variant(sys.argv[2], dict(a.split("=") for a in sys.argv[3:])))
+    else:
+        print(build(force=True, verbose=True))

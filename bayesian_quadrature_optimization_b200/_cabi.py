@@ -137,7 +137,11 @@ def load(path: Path | None = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = Path(path) if path is not None else LIB_PATH
+    import os
+    if path is None and os.environ.get("BQO_LIB_PATH"):
+        p = Path(os.environ["BQO_LIB_PATH"])  # tuning variants built by _build.build_variant
+    else:
+        p = Path(path) if path is not None else LIB_PATH
     if not p.exists():
         raise BqoLibraryError(
             "%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "

@@ -144,6 +144,71 @@ __device__ __forceinline__ void bqo_matern52_kg_fast(double r2, const double* __
     g = (t1 * e) * BQO_FC[9];
 }
 
+// NV independent evaluations in lock step.  A single evaluation is one long dependent chain of
+// DFMAs (profiles/r01_inner_maximize_v1.md: 46 % of the warp stalls were fixed-latency waits),
+// so the hot loop feeds NV of them through every stage together; ptxas then has NV independent
+// instructions per stage to interleave.  Outputs: e = exp(-sqrt5 r), t1 = 1 + sqrt5 r and
+// poly = 1 + sqrt5 r + 5/3 r^2, i.e. k = poly e and k'(r)/r = -(5/3) t1 e.
+template <int NV>
+__device__ __forceinline__ void bqo_matern52_fast_v(const double (&r2)[NV],
+                                                    const double* __restrict__ tab,
+                                                    double (&e)[NV], double (&t1)[NV],
+                                                    double (&poly)[NV]) {
+    double g[NV], h[NV], w[NV], s[NV], kf[NV], fr[NV], p[NV];
+    int n[NV];
+    const double magic = 6755399441055744.0;  // 1.5 * 2^52
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        double y;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(r2[q]));
+        g[q] = r2[q] * y;
+        h[q] = 0.5 * y;
+    }
+#pragma unroll
+    for (int q = 0; q < NV; ++q) w[q] = fma(-h[q], g[q], 0.5);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        g[q] = fma(g[q], w[q], g[q]);
+        h[q] = fma(h[q], w[q], h[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < NV; ++q) w[q] = fma(-g[q], g[q], r2[q]);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) g[q] = fma(w[q], h[q], g[q]);  // r
+#pragma unroll
+    for (int q = 0; q < NV; ++q) s[q] = BQO_FC[0] * g[q];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        double tk = fma(s[q], BQO_FC[1], magic);
+        n[q] = __double2loint(tk);
+        kf[q] = tk - magic;
+    }
+#pragma unroll
+    for (int q = 0; q < NV; ++q) fr[q] = fma(kf[q], BQO_FC[2], -s[q]);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) fr[q] = fma(kf[q], BQO_FC[3], fr[q]);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) p[q] = fma(BQO_FC[4], fr[q], BQO_FC[5]);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) p[q] = fma(p[q], fr[q], BQO_FC[6]);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) p[q] = fma(p[q], fr[q], BQO_FC[7]);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) p[q] = fma(p[q], fr[q], 0.5);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) p[q] = fma(p[q], fr[q], 1.0);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) p[q] = fma(p[q], fr[q], 1.0);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        n[q] = max(n[q], -32000);
+        double ev = p[q] * tab[n[q] & (BQO_EXP_TABLE - 1)];
+        e[q] = __hiloint2double(__double2hiint(ev) + ((n[q] >> 5) << 20), __double2loint(ev));
+        t1[q] = 1.0 + s[q];
+        poly[q] = fma(BQO_FC[8], r2[q], t1[q]);
+    }
+}
+
 __device__ __forceinline__ double bqo_warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

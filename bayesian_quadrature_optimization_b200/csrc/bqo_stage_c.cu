@@ -180,6 +180,11 @@ struct AbOut {
     double ga[DX], gb[DX];
 };
 
+// W samples pushed through the Matern stages together (independent DFMA chains per lane).
+#ifndef EVAL_NV
+#define EVAL_NV 2
+#endif
+
 // Warp-cooperative evaluation of a, b and their x-gradients at the raw point x.
 // `ws`: this evaluation's W samples, already divided by the w length scales, [M][DW].
 template <int DX, int DW>
@@ -201,26 +206,59 @@ __device__ __forceinline__ void eval_ab_warp(const UnitCtx<DX, DW>& u, const dou
             dxl[l] = xsc[l] - u.xs[l * u.ldx + j];
             Dx = fma(dxl[l], dxl[l], Dx);
         }
+        // ksum = sum_m k(r_m);  gsum = sum_m (1 + sqrt5 r_m) e^{-sqrt5 r_m}, the factor -5/3 of
+        // k'(r)/r is applied once per evaluation after the reduction
         double ksum = 0.0, gsum = 0.0;
         if (DW > 0) {
             double xw[DW > 0 ? DW : 1];
 #pragma unroll
             for (int l = 0; l < DW; ++l) xw[l] = u.xs[(DX + l) * u.ldx + j];
-#pragma unroll 2
-            for (int m = 0; m < M; ++m) {
-                double r2 = Dx;
+            int m = 0;
+            for (; m + EVAL_NV <= M; m += EVAL_NV) {
+                double r2v[EVAL_NV], ev[EVAL_NV], t1v[EVAL_NV], pv[EVAL_NV];
+#pragma unroll
+                for (int q = 0; q < EVAL_NV; ++q) {
+                    double r2 = Dx;
+#pragma unroll
+                    for (int l = 0; l < DW; ++l) {
+                        double dw = ws[(m + q) * DW + l] - xw[l];
+                        r2 = fma(dw, dw, r2);
+                    }
+                    r2v[q] = r2;
+                }
+                bqo_matern52_fast_v<EVAL_NV>(r2v, u.tab, ev, t1v, pv);
+                double k0 = 0.0, k1 = 0.0, g0 = 0.0, g1 = 0.0;
+#pragma unroll
+                for (int q = 0; q < EVAL_NV; ++q) {
+                    if (q & 1) {
+                        k1 = fma(pv[q], ev[q], k1);
+                        g1 = fma(t1v[q], ev[q], g1);
+                    } else {
+                        k0 = fma(pv[q], ev[q], k0);
+                        g0 = fma(t1v[q], ev[q], g0);
+                    }
+                }
+                ksum += k0 + k1;
+                gsum += g0 + g1;
+            }
+            for (; m < M; ++m) {
+                double r2v[1], ev[1], t1v[1], pv[1];
+                r2v[0] = Dx;
 #pragma unroll
                 for (int l = 0; l < DW; ++l) {
                     double dw = ws[m * DW + l] - xw[l];
-                    r2 = fma(dw, dw, r2);
+                    r2v[0] = fma(dw, dw, r2v[0]);
                 }
-                double k, g;
-                bqo_matern52_kg_fast(r2, u.tab, k, g);
-                ksum += k;
-                gsum += g;
+                bqo_matern52_fast_v<1>(r2v, u.tab, ev, t1v, pv);
+                ksum = fma(pv[0], ev[0], ksum);
+                gsum = fma(t1v[0], ev[0], gsum);
             }
         } else {
-            bqo_matern52_kg_fast(Dx, u.tab, ksum, gsum);
+            double r2v[1], ev[1], t1v[1], pv[1];
+            r2v[0] = Dx;
+            bqo_matern52_fast_v<1>(r2v, u.tab, ev, t1v, pv);
+            ksum = pv[0] * ev[0];
+            gsum = t1v[0] * ev[0];
         }
         const double wa = u.wa[j], wb = u.wb[j];
         Sa = fma(ksum, wa, Sa);
@@ -262,8 +300,8 @@ __device__ __forceinline__ void eval_ab_warp(const UnitCtx<DX, DW>& u, const dou
     o.b = u.scale * (u.wc * Kc - Sb) * u.inv_den;
 #pragma unroll
     for (int l = 0; l < DX; ++l) {
-        double ga = bqo_warp_sum(GA[l]);
-        double gb = bqo_warp_sum(GB[l]);
+        double ga = bqo_warp_sum(GA[l]) * (-BQO_FIVE_THIRDS);
+        double gb = bqo_warp_sum(GB[l]) * (-BQO_FIVE_THIRDS);
         double gc = bqo_warp_sum(GC[l]);
         o.ga[l] = u.scale * ga * u.inv_ls[l];
         o.gb[l] = u.scale * (u.wc * gc - gb) * u.inv_ls[l] * u.inv_den;
@@ -396,7 +434,11 @@ extern "C" int bqo_sample_ab_batched(const bqo_stage_c* pb, const double* pts,
 // L-BFGS-B call the reference makes (scipy fmin_l_bfgs_b via Optimization.optimize,
 // sbo/lib/optimization.py:87-155, with maxiter=10, factr=1e12 from sbo/services/bgo.py:43-44).
 // oracle/inner_opt.py restates the same iteration in numpy.
-#define IM_WARPS 16
+// 24 warps x 80 registers: measured best on B200 (sweep of {12,16,20,24,28} warps x {1,2,5}
+// interleaved W samples, profiles/r01_inner_maximize_v1.md)
+#ifndef IM_WARPS
+#define IM_WARPS 24
+#endif
 #define IM_MAX_VERT 64  // 2^DX for DX <= 6
 
 template <int DX>
@@ -438,20 +480,33 @@ __global__ void __launch_bounds__(IM_WARPS * 32, 1)
         reinterpret_cast<RunState<DX>*>(s_run + (size_t)opt.z_per_cta * n_starts * (1 + DX));
     int* s_counter = reinterpret_cast<int*>(s_state + IM_WARPS);
 
-    UnitCtx<DX, DW> u;
-    unit_ctx_init<DX, DW>(u, pb, unit);
-    u.tab = s_tab;
-    bqo_exp_table_init(s_tab);
-    if (STAGE) {
-        for (int e = threadIdx.x; e < D * n; e += blockDim.x) s_xs[e] = u.xs[e];
-        for (int e = threadIdx.x; e < n; e += blockDim.x) {
-            s_wa[e] = u.wa[e];
-            s_wb[e] = u.wb[e];
-        }
-        u.xs = s_xs;
-        u.wa = s_wa;
-        u.wb = s_wb;
+    // the unit's constants live in shared memory (read with broadcast loads where needed), not in
+    // 40 registers of every thread: registers buy resident warps, and resident warps are what
+    // hides the 8-cycle DFMA latency (tests/microbench/fp64_issue.cu)
+    __shared__ UnitCtx<DX, DW> s_u;
+    if (threadIdx.x == 0) {
+        unit_ctx_init<DX, DW>(s_u, pb, unit);
+        s_u.tab = s_tab;
     }
+    bqo_exp_table_init(s_tab);
+    __syncthreads();
+    if (STAGE) {
+        const double* gxs = s_u.xs;
+        const double* gwa = s_u.wa;
+        const double* gwb = s_u.wb;
+        for (int e = threadIdx.x; e < D * n; e += blockDim.x) s_xs[e] = gxs[e];
+        for (int e = threadIdx.x; e < n; e += blockDim.x) {
+            s_wa[e] = gwa[e];
+            s_wb[e] = gwb[e];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_u.xs = s_xs;
+            s_u.wa = s_wa;
+            s_u.wb = s_wb;
+        }
+    }
+    const UnitCtx<DX, DW>& u = s_u;
     if (DW > 0) {
         // every evaluation of this unit uses the W set of its candidate (sample-average
         // approximation: the objective of a run is a fixed smooth function)

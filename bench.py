@@ -40,7 +40,7 @@ N_HYPER, N_Z, M_W, N_WSETS = 20, 100, 10, 8
 N_CAND_TOTAL = 10000
 CAND_PER_STEP = 37          # 37 x 20 = 740 units = 5 per SM
 N_RESTARTS_MC, MAXITER_MC, FACTR_MC = 5, 10, 1e12  # bgo() defaults, sbo/services/bgo.py:43-44
-Z_PER_CTA = 25
+Z_PER_CTA = int(os.environ.get("BQO_Z_PER_CTA", "25"))
 
 
 def make_workload(seed_shift=0):
@@ -275,7 +275,7 @@ def run_gpu(args):
     # ---- stage A (once per BO iteration; secondary metric: log-likelihood + gradient per s) ----
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stage_a_ms = []
-    for rep in range(3):
+    for rep in range(2 if args.profile else 3):
         hb = eng.hypers(wl["thetas"])
         torch.cuda.synchronize()
         ev0.record()
@@ -364,7 +364,7 @@ def run_gpu(args):
 
     # ---- end to end through the public API (host numpy in, numpy out) ---------------------------
     e2e = None
-    if True:
+    if not args.profile:
         from bayesian_quadrature_optimization_b200.models.gp_fitting_gaussian import GPFittingGaussian
         from bayesian_quadrature_optimization_b200.numerical_tools.bayesian_quadrature import \
             BayesianQuadrature
@@ -464,13 +464,19 @@ def run_gpu(args):
 
 
 def main():
+    global CAND_PER_STEP
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="short run for ncu: 8 candidates per step, no stage-A repeats, no e2e, no CPU leg")
     args = ap.parse_args()
+    if args.profile:
+        CAND_PER_STEP = 8
+        args.no_cpu_baseline = True
     if args.impl == "reference":
         run_reference(args)
     else:
