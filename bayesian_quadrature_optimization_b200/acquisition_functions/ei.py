@@ -102,7 +102,8 @@ class EI(object):
         else:
             best = torch.full((hb.S,), float(np.max(gp.data['evaluations'])), dtype=torch.float64,
                               device=hb.eng.device)
-        ei, gei = hb.ei(np.asarray(points, dtype=float), best, grad=gradient)
+        pts_in = points if isinstance(points, torch.Tensor) else np.asarray(points, dtype=float)
+        ei, gei = hb.ei(pts_in, best, grad=gradient)
         val = ei.mean(dim=0).cpu().numpy()
         grad = gei.mean(dim=0).cpu().numpy() if gradient else None
         return val, grad

@@ -224,6 +224,164 @@ class SBO(object):
             return np.sum(np.diff(b[keep]) * tmp)
         return 0
 
+    # -- maximisation of the acquisition function: multi-start SGD on the device -------------------------
+    def _restart_points(self, n_restarts):
+        """Start points of SBO.optimize (:1688-1765): 100 random points, squared distance to the
+        data, draws from the (1/8,1/4) and (1/4,1/2) distance-quantile bands, replicated over the
+        tasks when W is finite.  Same numpy RNG calls as the reference."""
+        bq = self.bq
+        bounds = bq.bounds
+        new_points = np.array(DomainService.get_points_domain(100, bounds, type_bounds=bq.type_bounds))
+        current = np.array(bq.gp.data['points'])
+        finite = bq.separate_tasks and not bq.task_continue
+        if finite:
+            current = current[:, 0:-1]
+        d = new_points[:, None, :] - current[None, :, :new_points.shape[1]]
+        max_distances = np.min(np.einsum('ijk,ijk->ij', d, d), axis=1)
+        sort_dist_ind = sorted(range(len(max_distances)), key=lambda k: max_distances[k])
+        md = int(np.ceil(len(max_distances) / 2.0))
+        uq = int(np.ceil(len(max_distances) / 4.0))
+        lw = int(np.ceil(len(max_distances) / 8.0))
+        index_1 = n_restarts // 2
+        index_2 = n_restarts - index_1
+        index_1 = np.random.choice(range(uq, md), index_1, replace=False)
+        index_2 = np.random.choice(range(lw, uq), index_2, replace=False)
+        index = [sort_dist_ind[t] for t in index_1] + [sort_dist_ind[t] for t in index_2]
+        if finite:
+            n_tasks = len(bq.tasks)
+            return np.array([np.concatenate((new_points[i], [j])) for i in index
+                             for j in range(n_tasks)])
+        return np.array([new_points[i] for i in index])
+
+    def optimize(self, start=None, random_seed=None, parallel=True, monte_carlo=False, n_samples=1,
+                 n_restarts_mc=1, n_best_restarts_mc=0, n_restarts=1, n_best_restarts=0,
+                 start_ei=True, n_samples_parameters=0, start_new_chain=True,
+                 compute_max_mean_bayesian=False, maxepoch=10, default_n_samples=None,
+                 default_n_samples_parameters=None, default_restarts_mc=None, method_opt_mc=None,
+                 **opt_params_mc):
+        """:1571-1950 -> {'solution', 'optimal_value', 'gradient'} of the best restart.
+
+        Monte-Carlo / Bayesian branch on the device.  Every SGD epoch is ONE pass of the hot path:
+        the stochastic gradient of all restarts is the mean over n_samples_parameters resident
+        hyper-samples (drawn uniformly from the last n_parameters slice samples; the reference
+        advances the chain by one slice step per gradient, sbo.py:1129) times n_samples fresh
+        Z ~ N(0,1), i.e. N = n_samples * n_samples_parameters single-sample gradients
+        (sbo.py:1845) averaged, followed by the reference's Adam step, box projection and stop
+        rule (sbo/lib/stochastic_gradient_descent.py:83-130) for every restart at once."""
+        import torch
+        from .. import _cabi
+        from .ei import EI
+        from .multi_task import MultiTasks
+        from ..numerical_tools.bayesian_quadrature import BayesianQuadrature
+        from ..lib.constant import TASKS
+        if random_seed is not None:
+            np.random.seed(random_seed)
+        bq, gp = self.bq, self.bq.gp
+        n_parameters = 0 if n_samples_parameters == 0 else (
+            default_n_samples_parameters or DEFAULT_N_PARAMETERS)
+        if default_n_samples is None:
+            default_n_samples = DEFAULT_N_SAMPLES
+        if default_restarts_mc is None:
+            default_restarts_mc = n_restarts_mc
+        if n_samples_parameters > 0 and start_new_chain:
+            gp.start_new_chain()
+            gp.sample_parameters(n_parameters)
+        elif n_samples_parameters > 0 and len(gp.samples_parameters) < n_parameters:
+            gp.sample_parameters(n_parameters - len(gp.samples_parameters))
+
+        st_ei = None
+        if start_ei and not bq.separate_tasks:
+            opt_ei = EI(gp).optimize(n_restarts=100, n_samples_parameters=5, parallel=parallel,
+                                     n_best_restarts=10, maxepoch=50)
+            st_ei = opt_ei['solution'].reshape((1, -1))
+            n_restarts -= 1
+            n_best_restarts -= 1
+        elif start_ei:
+            quadrature_2 = BayesianQuadrature(gp, bq.x_domain, bq.distribution,
+                                              parameters_distribution=bq.parameters_distribution,
+                                              model_only_x=True)
+            mk = MultiTasks(quadrature_2, bq.n_tasks)
+            st_ei = mk.optimize(parallel=True, n_restarts=100, n_best_restarts=10,
+                                n_samples_parameters=5, maxepoch=50,
+                                start_new_chain=False)['solution'].reshape((1, -1))
+        if start is None:
+            if n_restarts > 0:
+                start = self._restart_points(n_restarts)
+                if 0 < n_best_restarts < start.shape[0]:
+                    out = self.evaluate_mc_bayesian_candidate_points_no_restarts(
+                        start, n_parameters, default_n_samples, default_restarts_mc,
+                        compute_max_mean=True, compute_gradient=False, **opt_params_mc)
+                    keep = np.argsort(out['evaluations'], kind='stable')[-n_best_restarts:]
+                    start = start[keep]
+                if st_ei is not None:
+                    start = np.concatenate((start, st_ei), axis=0)
+            else:
+                start = st_ei
+        start = np.asarray(start, dtype=float).reshape(-1, len(self.bounds_opt))
+
+        # ---- batched Adam over all restarts --------------------------------------------------------
+        parameters = gp.samples_parameters[-n_parameters:] if n_parameters > 0 else \
+            [gp.get_value_parameters_model]
+        bqe = bq.engine_for(np.array(parameters))
+        eng = bqe.eng
+        dim = start.shape[1]
+        dim_m = eng.desc.dim_m
+        lo = np.array([(-np.inf if b[0] is None else b[0]) for b in self.bounds_opt], dtype=float)
+        up = np.array([(np.inf if b[-1] is None else b[-1]) for b in self.bounds_opt], dtype=float)
+        pts = eng.to_device(start.copy())
+        R = int(pts.shape[0])
+        m0, v0 = torch.zeros_like(pts), torch.zeros_like(pts)
+        active = torch.ones(R, dtype=torch.int32, device=eng.device)
+        lo_d, up_d = eng.to_device(lo), eng.to_device(up)
+        n_k = max(1, min(n_samples_parameters if n_samples_parameters > 0 else 1, len(parameters)))
+        n_zs = max(1, n_samples)
+        bx = self._bounds_x()
+        for t in range(1, maxepoch + 1):
+            ks = np.random.choice(len(parameters), n_k, replace=False)
+            zs = np.random.normal(0, 1, n_zs)
+            starts_x = np.array(DomainService.get_points_domain(
+                default_restarts_mc + 1, bx, type_bounds=len(bx) * [0]))
+            res = bqe.evaluate_candidates(
+                pts, zs, starts_x, compute_gradient=True, hyper_indices=ks,
+                maxiter=opt_params_mc.get('maxiter', 15000), factr=opt_params_mc.get('factr', 1e7),
+                pgtol=self.inner_pgtol, max_ls=self.inner_max_ls, use_vertices=len(bx) < 7)
+            g = torch.zeros(R, dim, dtype=torch.float64, device=eng.device)
+            g[:, :dim_m] = -res['gradient']               # maximise: descend on -acquisition
+            bad = torch.isnan(g).any(dim=1)
+            if bool(bad.any()):
+                # gradient unavailable (den = 0): random perturbation of relative size 1e-6
+                # (stochastic_gradient_descent.py:51-75), no Adam step for those restarts
+                pert = 1e-6 * pts.norm(dim=1, keepdim=True) * (2 * torch.rand_like(pts) - 1)
+                pts = torch.where(bad.unsqueeze(1), torch.min(torch.max(pts + pert, lo_d), up_d), pts)
+                g = torch.where(bad.unsqueeze(1), torch.zeros_like(g), g)
+            _cabi.check(eng.lib.bqo_adam_step_batched(
+                _cabi.ptr(pts), _cabi.ptr(g.contiguous()), _cabi.ptr(m0), _cabi.ptr(v0),
+                _cabi.ptr(active), _cabi.ptr(lo_d), _cabi.ptr(up_d), R, dim, t, 0.1, 0.9, 0.999, 1e-8,
+                torch.cuda.current_stream().cuda_stream), "bqo_adam_step_batched")
+            if int(active.sum().item()) == 0:
+                break
+        candidate_points = pts.cpu().numpy()
+
+        # ---- final scoring of the end points (:1884-1900) ---------------------------------------------
+        output = self.evaluate_mc_bayesian_candidate_points_no_restarts(
+            candidate_points, n_parameters, default_n_samples, default_restarts_mc,
+            compute_max_mean=True, compute_gradient=True, **opt_params_mc)
+        ind_max = int(np.argmax(output['evaluations']))
+        solution = candidate_points[ind_max].copy()
+        gradient = output['gradient'][ind_max]
+        if np.any(np.isnan(gradient)):
+            # :1915-1946: perturb the solution when its gradient is unavailable
+            npt = solution[:-1] if (not bq.task_continue and bq.separate_tasks) else solution
+            pert = np.sqrt(np.sum(npt ** 2)) * 1e-6
+            for i in range(len(npt)):
+                lb = min(pert, npt[i] - lo[i])
+                ub = min(pert, up[i] - npt[i])
+                npt[i] += np.random.uniform(-lb, ub)
+        result = {'solution': solution, 'optimal_value': float(output['evaluations'][ind_max]),
+                  'gradient': gradient}
+        self.optimization_results.append(result)
+        return result
+
     def clean_cache(self):
         self.samples = None
         self.starting_points_sbo = None

@@ -28,6 +28,11 @@ F64 = torch.float64
 I32 = torch.int32
 
 
+def _cabi_taskc_offset() -> int:
+    """Offset (doubles) of the task covariance table inside a hyper block (BQO_H_TASKC)."""
+    return 4 + 2 * _cabi.MAX_DIM
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -218,6 +223,7 @@ class UnitBatch(object):
         self.cand = self.G = self.R = self.den = self.beta4 = None
         self.unit_k = self.unit_c = None
         self.C = 0
+        self.S_units = 0  # hyper-samples per candidate in the unit ordering u = c * S_units + k'
 
 
 class BQEngine(object):
@@ -263,6 +269,68 @@ class BQEngine(object):
         else:
             self.add_noise = hb.theta[:, 0].contiguous()
 
+    # -- posterior of G(x) = E_W F(x, W) ------------------------------------------------------------------
+    def quadrature_rows(self, xpts, w_set=0):
+        """B(x_p, X_j) for every hyper-sample: [S][P][n]
+        (evaluate_quadrature_cross_cov, sbo/numerical_tools/bayesian_quadrature.py:308-334)."""
+        eng, hb, d = self.eng, self.hb, self.eng.desc
+        xpts = eng.to_device(xpts).reshape(-1, self.dx)
+        P = int(xpts.shape[0])
+        if self.is_product:
+            # finite W: the task sum factorises, B = k_M(x, X_j.x) * q[task_j]; k_M comes from the
+            # cross-covariance kernel with a dummy task column, divided by its task factor
+            pts = torch.cat([xpts, torch.zeros(P, 1, dtype=F64, device=eng.device)], dim=1)
+            KP = hb.cross_cov(pts)                                   # k_M * C[0][task_j]
+            T = d.n_tasks
+            C = hb.hyp[:, _cabi_taskc_offset():_cabi_taskc_offset() + T * T].reshape(hb.S, T, T)
+            tid = hb.tid.long()
+            c0 = C[:, 0, :][:, tid]                                  # [S][n]
+            q = self.qt[:, tid]                                      # [S][n]
+            return KP * (q / c0).unsqueeze(1)
+        ws = self.wsets[w_set]                                       # [M][dw]
+        M = int(ws.shape[0])
+        pts = torch.cat([xpts.unsqueeze(1).expand(P, M, self.dx),
+                         ws.unsqueeze(0).expand(P, M, self.dw)], dim=2).reshape(P * M, d.dim)
+        KP = hb.cross_cov(pts.contiguous())                          # [S][P*M][n]
+        return KP.reshape(hb.S, P, M, eng.n).mean(dim=2)
+
+    def quadrature_prior_var(self, xpts, w_set=0):
+        """E_W E_W' k((x,W),(x,W')) for every hyper-sample: [S][P]
+        (evaluate_quadrate_cov, bayesian_quadrature.py:282-306; exact double sum for finite W,
+        the W set against itself for Monte-Carlo W)."""
+        eng, hb, d = self.eng, self.hb, self.eng.desc
+        xpts = eng.to_device(xpts).reshape(-1, self.dx)
+        P = int(xpts.shape[0])
+        if self.is_product:
+            T = d.n_tasks
+            C = hb.hyp[:, _cabi_taskc_offset():_cabi_taskc_offset() + T * T].reshape(hb.S, T, T)
+            w = self.weights if self.weights is not None else torch.ones(T, dtype=F64, device=eng.device)
+            w = w / w.sum()
+            v = torch.einsum('a,sab,b->s', w, C, w)
+            return v.unsqueeze(1).expand(hb.S, P).contiguous()
+        ws = self.wsets[w_set]
+        M = int(ws.shape[0])
+        out = eng.empty(hb.S, P)
+        for p in range(P):
+            pts = torch.cat([xpts[p:p + 1].expand(M, self.dx), ws], dim=1).contiguous()
+            tmp = GPEngine(d.kind, d.dim, d.n_tasks, bool(d.same_corr), device=eng.device)
+            tmp.set_data(pts, torch.zeros(M, dtype=F64, device=eng.device))
+            hb2 = tmp.hypers(hb.theta)
+            out[:, p] = hb2.cov().mean(dim=(1, 2))
+        return out
+
+    def quadrature_posterior(self, xpts, w_set=0, var=True):
+        """Posterior mean (and variance) of G at P points for every hyper-sample
+        (BayesianQuadrature.compute_posterior_parameters, :449-537) -> mean [S][P], var [S][P]."""
+        hb = self.hb
+        B = self.quadrature_rows(xpts, w_set)
+        mean = hb.theta[:, 1:2] + torch.einsum('spn,sn->sp', B, hb.alpha)
+        if not var:
+            return mean, None
+        sol = hb.solve(B.clone().contiguous())
+        v = self.quadrature_prior_var(xpts, w_set) - (B * sol).sum(dim=2)
+        return mean, v
+
     # -- stage B ---------------------------------------------------------------------------------------
     def setup(self, cands) -> UnitBatch:
         eng, hb, d = self.eng, self.hb, self.eng.desc
@@ -286,7 +354,21 @@ class BQEngine(object):
         u = torch.arange(Cn * hb.S, device=eng.device, dtype=torch.int64)
         ub.unit_c = (u // hb.S).to(I32).contiguous()
         ub.unit_k = (u % hb.S).to(I32).contiguous()
+        ub.S_units = hb.S
         return ub
+
+    def subset(self, ub: UnitBatch, hyper_indices) -> UnitBatch:
+        """Same candidates, units restricted to the given hyper-samples (u = c * len(ks) + k')."""
+        eng = self.eng
+        ks = eng.to_device(np.asarray(hyper_indices, dtype=np.int32), I32).reshape(-1)
+        nk = int(ks.shape[0])
+        sub = UnitBatch()
+        sub.cand, sub.G, sub.R, sub.den, sub.beta4, sub.C = ub.cand, ub.G, ub.R, ub.den, ub.beta4, ub.C
+        u = torch.arange(ub.C * nk, device=eng.device, dtype=torch.int64)
+        sub.unit_c = (u // nk).to(I32).contiguous()
+        sub.unit_k = ks[(u % nk)].contiguous()
+        sub.S_units = nk
+        return sub
 
     def _stage_c(self, ub: UnitBatch) -> StageC:
         eng, hb = self.eng, self.hb
@@ -361,14 +443,19 @@ class BQEngine(object):
         grad = eng.empty(ub.C, dim_g) if gvb is not None else None
         mm = None if max_mean is None else eng.to_device(max_mean).reshape(-1)
         check(eng.lib.bqo_acq_reduce(ptr(out_max), ptr(gvb), ptr(is_nan), ptr(z), ptr(mm), ub.C,
-                                     hb.S, n_z, dim_g, ptr(value), ptr(grad), _stream()),
+                                     ub.S_units, n_z, dim_g, ptr(value), ptr(grad), _stream()),
               "bqo_acq_reduce")
         return value, grad
 
-    def evaluate_candidates(self, cands, z, starts, max_mean=None, compute_gradient=True, **opt):
+    def evaluate_candidates(self, cands, z, starts, max_mean=None, compute_gradient=True,
+                            hyper_indices=None, **opt):
         """One pass of the hot path over a batch of candidates: stage B, inner maximisation for
-        every (candidate, hyper-sample, Z), gradient of b at the maximisers, MC reduction."""
+        every (candidate, hyper-sample, Z), gradient of b at the maximisers, MC reduction.
+        `hyper_indices` restricts the average to a subset of the resident hyper-samples (the
+        stochastic gradients of the SGD driver)."""
         ub = self.setup(cands)
+        if hyper_indices is not None:
+            ub = self.subset(ub, hyper_indices)
         out_max, out_arg, n_evals = self.inner_maximize(ub, z, starts, **opt)
         gvb = is_nan = None
         if compute_gradient:

@@ -150,7 +150,11 @@ class GPFittingGaussian(object):
         else:
             self.separate_tasks = False
         self.model_only_x = False
-        if len(self.samples_parameters) == 0:
+        self._define_priors()
+        self.slice_samplers = []
+        if define_samplers:
+            self.set_samplers()
+        elif len(self.samples_parameters) == 0:
             self.samples_parameters.append(self.get_value_parameters_model)
 
     # -- data plumbing ----------------------------------------------------------------------------
@@ -399,11 +403,123 @@ class GPFittingGaussian(object):
         self.best_solution[index] = best
         return best
 
+    # -- hyper-posterior: priors (host) + GPU likelihood, slice sampling ----------------------------
+    def _define_priors(self):
+        """Priors of set_parameters_kernel (:355-422) and of the kernels' define_default_kernel
+        (matern52.py:124-161, scaled_kernel.py:124-175, tasks_kernel.py:129-189)."""
+        from ..priors.priors import (UniformPrior, GaussianPrior, LogNormalSquare, HorseShoePrior,
+                                     NonNegativePrior, MultivariateNormalPrior, Constant)
+        from ..lib.constant import SMALLEST_POSITIVE_NUMBER, LARGEST_NUMBER
+        if self.noise and self.data.get('var_noise') is None:
+            self.mean.prior = GaussianPrior(1, self.mean_value[0], 1.0)
+            self.var_noise.prior = NonNegativePrior(1, HorseShoePrior(1, self.var_noise_value[0]))
+            self.var_noise.bounds = [(SMALLEST_POSITIVE_NUMBER, None)]
+        else:
+            self.mean.prior = Constant(1, 0.0)
+            self.var_noise.prior = Constant(1, 0.0)
+            self.var_noise.bounds = [(0.0, 0.0)]
+        dm = self._dim - 1 if self._kind == _cabi.KIND_PRODUCT_TASKS else self._dim
+        if self.bounds is not None and len(self.bounds) >= dm:
+            diffs = [float(self.bounds[l][-1] - self.bounds[l][0]) / 0.001 for l in range(dm)]
+        else:
+            diffs = dm * [LARGEST_NUMBER]
+        self._kernel_priors = [(slice(0, dm), UniformPrior(dm, dm * [SMALLEST_POSITIVE_NUMBER], diffs))]
+        kv = np.asarray(self.kernel_values, dtype=float)
+        if self._kind == _cabi.KIND_SCALED_MATERN52:
+            self._kernel_priors.append((slice(dm, dm + 1), LogNormalSquare(1, 1.0, np.sqrt(kv[dm]))))
+        elif self._kind == _cabi.KIND_PRODUCT_TASKS:
+            tv = kv[dm:]
+            if np.all(tv == 0.0):
+                prior = UniformPrior(len(tv), len(tv) * [-1.0], len(tv) * [1.0])
+            elif self._n_tasks == 1:
+                prior = LogNormalSquare(1, 1.0, np.sqrt(tv[0]))
+            else:
+                prior = MultivariateNormalPrior(len(tv), tv, np.eye(len(tv)))
+            self._kernel_priors.append((slice(dm, len(kv)), prior))
+        self.length_scale_indexes = list(range(2, 2 + dm))
+
     def log_prob_parameters(self, parameters):
-        """:1543-1567 (priors are host-side; without priors this is the log-likelihood)."""
-        lp = 0.0
-        for par, sl in ((self.var_noise, slice(0, 1)), (self.mean, slice(1, 2))):
-            lp += par.log_prior(parameters[sl])
+        """:1543-1567: sum of log-priors + GPU log-likelihood."""
+        parameters = np.asarray(parameters, dtype=float)
+        lp = self.var_noise.log_prior(parameters[0:1]) + self.mean.log_prior(parameters[1:2])
+        kp = parameters[2:]
+        for sl, prior in self._kernel_priors:
+            lp += prior.logprob(kp[sl])
         if not np.isinf(lp):
-            lp += self.log_likelihood(parameters[0], parameters[1], parameters[2:])
+            try:
+                lp += self.log_likelihood(parameters[0], parameters[1], kp)
+            except linalg.LinAlgError:
+                return -np.inf
         return lp
+
+    def set_samplers(self):
+        """:214-269: a random-direction slice sampler on the non-length-scale parameters and a
+        component-wise one on the length scales; optional burn-in."""
+        from ..samplers.hyper_slice_sampler import SliceSampling
+        log_prob = lambda vector, model: model.log_prob_parameters(vector)
+        self.slice_samplers = []
+        indexes = [i for i in range(self.dimension_parameters) if i not in self.length_scale_indexes]
+        ignore_index = None
+        if not self.noise or self.data.get('var_noise') is not None:
+            ignore_index = [0, 1]
+        if ignore_index is None or len(indexes) != len(ignore_index):
+            self.slice_samplers.append(SliceSampling(
+                log_prob, indexes, ignore_index=ignore_index,
+                max_steps_out=self.max_steps_out, component_wise=False))
+        self.slice_samplers.append(SliceSampling(
+            log_prob, self.length_scale_indexes, max_steps_out=self.max_steps_out,
+            component_wise=True))
+        self._two_blocks = len(self.slice_samplers) == 2
+        if self.start_point_sampler is not None and len(self.start_point_sampler) > 0:
+            if len(self.samples_parameters) == 0:
+                self.samples_parameters.append(np.array(self.start_point_sampler))
+        else:
+            self.samples_parameters = [self.get_value_parameters_model]
+            if self.n_burning > 0:
+                parameters = self.sample_parameters(float(self.n_burning) / (self.thinning + 1))
+                self.samples_parameters = [parameters[-1]]
+                self.start_point_sampler = parameters[-1]
+            else:
+                self.start_point_sampler = self.get_value_parameters_model
+
+    def start_new_chain(self, random_seed=None):
+        """:271-287."""
+        if random_seed is not None:
+            np.random.seed(random_seed)
+        if self.n_burning > 0:
+            parameters = self.sample_parameters(float(self.n_burning) / (self.thinning + 1))
+        else:
+            parameters = [self.samples_parameters[-1]]
+        self.samples_parameters = [parameters[-1]]
+        self.start_point_sampler = parameters[-1]
+
+    def sample_parameters(self, n_samples, start_point=None, random_seed=None):
+        """:289-353: n_samples * (thinning + 1) sweeps, every (thinning + 1)-th kept."""
+        from ..samplers.hyper_slice_sampler import separate_vector, combine_vectors
+        if random_seed is not None:
+            np.random.seed(random_seed)
+        if start_point is None:
+            start_point = self.samples_parameters[-1]
+        n_sweeps = int(n_samples * (self.thinning + 1))
+        samples = []
+        for _ in range(n_sweeps):
+            points = separate_vector(start_point, self.length_scale_indexes)  # [others, ls]
+            if self._two_blocks:
+                blocks = [(self.slice_samplers[0], 0), (self.slice_samplers[1], 1)]
+            else:
+                blocks = [(self.slice_samplers[0], 1)]
+            for sampler, which in blocks:
+                new_point, n_try = None, 0
+                while new_point is None and n_try < 10:
+                    try:
+                        new_point = sampler.slice_sample(points[which], points[1 - which], self)
+                    except Exception:
+                        n_try += 1
+                if new_point is None:
+                    raise RuntimeError('program failed to compute a sample of the parameters')
+                points[which] = new_point
+            start_point = combine_vectors(points[1], points[0], self.length_scale_indexes)
+            samples.append(start_point)
+        samples_return = samples[::self.thinning + 1]
+        self.samples_parameters += samples_return
+        return samples_return

@@ -1,0 +1,262 @@
+"""GPU tests of the reference-facing Python API (GPFittingGaussian, BayesianQuadrature, SBO, EI,
+MultiTasks, bgo): same calls as the reference's own tests make, checked against the fixtures
+generated from the unmodified reference (tests/golden) and against the oracle."""
+import numpy as np
+import pytest
+
+from oracle import bqo_oracle as orc
+from tests.helpers import assert_close, cond_rtol, oracle_from_golden
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["product_uniform", "product_weighted", "scaled_gamma"]
+
+
+def _models(g):
+    from bayesian_quadrature_optimization_b200.models.gp_fitting_gaussian import GPFittingGaussian
+    from bayesian_quadrature_optimization_b200.numerical_tools.bayesian_quadrature import \
+        BayesianQuadrature
+    from bayesian_quadrature_optimization_b200.lib import constant as K
+    kind = int(g["kind"])
+    dim = g["points"].shape[1]
+    dx = int(g["dx"])
+    vno = list(g["var_noise_obs"]) if "var_noise_obs" in g else []
+    td = {"points": g["points"].tolist(), "evaluations": list(g["evaluations"]), "var_noise": vno}
+    hi = 100.0 if g["points"][:, 0].max() > 2 else 1.0
+    th0 = g["thetas"][0]
+    if kind == 2:
+        T = int(g["n_tasks"])
+        gp = GPFittingGaussian(
+            [K.PRODUCT_KERNELS_SEPARABLE, K.MATERN52_NAME, K.TASKS_KERNEL_NAME], td, [dim, dx, T],
+            bounds_domain=[[0, hi]] * dx + [list(range(T))], type_bounds=[0] * dx + [1],
+            noise=len(vno) > 0, kernel_values=list(th0[2:]), define_samplers=False,
+            **{K.SAME_CORRELATION: bool(int(g["same_correlation"]))})
+        if "weights" in g:
+            bq = BayesianQuadrature(gp, list(range(dx)), K.WEIGHTED_UNIFORM_FINITE,
+                                    parameters_distribution={
+                                        "weights": g["weights"],
+                                        "domain_random": np.arange(T).reshape(T, 1)})
+        else:
+            bq = BayesianQuadrature(gp, list(range(dx)), K.UNIFORM_FINITE,
+                                    parameters_distribution={K.TASKS: T})
+    else:
+        gp = GPFittingGaussian([K.SCALED_KERNEL, K.MATERN52_NAME], td, [dim],
+                               bounds_domain=[[0, 1]] * dx + [[0, 10]] * (dim - dx), noise=True,
+                               kernel_values=list(th0[2:]), mean_value=[th0[1]],
+                               var_noise_value=[th0[0]], define_samplers=False)
+        bq = BayesianQuadrature(gp, list(range(dx)), K.GAMMA,
+                                parameters_distribution={"a": [2.0], "scale": [1.0]})
+        bq.set_w_sets(g["wset"])
+    return gp, bq
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_gp_facade_against_reference(golden, name):
+    g = golden(name)
+    gp, _ = _models(g)
+    for s, th in enumerate(g["thetas"]):
+        vn, mu, pk = th[0], th[1], th[2:]
+        assert_close(gp.evaluate_cov(g["points"], pk), g["cov"][s], rtol=1e-13)
+        gc = gp.evaluate_grad_cov(pk, g["points"])
+        assert_close(np.stack([gc[i] for i in range(len(pk))]), g["grad_cov"][s], rtol=1e-10,
+                     atol=1e-15)
+        chol, cov = gp._chol_cov_including_noise(vn, pk)
+        assert_close(chol, g["chol"][s], rtol=1e-10, atol=1e-14)
+        assert isinstance(gp.log_likelihood(vn, mu, pk), float)
+        assert_close(gp.log_likelihood(vn, mu, pk), g["llh"][s], rtol=1e-11)
+        assert_close(gp.grad_log_likelihood(vn, mu, pk), g["grad_llh"][s], rtol=1e-8, atol=1e-9)
+        post = gp.compute_posterior_parameters(g["query"], vn, mu, pk)
+        assert_close(post["mean"], g["post_mean"][s], rtol=1e-10)
+        assert_close(post["cov"], g["post_cov"][s], rtol=max(1e-8, 10 * cond_rtol(g, s)), atol=1e-11)
+        one = gp.compute_posterior_parameters(g["query"][0:1], vn, mu, pk)
+        assert one["cov"].shape == (1, 1)
+        gr = gp.gradient_posterior_parameters(g["query"][1:2], vn, mu, pk)
+        assert_close(gr["mean"], g["grad_post_mean"][s, 1], rtol=1e-9, atol=1e-13)
+        assert_close(gr["cov"].reshape(-1), g["grad_post_cov"][s, 1], rtol=1e-8, atol=1e-12)
+    sol = gp._cholesky_solve_vectors_for_posterior(*[g["thetas"][0][0], g["thetas"][0][1],
+                                                    g["thetas"][0][2:]])
+    assert sol["chol"].shape == g["chol"][0].shape and sol["solve"].shape == (len(g["points"]),)
+    llb = gp.log_likelihood_batch(g["thetas"])
+    assert_close(llb, g["llh"], rtol=1e-11)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_quadrature_and_sbo_facade_against_reference(golden, name):
+    from bayesian_quadrature_optimization_b200.acquisition_functions.sbo import SBO
+    g = golden(name)
+    gp, bq = _models(g)
+    disc = g["discretization"] if "discretization" in g else None
+    sbo = SBO(bq, disc)
+    xq, cands, zs = g["xq"], g["cands"], g["zs"]
+    for s, th in enumerate(g["thetas"]):
+        vn, mu, pk = th[0], th[1], th[2:]
+        tol = cond_rtol(g, s)
+        for p in range(xq.shape[0]):
+            x = xq[p:p + 1, :]
+            assert_close(bq.evaluate_quadrature_cross_cov(x, g["points"], pk), g["B"][s, p],
+                         rtol=1e-12)
+            assert_close(bq.evaluate_grad_quadrature_cross_cov(x, g["points"], pk),
+                         g["grad_B"][s, p], rtol=1e-10, atol=1e-16)
+            post = bq.compute_posterior_parameters(x, vn, mu, pk, only_mean=True)
+            assert_close(post["mean"][0], g["q_mean"][s, p], rtol=1e-10)
+            assert_close(bq.gradient_posterior_mean(x, vn, mu, pk), g["grad_q_mean"][s, p],
+                         rtol=1e-9, atol=1e-13)
+            if "w100" not in g:  # finite W: the double expectation is exact
+                full = bq.compute_posterior_parameters(x, vn, mu, pk)
+                assert_close(full["cov"], g["q_var"][s, p], rtol=max(1e-8, tol), atol=1e-11)
+        for c in range(cands.shape[0]):
+            cand = cands[c:c + 1, :]
+            par = bq.get_parameters_for_samples(True, cand, pk, vn, mu)
+            assert_close(par["gamma"][:, 0], g["gamma"][s, c], rtol=1e-13)
+            assert_close(par["solve_2"][:, 0], g["solve_2"][s, c], rtol=max(1e-8, tol), atol=1e-12)
+            assert_close(par["denominator"][0], g["den"][s, c], rtol=1e-9)
+            for p in range(xq.shape[0]):
+                x = xq[p:p + 1, :]
+                v = bq.compute_parameters_for_sample(x, cand, vn, mu, pk)
+                gr = bq.compute_gradient_parameters_for_sample(x, cand, vn, mu, pk)
+                got = np.concatenate([v["a"], v["b"].reshape(-1), gr["a"], gr["b"]])
+                assert_close(got, g["ab"][s, c, p], rtol=tol, atol=1e-11)
+                for iz, z in enumerate(zs):
+                    val = sbo.evaluate_sample(x, cand, z, vn, mu, pk)
+                    assert_close(val, g["sample_val"][s, c, p, iz], rtol=tol, atol=1e-11)
+            gvb = bq.gradient_vector_b(cand, xq, vn, mu, pk)
+            assert gvb.shape == g["gvb"][s, c].shape
+            assert_close(gvb, g["gvb"][s, c], rtol=10 * tol, atol=1e-11)
+            if disc is not None:
+                assert_close(sbo.evaluate(cand, vn, mu, pk), g["kg"][s, c], rtol=1e-8, atol=1e-13)
+                assert_close(sbo.evaluate_gradient(cand, vn, mu, pk), g["grad_kg"][s, c],
+                             rtol=1e-7, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_ei_facade_and_bayesian_average(golden, name):
+    from bayesian_quadrature_optimization_b200.acquisition_functions.ei import EI
+    g = golden(name)
+    gp, _ = _models(g)
+    ei = EI(gp)
+    vals = []
+    for s, th in enumerate(g["thetas"]):
+        vn, mu, pk = th[0], th[1], th[2:]
+        for q in range(g["query"].shape[0]):
+            pt = g["query"][q:q + 1, :]
+            assert_close(ei.evaluate(pt, vn, mu, pk)[0], g["ei"][s, q], rtol=1e-8, atol=1e-300)
+            assert_close(ei.evaluate_gradient(pt, vn, mu, pk), g["grad_ei"][s, q], rtol=1e-7,
+                         atol=1e-300)
+    gp.samples_parameters = [t.copy() for t in g["thetas"]]
+    avg, _ = ei.evaluate_bayesian(g["query"], n_samples_parameters=3)
+    assert_close(avg, g["ei"].mean(axis=0), rtol=1e-8, atol=1e-300)
+
+
+@pytest.mark.parametrize("name", ["product_uniform", "product_weighted"])
+def test_chosen_task_index_is_exact(golden, name):
+    """MultiTasks.choose_best_task_given_x: argmax over tasks of the Bayesian-averaged EI of F at
+    (x, t) -- the index must equal the oracle's (bit-exact contract of the north star)."""
+    from bayesian_quadrature_optimization_b200.acquisition_functions.multi_task import MultiTasks
+    g = golden(name)
+    gp, bq = _models(g)
+    gp.samples_parameters = [t.copy() for t in g["thetas"]]
+    spec, ogp, obq = oracle_from_golden(g)
+    T = int(g["n_tasks"])
+    mt = MultiTasks(bq, T)
+    rng = np.random.RandomState(0)
+    dx = int(g["dx"])
+    hi = 100.0 if g["points"][:, 0].max() > 2 else 1.0
+    for _ in range(6):
+        x = rng.uniform(0, hi, dx)
+        task, value = mt.choose_best_task_given_x(x)
+        want = []
+        for t in range(T):
+            pt = np.concatenate([x, [float(t)]]).reshape(1, -1)
+            want.append(np.mean([orc.ei_evaluate(ogp, pt, th[0], th[1], th[2:])[0]
+                                 for th in g["thetas"]]))
+        assert task == int(np.argmax(want))
+        assert_close(value, np.max(want), rtol=1e-8, atol=1e-300)
+    sol = mt.optimize(random_seed=3, n_restarts=20, n_samples_parameters=0, start_new_chain=False)
+    assert sol["solution"].shape == (dx + 1,) and 0 <= int(sol["solution"][-1]) < T
+
+
+def test_mc_acquisition_through_public_api(golden):
+    """evaluate_mc_bayesian_candidate_points_no_restarts and evaluate_sbo_by_sample through the
+    reference-facing classes, against the oracle evaluated at the device's own maximisers."""
+    from bayesian_quadrature_optimization_b200.acquisition_functions.sbo import SBO
+    g = golden("product_weighted")
+    gp, bq = _models(g)
+    gp.samples_parameters = [t.copy() for t in g["thetas"]]
+    sbo = SBO(bq)
+    spec, ogp, obq = oracle_from_golden(g)
+    np.random.seed(4)
+    out = sbo.evaluate_mc_bayesian_candidate_points_no_restarts(
+        g["cands"], 3, 6, n_restarts=3, compute_max_mean=True, compute_gradient=True,
+        factr=1e12, maxiter=10)
+    assert out["evaluations"].shape == (2,) and out["gradient"].shape == g["cands"].shape
+    assert np.all(np.isfinite(out["evaluations"])) and np.all(out["gradient"][:, -1] == 0.0)
+    th = g["thetas"][1]
+    r = sbo.evaluate_sbo_by_sample(g["cands"][0:1], 0.6, var_noise=th[0], mean=th[1],
+                                   parameters_kernel=th[2:], n_restarts=4, factr=1e12, maxiter=10)
+    v = obq.compute_parameters_for_sample(r["optimum"], g["cands"][0:1], th[0], th[1], th[2:])
+    assert_close(r["max"], v["a"][0] + 0.6 * np.asarray(v["b"]).reshape(-1)[0], rtol=1e-9)
+    # the maximum dominates every box vertex and random point
+    osbo = orc.OracleSBO(obq, [(0.0, 1.0)] * 2)
+    for x in np.random.RandomState(1).uniform(0, 1, (20, 2)):
+        assert r["max"] >= osbo.evaluate_sample(x, g["cands"][0:1], 0.6, th[0], th[1], th[2:]) - 1e-3
+
+
+def test_slice_sampling_chain_and_sbo_optimize():
+    """Hyper-posterior chain on the GPU likelihood, then SBO.optimize (multi-start SGD)."""
+    from bayesian_quadrature_optimization_b200.models.gp_fitting_gaussian import GPFittingGaussian
+    from bayesian_quadrature_optimization_b200.numerical_tools.bayesian_quadrature import \
+        BayesianQuadrature
+    from bayesian_quadrature_optimization_b200.acquisition_functions.sbo import SBO
+    from bayesian_quadrature_optimization_b200.lib import constant as K
+    rng = np.random.RandomState(0)
+    n, T = 24, 2
+    x = rng.uniform(0, 1, (n, 1))
+    t = rng.randint(0, T, n)
+    pts = np.concatenate([x, t.reshape(-1, 1).astype(float)], 1)
+    y = np.sin(4 * x[:, 0]) + 0.5 * t
+    td = {"points": pts.tolist(), "evaluations": list(y), "var_noise": []}
+
+    def make(seed):
+        return GPFittingGaussian(
+            [K.PRODUCT_KERNELS_SEPARABLE, K.MATERN52_NAME, K.TASKS_KERNEL_NAME], td, [2, 1, T],
+            bounds_domain=[[0, 1], [0, 1]], type_bounds=[0, 1], thinning=1, n_burning=4,
+            max_steps_out=20, random_seed=seed, **{K.SAME_CORRELATION: True})
+
+    gp = make(1)
+    s1 = gp.sample_parameters(3, random_seed=7)
+    gp2 = make(1)
+    s2 = gp2.sample_parameters(3, random_seed=7)
+    assert len(s1) == 3 and all(np.all(np.isfinite(v)) for v in s1)
+    assert_close(np.array(s1), np.array(s2), rtol=1e-9)            # seeded chain reproduces
+    for v in s1:
+        assert v[0] == 0.0 and v[1] == 0.0 and v[2] > 0.0          # noise-free model, ls > 0
+        assert np.isfinite(gp.log_prob_parameters(v))
+    bq = BayesianQuadrature(gp, [0], K.UNIFORM_FINITE, parameters_distribution={K.TASKS: T})
+    sbo = SBO(bq)
+    res = sbo.optimize(random_seed=2, monte_carlo=True, n_samples=2, n_restarts_mc=2, n_restarts=2,
+                       n_samples_parameters=2, start_new_chain=False, maxepoch=3,
+                       default_n_samples=4, default_n_samples_parameters=3, factr=1e12, maxiter=10)
+    assert res["solution"].shape == (2,) and 0.0 <= res["solution"][0] <= 1.0
+    assert int(res["solution"][1]) in (0, 1) and np.isfinite(res["optimal_value"])
+
+
+def test_bgo_end_to_end_small():
+    from bayesian_quadrature_optimization_b200.services.bgo import bgo
+
+    def g(x):
+        return [-(x[0] - 0.3) ** 2]
+
+    def f(xw):
+        return [-(xw[0] - 0.3) ** 2 + (0.2 if int(xw[1]) == 0 else -0.2)]
+
+    sol = bgo(g, [(0.0, 1.0)], integrand_function=f, bounds_domain_w=[[0, 1]], type_bounds=[0, 1],
+              name_method='bqo', n_iterations=1, random_seed=3, n_training=6, thinning=1,
+              n_burning=2, max_steps_out=10, n_restarts=2, n_samples_parameters=2, maxepoch=2,
+              n_samples_mc=2, n_restarts_mc=2, default_n_samples=4, default_n_samples_parameters=3,
+              n_restarts_mean=10)
+    assert set(sol) == {"optimal_solution", "optimal_value"}
+    assert sol["optimal_solution"].shape == (1,) and 0.0 <= sol["optimal_solution"][0] <= 1.0
+    sol = bgo(g, [(0.0, 1.0)], name_method='ei', n_iterations=1, random_seed=3, n_training=5,
+              thinning=1, n_burning=2, max_steps_out=10, n_restarts=3, n_samples_parameters=2,
+              maxepoch=2, n_restarts_mean=10)
+    assert 0.0 <= sol["optimal_solution"][0] <= 1.0 and np.isfinite(sol["optimal_value"])
