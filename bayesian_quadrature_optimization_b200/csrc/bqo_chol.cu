@@ -49,16 +49,23 @@ __device__ int potrf_block_smem(double* Ls, int nv, int* flag_sm) {
     return 0;
 }
 
-// Diagonal block kernel: factor the NB x NB block at k0 in place (only launched for k0 = 0; the
-// later diagonal blocks are factored by the trailing-update CTA that finalises them).
-__global__ void __launch_bounds__(128) potrf_diag_kernel(double* __restrict__ A, int n, int k0,
-                                                         int* __restrict__ info) {
+// Panel kernel for block column k0.  grid = (row tiles from the diagonal tile down, S).
+// Every CTA factors the 64x64 diagonal block in its own shared memory (redundant, ~5 us, but it
+// removes the launch and the global synchronisation a separate diagonal kernel would need) and
+// then solves its 64 rows of the panel, X L11^T = A21, one thread per row with L11 broadcast
+// from shared memory.  The diagonal tile's CTA stores the factor in `diag_scratch` instead of in
+// place: the other CTAs of this launch still read the unfactored block from A.
+__global__ void __launch_bounds__(128) potrf_panel_kernel(double* __restrict__ A, int n, int k0,
+                                                          int* __restrict__ info,
+                                                          double* __restrict__ diag_scratch) {
     extern __shared__ double dyn_smem[];
     double* Ls = dyn_smem;
     __shared__ int flag;
-    const int s = blockIdx.x;
+    const int s = blockIdx.y;
+    if (info[s] != 0) return;  // this matrix already failed
     double* As = A + (int64_t)s * n * n;
     const int nv = (n - k0 < NB) ? n - k0 : NB;
+    const int nb = (n + NB - 1) / NB;
     const int t = threadIdx.x;
     for (int e = t; e < NB * NB; e += blockDim.x) {
         int r = e / NB, c = e % NB;
@@ -69,31 +76,18 @@ __global__ void __launch_bounds__(128) potrf_diag_kernel(double* __restrict__ A,
     __syncthreads();
     int bad = potrf_block_smem(Ls, nv, &flag);
     if (bad) {
-        if (t == 0) info[s] = k0 + bad;
+        if (blockIdx.x == 0 && t == 0) info[s] = k0 + bad;
         return;
     }
-    for (int e = t; e < NB * NB; e += blockDim.x) {
-        int r = e / NB, c = e % NB;
-        if (r < nv && c <= r) As[(int64_t)(k0 + r) * n + (k0 + c)] = Ls[r * LDT + c];
+    if (blockIdx.x == 0) {
+        double* dst = diag_scratch + ((int64_t)s * nb + k0 / NB) * NB * NB;
+        for (int e = t; e < NB * NB; e += blockDim.x) {
+            int r = e / NB, c = e % NB;
+            dst[e] = (r < nv && c <= r) ? Ls[r * LDT + c] : 0.0;
+        }
+        return;
     }
-}
-
-// Panel solve for block column k0: rows below the diagonal block, X L11^T = A21.
-// grid = (row tiles below the diagonal, S); one thread per row, L11 broadcast from smem.
-__global__ void __launch_bounds__(128) potrf_trsm_kernel(double* __restrict__ A, int n, int k0,
-                                                         const int* __restrict__ info) {
-    extern __shared__ double dyn_smem[];
-    double* Ls = dyn_smem;
-    const int s = blockIdx.y;
-    if (info[s] != 0) return;  // this matrix already failed
-    double* As = A + (int64_t)s * n * n;
-    const int t = threadIdx.x;
-    for (int e = t; e < NB * NB; e += blockDim.x) {
-        int r = e / NB, c = e % NB;
-        Ls[r * LDT + c] = (c <= r) ? As[(int64_t)(k0 + r) * n + (k0 + c)] : 0.0;
-    }
-    __syncthreads();
-    const int row = k0 + NB + blockIdx.x * NB + t;
+    const int row = k0 + blockIdx.x * NB + t;
     if (t < NB && row < n) {
         double x[NB];
         double* ap = As + (int64_t)row * n + k0;
@@ -112,14 +106,11 @@ __global__ void __launch_bounds__(128) potrf_trsm_kernel(double* __restrict__ A,
 }
 
 // Trailing update: A[i][j] -= sum_k L[i][k0+k] L[j][k0+k] for i, j >= k0 + NB, lower tiles only.
-// The CTA of tile (0,0) finalises the next diagonal block and factors it on the spot.
 __global__ void __launch_bounds__(128) potrf_syrk_kernel(double* __restrict__ A, int n, int k0,
-                                                         int* __restrict__ info) {
+                                                         const int* __restrict__ info) {
     extern __shared__ double dyn_smem[];
     double* Asm = dyn_smem;
     double* Bsm = Asm + BQO_OPER_TILE_DOUBLES;
-    double* Ls = Bsm + BQO_OPER_TILE_DOUBLES;
-    __shared__ int flag;
     const int s = blockIdx.z;
     if (info[s] != 0) return;
     const int bi = blockIdx.y, bj = blockIdx.x;
@@ -133,57 +124,52 @@ __global__ void __launch_bounds__(128) potrf_syrk_kernel(double* __restrict__ A,
     acc.zero();
     bqo_gemm_tile<true, true>(acc, As + (int64_t)i0 * n + k0, n, ri, As + (int64_t)j0 * n + k0, n,
                               rj, NB, Asm, Bsm);
-    if (bi == 0 && bj == 0) {
-        bqo_acc_foreach(acc, [&](int r, int c, double& v) {
-            double a = (r < ri && c <= r && c < rj) ? As[(int64_t)(i0 + r) * n + (j0 + c)] - v : 0.0;
-            Ls[r * LDT + c] = a;
-        });
-        __syncthreads();
-        int bad = potrf_block_smem(Ls, ri, &flag);
-        if (bad) {
-            if (threadIdx.x == 0) info[s] = i0 + bad;
-            return;
-        }
-        for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
-            int r = e / NB, c = e % NB;
-            if (r < ri && c <= r) As[(int64_t)(i0 + r) * n + (j0 + c)] = Ls[r * LDT + c];
-        }
-        return;
-    }
     bqo_acc_foreach(acc, [&](int r, int c, double& v) {
         if (r < ri && c < rj) As[(int64_t)(i0 + r) * n + (j0 + c)] -= v;
     });
 }
 
-__global__ void zero_upper_kernel(double* __restrict__ A, int n) {
+// Copies the factored diagonal blocks into place and zeroes the strict upper triangle
+// (scipy dpotrf clean=1).
+__global__ void potrf_finish_kernel(double* __restrict__ A, int n, const int* __restrict__ info,
+                                    const double* __restrict__ diag_scratch) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     int i = blockIdx.y;
     int s = blockIdx.z;
-    if (j < n && j > i) A[((int64_t)s * n + i) * n + j] = 0.0;
+    if (j >= n) return;
+    if (j > i) {
+        A[((int64_t)s * n + i) * n + j] = 0.0;
+    } else if (i / NB == j / NB && info[s] == 0) {
+        const int nb = (n + NB - 1) / NB;
+        const int kb = i / NB;
+        A[((int64_t)s * n + i) * n + j] =
+            diag_scratch[(((int64_t)s * nb + kb) * NB + (i - kb * NB)) * NB + (j - kb * NB)];
+    }
 }
 
 #define SMEM_LS ((size_t)NB * LDT * sizeof(double))
-#define SMEM_SYRK ((size_t)(2 * BQO_OPER_TILE_DOUBLES + NB * LDT) * sizeof(double))
+#define SMEM_SYRK ((size_t)(2 * BQO_OPER_TILE_DOUBLES) * sizeof(double))
 #define SMEM_TRSM ((size_t)(2 * BQO_OPER_TILE_DOUBLES + 2 * NB * LDT) * sizeof(double))
 
 static int potrf_launch(double* A, int n, int S, int* info, cudaStream_t cs) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(potrf_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)SMEM_SYRK);
-        attr_done = true;
-    }
+    const int nb = (n + NB - 1) / NB;
+    double* diag_scratch = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&diag_scratch, sizeof(double) * (size_t)S * nb * NB * NB, cs);
+    if (e != cudaSuccess) return (int)e;
     cudaMemsetAsync(info, 0, sizeof(int) * S, cs);
-    potrf_diag_kernel<<<S, 128, SMEM_LS, cs>>>(A, n, 0, info);
-    for (int k0 = 0; k0 + NB < n; k0 += NB) {
-        int tr = (n - k0 - NB + NB - 1) / NB;  // row tiles below the diagonal block
-        dim3 pg(tr, S);
-        potrf_trsm_kernel<<<pg, 128, SMEM_LS, cs>>>(A, n, k0, info);
-        dim3 sg(tr, tr, S);
-        potrf_syrk_kernel<<<sg, 128, SMEM_SYRK, cs>>>(A, n, k0, info);
+    for (int k0 = 0; k0 < n; k0 += NB) {
+        int tiles = (n - k0 + NB - 1) / NB;  // diagonal tile + row tiles below it
+        dim3 pg(tiles, S);
+        potrf_panel_kernel<<<pg, 128, SMEM_LS, cs>>>(A, n, k0, info, diag_scratch);
+        int tr = tiles - 1;
+        if (tr > 0) {
+            dim3 sg(tr, tr, S);
+            potrf_syrk_kernel<<<sg, 128, SMEM_SYRK, cs>>>(A, n, k0, info);
+        }
     }
     dim3 zg((n + 255) / 256, n, S);
-    zero_upper_kernel<<<zg, 256, 0, cs>>>(A, n);
+    potrf_finish_kernel<<<zg, 256, 0, cs>>>(A, n, info, diag_scratch);
+    cudaFreeAsync(diag_scratch, cs);
     return (int)cudaGetLastError();
 }
 
@@ -286,7 +272,7 @@ __global__ void __launch_bounds__(128) trsm_kernel(const double* __restrict__ L,
 }
 
 static int potrs_launch(const double* L, int n, int S, double* Bt, int m, int identity_rhs,
-                        cudaStream_t cs) {
+                        cudaStream_t cs, bool forward_only = false) {
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute(trsm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -297,6 +283,7 @@ static int potrs_launch(const double* L, int n, int S, double* Bt, int m, int id
     }
     dim3 grid((m + NB - 1) / NB, S);
     trsm_kernel<true><<<grid, 128, SMEM_TRSM, cs>>>(L, n, Bt, m, identity_rhs);
+    if (forward_only) return (int)cudaGetLastError();
     trsm_kernel<false><<<grid, 128, SMEM_TRSM, cs>>>(L, n, Bt, m, 0);
     return (int)cudaGetLastError();
 }
@@ -311,8 +298,14 @@ extern "C" int bqo_potrs_batched(const double* L, int32_t n, int32_t S, double* 
     return potrs_launch(L, n, S, Bt, m, 0, (cudaStream_t)stream);
 }
 
-// Internal: Sigma^{-1} via potrs on the identity (used by the log-likelihood gradient).
-int bqo_internal_inverse_from_chol(const double* L, int n, int S, double* Inv, cudaStream_t cs);
+static int trsm_forward_launch(const double* L, int n, int S, double* Bt, int m, int identity_rhs,
+                               cudaStream_t cs) {
+    return potrs_launch(L, n, S, Bt, m, identity_rhs, cs, true);
+}
+
+// Internal: Sigma^{-1} = L^-T L^-1 (used by the log-likelihood gradient).
+int bqo_internal_inverse_from_chol(const double* L, int n, int S, double* Inv, double* Wbuf,
+                                   cudaStream_t cs);
 
 __global__ void set_identity_kernel(double* __restrict__ A, int n) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -321,10 +314,48 @@ __global__ void set_identity_kernel(double* __restrict__ A, int n) {
     if (j < n) A[((int64_t)s * n + i) * n + j] = (i == j) ? 1.0 : 0.0;
 }
 
-int bqo_internal_inverse_from_chol(const double* L, int n, int S, double* Inv, cudaStream_t cs) {
+// Inv = W^T W with W = L^-1 held right-hand-side-major (Wt[r][i] = W[i][r], zero for i < r):
+// Inv[a][b] = sum_{i >= max(a,b)} Wt[a][i] Wt[b][i].  Lower tiles only, K range starts at the
+// tile's first row (the skipped part of W is zero); each tile is also stored transposed so that
+// Inv comes out full and symmetric.  n^3/3 flops instead of the n^3 of a backward solve.
+__global__ void __launch_bounds__(128) inv_syrk_kernel(const double* __restrict__ Wt, int n,
+                                                       double* __restrict__ Inv) {
+    extern __shared__ double dyn_smem[];
+    double* Asm = dyn_smem;
+    double* Bsm = Asm + BQO_OPER_TILE_DOUBLES;
+    const int s = blockIdx.z;
+    const int ba = blockIdx.y, bb = blockIdx.x;
+    if (bb > ba) return;
+    const double* W = Wt + (int64_t)s * n * n;
+    double* Iv = Inv + (int64_t)s * n * n;
+    const int a0 = ba * NB, b0 = bb * NB;
+    const int ra = (n - a0 < NB) ? n - a0 : NB;
+    const int rb = (n - b0 < NB) ? n - b0 : NB;
+    BqoAcc acc;
+    acc.zero();
+    bqo_gemm_tile<true, true>(acc, W + (int64_t)a0 * n + a0, n, ra, W + (int64_t)b0 * n + a0, n, rb,
+                              n - a0, Asm, Bsm);
+    bqo_acc_foreach(acc, [&](int r, int c, double& v) {
+        if (r < ra && c < rb) {
+            Iv[(int64_t)(a0 + r) * n + (b0 + c)] = v;
+            Iv[(int64_t)(b0 + c) * n + (a0 + r)] = v;
+        }
+    });
+}
+
+static int trsm_forward_launch(const double* L, int n, int S, double* Bt, int m, int identity_rhs,
+                               cudaStream_t cs);
+
+int bqo_internal_inverse_from_chol(const double* L, int n, int S, double* Inv, double* Wbuf,
+                                   cudaStream_t cs) {
     dim3 zg((n + 255) / 256, n, S);
-    set_identity_kernel<<<zg, 256, 0, cs>>>(Inv, n);
-    return potrs_launch(L, n, S, Inv, n, 1, cs);
+    set_identity_kernel<<<zg, 256, 0, cs>>>(Wbuf, n);
+    int rc = trsm_forward_launch(L, n, S, Wbuf, n, 1, cs);
+    if (rc) return rc;
+    const int nb = (n + NB - 1) / NB;
+    dim3 sg(nb, nb, S);
+    inv_syrk_kernel<<<sg, 128, SMEM_SYRK, cs>>>(Wbuf, n, Inv);
+    return (int)cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -90,20 +90,70 @@ __device__ __forceinline__ void bqo_mma_slab(BqoAcc& acc, const double* __restri
     }
 }
 
+// Register-staged variant of bqo_load_oper: global -> 8 registers now, registers -> shared later,
+// so that the global loads of slab k+1 are in flight while the DMMAs of slab k execute.
+template <bool KCONTIG>
+__device__ __forceinline__ void bqo_fetch_oper(double (&r)[8], const double* __restrict__ base,
+                                               int64_t ld, int rows_valid, int k_valid) {
+    const int t = threadIdx.x;
+    if (KCONTIG) {
+        int row = t >> 1, kh = (t & 1) * 8;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+            int k = kh + kk;
+            r[kk] = (row < rows_valid && k < k_valid) ? base[(int64_t)row * ld + k] : 0.0;
+        }
+    } else {
+        int k = t >> 3, r0 = (t & 7) * 8;
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+            int row = r0 + rr;
+            r[rr] = (row < rows_valid && k < k_valid) ? base[(int64_t)k * ld + row] : 0.0;
+        }
+    }
+}
+
+template <bool KCONTIG>
+__device__ __forceinline__ void bqo_commit_oper(double* __restrict__ sm, const double (&r)[8]) {
+    const int t = threadIdx.x;
+    if (KCONTIG) {
+        int row = t >> 1, kh = (t & 1) * 8;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) sm[row * BQO_LDK + kh + kk] = r[kk];
+    } else {
+        int k = t >> 3, r0 = (t & 7) * 8;
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) sm[k * BQO_LDR + r0 + rr] = r[rr];
+    }
+}
+
 // Full K loop: acc += sum_k A(row,k) B(col,k).  As/Bs: shared operand buffers of
 // BQO_OPER_TILE_DOUBLES doubles each.  A(row,k) at A[row*lda + k] (A_KCONTIG) or A[k*lda + row];
-// likewise for B with its own leading dimension.
+// likewise for B with its own leading dimension.  Software pipelined: slab k+1 is fetched into
+// registers before the DMMAs of slab k are issued.
 template <bool A_KCONTIG, bool B_KCONTIG>
 __device__ __forceinline__ void bqo_gemm_tile(BqoAcc& acc, const double* __restrict__ A,
                                               int64_t lda, int a_rows, const double* __restrict__ B,
                                               int64_t ldb, int b_rows, int K, double* As,
                                               double* Bs) {
+    if (K <= 0) return;
+    double ra[8], rb[8];
+    {
+        int kv = K < BQO_BK ? K : BQO_BK;
+        bqo_fetch_oper<A_KCONTIG>(ra, A, lda, a_rows, kv);
+        bqo_fetch_oper<B_KCONTIG>(rb, B, ldb, b_rows, kv);
+    }
     for (int k0 = 0; k0 < K; k0 += BQO_BK) {
-        int kv = K - k0 < BQO_BK ? K - k0 : BQO_BK;
+        __syncthreads();  // previous slab's fragments have been read
+        bqo_commit_oper<A_KCONTIG>(As, ra);
+        bqo_commit_oper<B_KCONTIG>(Bs, rb);
         __syncthreads();
-        bqo_load_oper<A_KCONTIG>(As, A_KCONTIG ? A + k0 : A + (int64_t)k0 * lda, lda, a_rows, kv);
-        bqo_load_oper<B_KCONTIG>(Bs, B_KCONTIG ? B + k0 : B + (int64_t)k0 * ldb, ldb, b_rows, kv);
-        __syncthreads();
+        const int kn = k0 + BQO_BK;
+        if (kn < K) {
+            int kv = K - kn < BQO_BK ? K - kn : BQO_BK;
+            bqo_fetch_oper<A_KCONTIG>(ra, A_KCONTIG ? A + kn : A + (int64_t)kn * lda, lda, a_rows, kv);
+            bqo_fetch_oper<B_KCONTIG>(rb, B_KCONTIG ? B + kn : B + (int64_t)kn * ldb, ldb, b_rows, kv);
+        }
         bqo_mma_slab<A_KCONTIG, B_KCONTIG>(acc, As, Bs);
     }
 }

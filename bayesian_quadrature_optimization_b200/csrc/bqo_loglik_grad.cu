@@ -10,7 +10,8 @@
 // per CTA and added in a fixed order, so the result is bit-reproducible.
 #include "bqo_common.cuh"
 
-int bqo_internal_inverse_from_chol(const double* L, int n, int S, double* Inv, cudaStream_t cs);
+int bqo_internal_inverse_from_chol(const double* L, int n, int S, double* Inv, double* Wbuf,
+                                   cudaStream_t cs);
 
 #define LG_MAX_ACC (BQO_MAX_DIM + 4)
 // accumulator slots: [0..dim_m) length scales, then
@@ -149,7 +150,7 @@ __global__ void loglik_grad_final_kernel(bqo_kernel_desc d, const double* __rest
 
 extern "C" int64_t bqo_loglik_grad_workspace_bytes(int32_t n, int32_t S) {
     int64_t nblk = (int64_t)((n + 31) / 32) * ((n + 31) / 32);
-    int64_t d = (int64_t)S * n * n + (int64_t)S * LG_MAX_ACC * nblk + (int64_t)S * 128 * 128;
+    int64_t d = 2 * (int64_t)S * n * n + (int64_t)S * LG_MAX_ACC * nblk + (int64_t)S * 128 * 128;
     return d * (int64_t)sizeof(double);
 }
 
@@ -172,9 +173,10 @@ extern "C" int bqo_loglik_grad_batched(const bqo_kernel_desc* desc, const double
     const int nb = (n + 31) / 32;
     const int64_t nblk = (int64_t)nb * nb;
     double* Inv = (double*)workspace;
-    double* partial = Inv + (int64_t)S * n * n;
+    double* Wbuf = Inv + (int64_t)S * n * n;
+    double* partial = Wbuf + (int64_t)S * n * n;
     double* Wtask = partial + (int64_t)S * LG_MAX_ACC * nblk;
-    int rc = bqo_internal_inverse_from_chol(L, n, S, Inv, cs);
+    int rc = bqo_internal_inverse_from_chol(L, n, S, Inv, Wbuf, cs);
     if (rc) return rc;
     if (desc->kind == BQO_KIND_PRODUCT_TASKS && !desc->same_corr)
         cudaMemsetAsync(Wtask, 0, sizeof(double) * S * desc->n_tasks * desc->n_tasks, cs);
