@@ -209,6 +209,68 @@ __device__ __forceinline__ void bqo_matern52_fast_v(const double (&r2)[NV],
     }
 }
 
+// Leanest form, used by the stage-C evaluation loop.  The caller works in coordinates that are
+// pre-multiplied by sqrt(5) (BQO_PRESCALE), i.e. it passes q2 = 5 r^2, so that
+// s = sqrt5 r = sqrt(q2) needs no multiply.  Returns e = exp(-s) and t1 = 1 + s; with them
+//   k = (t1 + q2/3) e            (1 + sqrt5 r + 5/3 r^2 = t1 + q2/3)
+//   k'(r)/r = -(5/3) t1 e
+// so the caller keeps just two running sums per training point, sum t1 e and sum q2 e.
+// 23 FP64 instructions per evaluation including the distance and the two accumulations:
+//   sqrt 6 (the 1/(2 sqrt) estimate h is not refreshed: the last correction d*h is already
+//   2^-44 small, so h's 2^-22 accuracy suffices), exp 11, t1 1, distance 4, sums 2 - minus one.
+template <int NV>
+__device__ __forceinline__ void bqo_matern52_q_v(const double (&q2)[NV],
+                                                 const double* __restrict__ tab, double (&e)[NV],
+                                                 double (&t1)[NV]) {
+    double g[NV], h[NV], w[NV], kf[NV], fr[NV], p[NV];
+    int n[NV];
+    const double magic = 6755399441055744.0;  // 1.5 * 2^52
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        double y;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(q2[q]));
+        g[q] = q2[q] * y;
+        h[q] = 0.5 * y;
+    }
+#pragma unroll
+    for (int q = 0; q < NV; ++q) w[q] = fma(-h[q], g[q], 0.5);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) g[q] = fma(g[q], w[q], g[q]);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) w[q] = fma(-g[q], g[q], q2[q]);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) g[q] = fma(w[q], h[q], g[q]);  // s = sqrt(q2)
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        double tk = fma(g[q], BQO_FC[1], magic);
+        n[q] = __double2loint(tk);
+        kf[q] = tk - magic;
+    }
+#pragma unroll
+    for (int q = 0; q < NV; ++q) fr[q] = fma(kf[q], BQO_FC[2], -g[q]);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) fr[q] = fma(kf[q], BQO_FC[3], fr[q]);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) p[q] = fma(BQO_FC[4], fr[q], BQO_FC[5]);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) p[q] = fma(p[q], fr[q], BQO_FC[6]);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) p[q] = fma(p[q], fr[q], BQO_FC[7]);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) p[q] = fma(p[q], fr[q], 0.5);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) p[q] = fma(p[q], fr[q], 1.0);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) p[q] = fma(p[q], fr[q], 1.0);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        n[q] = max(n[q], -32000);
+        double ev = p[q] * tab[n[q] & (BQO_EXP_TABLE - 1)];
+        e[q] = __hiloint2double(__double2hiint(ev) + ((n[q] >> 5) << 20), __double2loint(ev));
+        t1[q] = 1.0 + g[q];
+    }
+}
+
 __device__ __forceinline__ double bqo_warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -180,90 +180,123 @@ struct AbOut {
     double ga[DX], gb[DX];
 };
 
+// Operand pointers of one evaluation, kept in registers.  In the inner maximiser they are built
+// straight from the dynamic shared-memory carve-up so that ptxas knows the address space (LDS);
+// loaded back from a struct in shared memory they degrade to generic LD instructions.
+struct EvalPtrs {
+    const double* xs;   // [(DX+DW)][ldx]
+    const double* wa;   // [n]
+    const double* wb;   // [n]
+    const double* tab;  // exp table (shared memory)
+    int ldx, n, M;
+};
+
+template <int DX, int DW>
+__device__ __forceinline__ EvalPtrs eval_ptrs_from(const UnitCtx<DX, DW>& u) {
+    EvalPtrs p;
+    p.xs = u.xs;
+    p.wa = u.wa;
+    p.wb = u.wb;
+    p.tab = u.tab;
+    p.ldx = u.ldx;
+    p.n = u.n;
+    p.M = u.M;
+    return p;
+}
+
 // W samples pushed through the Matern stages together (independent DFMA chains per lane).
 #ifndef EVAL_NV
 #define EVAL_NV 2
 #endif
 
 // Warp-cooperative evaluation of a, b and their x-gradients at the raw point x.
-// `ws`: this evaluation's W samples, already divided by the w length scales, [M][DW].
-template <int DX, int DW>
-__device__ __forceinline__ void eval_ab_warp(const UnitCtx<DX, DW>& u, const double* x,
-                                             const double* __restrict__ ws, AbOut<DX>& o) {
+// Works in coordinates multiplied by sqrt(5) (q2 = 5 r^2, see bqo_matern52_q_v):
+//   `ws`: this evaluation's W samples times sqrt5 / ls_w, [M][DW];
+//   PRE = true: u.xs already holds sqrt5 * X / ls (staged copy); false: X / ls, scaled on load.
+// Per training point only two sums over the W samples are kept, G = sum (1+s) e^-s and
+// H = sum q2 e^-s; then sum_m k = G + H/3 and sum_m k'(r)/r = -(5/3) G.
+template <int DX, int DW, bool PRE>
+__device__ __forceinline__ void eval_ab_warp(const EvalPtrs& p, const UnitCtx<DX, DW>& u,
+                                             const double* x, const double* __restrict__ ws,
+                                             AbOut<DX>& o) {
     const int lane = threadIdx.x & 31;
     double xsc[DX];
 #pragma unroll
-    for (int l = 0; l < DX; ++l) xsc[l] = x[l] / u.ls[l];
+    for (int l = 0; l < DX; ++l) xsc[l] = (x[l] / u.ls[l]) * BQO_SQRT5;
     double Sa = 0.0, Sb = 0.0, GA[DX], GB[DX];
 #pragma unroll
     for (int l = 0; l < DX; ++l) GA[l] = GB[l] = 0.0;
-    const int M = u.M;
-    for (int j = lane; j < u.n; j += 32) {
+    const int M = p.M;
+    for (int j = lane; j < p.n; j += 32) {
         double dxl[DX];
-        double Dx = 1e-300;  // keeps r2 a normal positive number for the fast sqrt (k(0) = 1)
+        double Dx = 1e-300;  // keeps q2 a normal positive number for the fast sqrt (k(0) = 1)
 #pragma unroll
         for (int l = 0; l < DX; ++l) {
-            dxl[l] = xsc[l] - u.xs[l * u.ldx + j];
+            double xj = p.xs[l * p.ldx + j];
+            if (!PRE) xj *= BQO_SQRT5;
+            dxl[l] = xsc[l] - xj;
             Dx = fma(dxl[l], dxl[l], Dx);
         }
-        // ksum = sum_m k(r_m);  gsum = sum_m (1 + sqrt5 r_m) e^{-sqrt5 r_m}, the factor -5/3 of
-        // k'(r)/r is applied once per evaluation after the reduction
-        double ksum = 0.0, gsum = 0.0;
+        double G = 0.0, H = 0.0;
         if (DW > 0) {
             double xw[DW > 0 ? DW : 1];
 #pragma unroll
-            for (int l = 0; l < DW; ++l) xw[l] = u.xs[(DX + l) * u.ldx + j];
+            for (int l = 0; l < DW; ++l) {
+                xw[l] = p.xs[(DX + l) * p.ldx + j];
+                if (!PRE) xw[l] *= BQO_SQRT5;
+            }
             int m = 0;
             for (; m + EVAL_NV <= M; m += EVAL_NV) {
-                double r2v[EVAL_NV], ev[EVAL_NV], t1v[EVAL_NV], pv[EVAL_NV];
+                double q2v[EVAL_NV], ev[EVAL_NV], t1v[EVAL_NV];
 #pragma unroll
                 for (int q = 0; q < EVAL_NV; ++q) {
-                    double r2 = Dx;
+                    double q2 = Dx;
 #pragma unroll
                     for (int l = 0; l < DW; ++l) {
                         double dw = ws[(m + q) * DW + l] - xw[l];
-                        r2 = fma(dw, dw, r2);
+                        q2 = fma(dw, dw, q2);
                     }
-                    r2v[q] = r2;
+                    q2v[q] = q2;
                 }
-                bqo_matern52_fast_v<EVAL_NV>(r2v, u.tab, ev, t1v, pv);
-                double k0 = 0.0, k1 = 0.0, g0 = 0.0, g1 = 0.0;
+                bqo_matern52_q_v<EVAL_NV>(q2v, p.tab, ev, t1v);
+                double g0 = 0.0, g1 = 0.0, h0 = 0.0, h1 = 0.0;
 #pragma unroll
                 for (int q = 0; q < EVAL_NV; ++q) {
                     if (q & 1) {
-                        k1 = fma(pv[q], ev[q], k1);
                         g1 = fma(t1v[q], ev[q], g1);
+                        h1 = fma(q2v[q], ev[q], h1);
                     } else {
-                        k0 = fma(pv[q], ev[q], k0);
                         g0 = fma(t1v[q], ev[q], g0);
+                        h0 = fma(q2v[q], ev[q], h0);
                     }
                 }
-                ksum += k0 + k1;
-                gsum += g0 + g1;
+                G += g0 + g1;
+                H += h0 + h1;
             }
             for (; m < M; ++m) {
-                double r2v[1], ev[1], t1v[1], pv[1];
-                r2v[0] = Dx;
+                double q2v[1], ev[1], t1v[1];
+                q2v[0] = Dx;
 #pragma unroll
                 for (int l = 0; l < DW; ++l) {
                     double dw = ws[m * DW + l] - xw[l];
-                    r2v[0] = fma(dw, dw, r2v[0]);
+                    q2v[0] = fma(dw, dw, q2v[0]);
                 }
-                bqo_matern52_fast_v<1>(r2v, u.tab, ev, t1v, pv);
-                ksum = fma(pv[0], ev[0], ksum);
-                gsum = fma(t1v[0], ev[0], gsum);
+                bqo_matern52_q_v<1>(q2v, p.tab, ev, t1v);
+                G = fma(t1v[0], ev[0], G);
+                H = fma(q2v[0], ev[0], H);
             }
         } else {
-            double r2v[1], ev[1], t1v[1], pv[1];
-            r2v[0] = Dx;
-            bqo_matern52_fast_v<1>(r2v, u.tab, ev, t1v, pv);
-            ksum = pv[0] * ev[0];
-            gsum = t1v[0] * ev[0];
+            double q2v[1], ev[1], t1v[1];
+            q2v[0] = Dx;
+            bqo_matern52_q_v<1>(q2v, p.tab, ev, t1v);
+            G = t1v[0] * ev[0];
+            H = q2v[0] * ev[0];
         }
-        const double wa = u.wa[j], wb = u.wb[j];
+        const double ksum = fma(H, 1.0 / 3.0, G);
+        const double wa = p.wa[j], wb = p.wb[j];
         Sa = fma(ksum, wa, Sa);
         Sb = fma(ksum, wb, Sb);
-        const double ua = gsum * wa, ub = gsum * wb;
+        const double ua = G * wa, ub = G * wb;
 #pragma unroll
         for (int l = 0; l < DX; ++l) {
             GA[l] = fma(ua, dxl[l], GA[l]);
@@ -276,33 +309,36 @@ __device__ __forceinline__ void eval_ab_warp(const UnitCtx<DX, DW>& u, const dou
     for (int l = 0; l < DX; ++l) GC[l] = 0.0;
     for (int m = lane; m < M; m += 32) {
         double dxl[DX];
-        double r2 = 1e-300;
+        double q2v[1], ev[1], t1v[1];
+        q2v[0] = 1e-300;
 #pragma unroll
         for (int l = 0; l < DX; ++l) {
-            dxl[l] = xsc[l] - u.cs[l];
-            r2 = fma(dxl[l], dxl[l], r2);
+            dxl[l] = xsc[l] - u.cs[l] * BQO_SQRT5;
+            q2v[0] = fma(dxl[l], dxl[l], q2v[0]);
         }
 #pragma unroll
         for (int l = 0; l < DW; ++l) {
-            double dw = ws[m * DW + l] - u.cs[DX + l];
-            r2 = fma(dw, dw, r2);
+            double dw = ws[m * DW + l] - u.cs[DX + l] * BQO_SQRT5;
+            q2v[0] = fma(dw, dw, q2v[0]);
         }
-        double k, g;
-        bqo_matern52_kg_fast(r2, u.tab, k, g);
-        Kc += k;
+        bqo_matern52_q_v<1>(q2v, p.tab, ev, t1v);
+        const double gm = t1v[0] * ev[0];
+        Kc += fma(q2v[0] * ev[0], 1.0 / 3.0, gm);
 #pragma unroll
-        for (int l = 0; l < DX; ++l) GC[l] = fma(g, dxl[l], GC[l]);
+        for (int l = 0; l < DX; ++l) GC[l] = fma(gm, dxl[l], GC[l]);
     }
     Sa = bqo_warp_sum(Sa);
     Sb = bqo_warp_sum(Sb);
     Kc = bqo_warp_sum(Kc);
     o.a = u.mean + u.scale * Sa;
     o.b = u.scale * (u.wc * Kc - Sb) * u.inv_den;
+    // d/dx: k'(r)/r * (x - X)/ls^2 = -(5/3) G * (dx'/sqrt5) / ls  with dx' the prescaled difference
+    const double gfac = -BQO_FIVE_THIRDS / BQO_SQRT5;
 #pragma unroll
     for (int l = 0; l < DX; ++l) {
-        double ga = bqo_warp_sum(GA[l]) * (-BQO_FIVE_THIRDS);
-        double gb = bqo_warp_sum(GB[l]) * (-BQO_FIVE_THIRDS);
-        double gc = bqo_warp_sum(GC[l]);
+        double ga = bqo_warp_sum(GA[l]) * gfac;
+        double gb = bqo_warp_sum(GB[l]) * gfac;
+        double gc = bqo_warp_sum(GC[l]) * gfac;
         o.ga[l] = u.scale * ga * u.inv_ls[l];
         o.gb[l] = u.scale * (u.wc * gc - gb) * u.inv_ls[l] * u.inv_den;
     }
@@ -311,10 +347,11 @@ __device__ __forceinline__ void eval_ab_warp(const UnitCtx<DX, DW>& u, const dou
 // Scale one W sample set by the w length scales into `dst` ([M][DW]); executed by a warp.
 template <int DX, int DW>
 __device__ __forceinline__ void scale_wset(const UnitCtx<DX, DW>& u, const double* __restrict__ w,
-                                           double* dst) {
+                                           double* dst, double mult) {
     if (DW == 0) return;
     const int lane = threadIdx.x & 31;
-    for (int e = lane; e < u.M * DW; e += 32) dst[e] = w[e] / u.ls[DX + (e % (DW > 0 ? DW : 1))];
+    for (int e = lane; e < u.M * DW; e += 32)
+        dst[e] = (w[e] / u.ls[DX + (e % (DW > 0 ? DW : 1))]) * mult;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -338,14 +375,15 @@ __global__ void __launch_bounds__(AB_WARPS * 32) sample_ab_kernel(bqo_stage_c pb
     u.tab = dyn_smem;
     if (DW > 0) {
         int wsi = pt_wset ? pt_wset[q] : 0;
-        scale_wset<DX, DW>(u, pb.wsets + (int64_t)wsi * pb.M * DW, ws);
+        scale_wset<DX, DW>(u, pb.wsets + (int64_t)wsi * pb.M * DW, ws, BQO_SQRT5);
         __syncwarp();
     }
     double x[DX];
 #pragma unroll
     for (int l = 0; l < DX; ++l) x[l] = pts[(int64_t)q * DX + l];
     AbOut<DX> o;
-    eval_ab_warp<DX, DW>(u, x, ws, o);
+    const EvalPtrs ep = eval_ptrs_from<DX, DW>(u);
+    eval_ab_warp<DX, DW, false>(ep, u, x, ws, o);
     if (lane == 0) {
         double* op = out + (int64_t)q * (2 + 2 * DX);
         op[0] = o.a;
@@ -494,7 +532,7 @@ __global__ void __launch_bounds__(IM_WARPS * 32, 1)
         const double* gxs = s_u.xs;
         const double* gwa = s_u.wa;
         const double* gwb = s_u.wb;
-        for (int e = threadIdx.x; e < D * n; e += blockDim.x) s_xs[e] = gxs[e];
+        for (int e = threadIdx.x; e < D * n; e += blockDim.x) s_xs[e] = gxs[e] * BQO_SQRT5;
         for (int e = threadIdx.x; e < n; e += blockDim.x) {
             s_wa[e] = gwa[e];
             s_wb[e] = gwb[e];
@@ -507,12 +545,21 @@ __global__ void __launch_bounds__(IM_WARPS * 32, 1)
         }
     }
     const UnitCtx<DX, DW>& u = s_u;
+    EvalPtrs ep;
+    ep.xs = STAGE ? s_xs : pb.Xs + (int64_t)pb.unit_k[unit] * D * n;
+    ep.wa = STAGE ? s_wa : pb.alpha + (int64_t)pb.unit_k[unit] * n;
+    ep.wb = STAGE ? s_wb
+                  : pb.R + (((int64_t)pb.unit_k[unit] * pb.C + pb.unit_c[unit]) * (1 + D)) * n;
+    ep.tab = s_tab;
+    ep.ldx = n;
+    ep.n = n;
+    ep.M = M;
     if (DW > 0) {
         // every evaluation of this unit uses the W set of its candidate (sample-average
         // approximation: the objective of a run is a fixed smooth function)
         const double* wsrc = pb.wsets + (size_t)(pb.unit_c[unit] % pb.n_wsets) * M * DW;
         for (int e = threadIdx.x; e < M * DW; e += blockDim.x)
-            s_ws[e] = wsrc[e] / u.ls[DX + (e % (DW > 0 ? DW : 1))];
+            s_ws[e] = (wsrc[e] / u.ls[DX + (e % (DW > 0 ? DW : 1))]) * BQO_SQRT5;
     }
     if (threadIdx.x == 0) *s_counter = 0;
     const double* st = starts + (opt.starts_per_hyper ? (int64_t)pb.unit_k[unit] * n_starts * DX : 0);
@@ -536,7 +583,7 @@ __global__ void __launch_bounds__(IM_WARPS * 32, 1)
             for (int l = 0; l < DX; ++l) x[l] = ((v >> (DX - 1 - l)) & 1) ? pb.upper[l] : pb.lower[l];
         }
         AbOut<DX> o;
-        eval_ab_warp<DX, DW>(u, x, s_ws, o);
+        eval_ab_warp<DX, DW, STAGE>(ep, u, x, s_ws, o);
         ++evals;
         if (lane == 0) {
             double* op = s_pre + (size_t)p * (2 + 2 * DX);
@@ -637,7 +684,7 @@ __global__ void __launch_bounds__(IM_WARPS * 32, 1)
                     decr = fma(S.g[l], t - S.x[l], decr);
                 }
                 AbOut<DX> o;
-                eval_ab_warp<DX, DW>(u, xn, s_ws, o);
+                eval_ab_warp<DX, DW, STAGE>(ep, u, xn, s_ws, o);
                 ++evals;
                 phin = -(o.a + Z * o.b);
                 if (phin <= S.phi + c1 * decr) {
@@ -864,7 +911,7 @@ __global__ void __launch_bounds__(AB_WARPS * 32)
     if (DW > 0) {
         // default: the W set of the unit's candidate, like the inner maximiser
         int wsi = pt_wset ? pt_wset[gp] : (c % pb.n_wsets);
-        scale_wset<DX, DW>(u, pb.wsets + (int64_t)wsi * pb.M * DW, ws);
+        scale_wset<DX, DW>(u, pb.wsets + (int64_t)wsi * pb.M * DW, ws, 1.0);
         __syncwarp();
     }
     double xsc[DX];
