@@ -71,153 +71,44 @@ __device__ __forceinline__ double bqo_matern52_dr(double r, double r2) {
 }
 
 // ---- fast path of the streaming stage (stage C) ---------------------------------------------
-// Every FP64 instruction counts there (64 DFMA lanes per SM per clock is the roof), so sqrt and
-// exp are open-coded:
-//   sqrt : MUFU.RSQ64H seed (SFU pipe), one Goldschmidt step and one Newton correction;
-//   exp  : exp(-sqrt5 r) = 2^(n/32), n = round(-32 sqrt5 log2(e) r); 2^(n/32) = 2^k T[j] P(f)
-//          with a 32-entry table T[j] = 2^(j/32) in shared memory, a degree-6 Taylor
-//          polynomial P on |f| <= 1/2 (argument <= ln2/64, truncation error 3e-18) and the
-//          power of two applied to the exponent field with integer adds (ALU pipe).
-// Both are accurate to about 1.5 ulp (checked against libm in tests/test_gpu_parity.py).
+// On B200 an FP64 instruction occupies the issue port of an SM sub-partition for two cycles and
+// every other instruction for one (tests/microbench/fp64_issue.cu), and the evaluation loop is
+// bound by exactly that port (profiles/r01_inner_maximize_v1.md).  So every instruction counts,
+// FP64 or not, and sqrt and exp are open-coded:
+//   sqrt : MUFU.RSQ64H seed (SFU pipe), one Goldschmidt step and one Newton correction; the
+//          1/(2 sqrt) estimate h is not refreshed (the last correction d*h is already 2^-44
+//          small, h's 2^-22 accuracy suffices);
+//   exp  : exp(-s) = 2^(n/32) exp(fr), n = round(-32 s / ln2), fr = -s - n ln2/32 by a two-part
+//          Cody-Waite reduction (|fr| <= ln2/64); exp(fr) by the degree-6 Taylor polynomial in
+//          MONIC Horner form (f+6)f+30)f+120)f+360)f+720)f+720 whose coefficients are exact
+//          FP64 immediates (no constant loads), with the common factor 1/720 folded into the
+//          32-entry table T[j] = 2^(j/32) / 720 kept in shared memory; 2^(n>>5) is applied to the
+//          exponent field with integer adds.
+// Accuracy: about 1.8 ulp against libm (tests/test_gpu_parity.py compares the whole a/b path
+// with the reference at 1e-9).
 #define BQO_EXP_TABLE 32
 
-// Constants of the fast path live in constant memory so that DFMA/DMUL read them as c[bank][off]
-// operands; as literals ptxas re-materialises each 64-bit constant with two UMOVs inside the loop
+// Constants that cannot be FP64 immediates live in constant memory so that DFMA reads them as
+// c[bank][off] operands; as literals ptxas re-materialised each with two UMOVs inside the loop
 // (27% of all issued instructions in the first profile, profiles/r01_inner_maximize_v0.md).
-static __constant__ double BQO_FC[10] = {
-    2.23606797749978969640917366873128,   // 0 sqrt(5)
-    -46.16624130844683,                   // 1 -32/ln2
-    -0.02166084938653512,                 // 2 -(ln2/32) high 32 bits
-    -5.9631716539705866e-12,              // 3 -(ln2/32) low part
-    1.0 / 720.0,                          // 4
-    1.0 / 120.0,                          // 5
-    1.0 / 24.0,                           // 6
-    1.0 / 6.0,                            // 7
-    5.0 / 3.0,                            // 8
-    -5.0 / 3.0,                           // 9
+static __constant__ double BQO_FC[3] = {
+    -46.16624130844683,       // 0: -32/ln2
+    -0.02166084938653512,     // 1: -(ln2/32) high 32 bits
+    -5.9631716539705866e-12,  // 2: -(ln2/32) low part
 };
 
 __device__ __forceinline__ void bqo_exp_table_init(double* tab) {
     for (int j = threadIdx.x; j < BQO_EXP_TABLE; j += blockDim.x)
-        tab[j] = exp2((double)j / (double)BQO_EXP_TABLE);
+        tab[j] = exp2((double)j / (double)BQO_EXP_TABLE) / 720.0;
 }
 
-// sqrt(x) for normal x > 0.
-__device__ __forceinline__ double bqo_fast_sqrt(double x) {
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double g = x * y;        // ~ sqrt(x)
-    double h = 0.5 * y;      // ~ 1 / (2 sqrt(x))
-    double r = fma(-h, g, 0.5);
-    g = fma(g, r, g);
-    h = fma(h, r, h);
-    double d = fma(-g, g, x);
-    return fma(d, h, g);
-}
-
-// k(r) and g(r) = k'(r)/r from the squared scaled distance r2 (must be a normal number > 0:
-// callers start the accumulation of r2 at 1e-300).
-__device__ __forceinline__ void bqo_matern52_kg_fast(double r2, const double* __restrict__ tab,
-                                                     double& k, double& g) {
-    const double r = bqo_fast_sqrt(r2);
-    const double s = BQO_FC[0] * r;  // the reference's np.sqrt(5) * r, same rounding
-    // n = round(-s * 32 / ln2); Cody-Waite reduction fr = -s - n ln2/32 with a two-part constant
-    const double magic = 6755399441055744.0;  // 1.5 * 2^52
-    const double tk = fma(s, BQO_FC[1], magic);
-    int n = __double2loint(tk);
-    const double kf = tk - magic;
-    double fr = fma(kf, BQO_FC[2], -s);   // ln2/32, high 32 bits
-    fr = fma(kf, BQO_FC[3], fr);          // ln2/32, low part
-    // exp(fr), |fr| <= ln2/64: Taylor degree 6 (truncation error < 3e-18)
-    double p = fma(BQO_FC[4], fr, BQO_FC[5]);
-    p = fma(p, fr, BQO_FC[6]);
-    p = fma(p, fr, BQO_FC[7]);
-    p = fma(p, fr, 0.5);
-    p = fma(p, fr, 1.0);
-    p = fma(p, fr, 1.0);
-    n = max(n, -32000);  // exp underflow: keep the exponent arithmetic in the normal range
-    double e = p * tab[n & (BQO_EXP_TABLE - 1)];
-    e = __hiloint2double(__double2hiint(e) + ((n >> 5) << 20), __double2loint(e));
-    // k = (1 + sqrt5 r + 5/3 r^2) e,  g = -(5/3)(1 + sqrt5 r) e
-    const double t1 = 1.0 + s;
-    k = fma(BQO_FC[8], r2, t1) * e;
-    g = (t1 * e) * BQO_FC[9];
-}
-
-// NV independent evaluations in lock step.  A single evaluation is one long dependent chain of
-// DFMAs (profiles/r01_inner_maximize_v1.md: 46 % of the warp stalls were fixed-latency waits),
-// so the hot loop feeds NV of them through every stage together; ptxas then has NV independent
-// instructions per stage to interleave.  Outputs: e = exp(-sqrt5 r), t1 = 1 + sqrt5 r and
-// poly = 1 + sqrt5 r + 5/3 r^2, i.e. k = poly e and k'(r)/r = -(5/3) t1 e.
-template <int NV>
-__device__ __forceinline__ void bqo_matern52_fast_v(const double (&r2)[NV],
-                                                    const double* __restrict__ tab,
-                                                    double (&e)[NV], double (&t1)[NV],
-                                                    double (&poly)[NV]) {
-    double g[NV], h[NV], w[NV], s[NV], kf[NV], fr[NV], p[NV];
-    int n[NV];
-    const double magic = 6755399441055744.0;  // 1.5 * 2^52
-#pragma unroll
-    for (int q = 0; q < NV; ++q) {
-        double y;
-        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(r2[q]));
-        g[q] = r2[q] * y;
-        h[q] = 0.5 * y;
-    }
-#pragma unroll
-    for (int q = 0; q < NV; ++q) w[q] = fma(-h[q], g[q], 0.5);
-#pragma unroll
-    for (int q = 0; q < NV; ++q) {
-        g[q] = fma(g[q], w[q], g[q]);
-        h[q] = fma(h[q], w[q], h[q]);
-    }
-#pragma unroll
-    for (int q = 0; q < NV; ++q) w[q] = fma(-g[q], g[q], r2[q]);
-#pragma unroll
-    for (int q = 0; q < NV; ++q) g[q] = fma(w[q], h[q], g[q]);  // r
-#pragma unroll
-    for (int q = 0; q < NV; ++q) s[q] = BQO_FC[0] * g[q];
-#pragma unroll
-    for (int q = 0; q < NV; ++q) {
-        double tk = fma(s[q], BQO_FC[1], magic);
-        n[q] = __double2loint(tk);
-        kf[q] = tk - magic;
-    }
-#pragma unroll
-    for (int q = 0; q < NV; ++q) fr[q] = fma(kf[q], BQO_FC[2], -s[q]);
-#pragma unroll
-    for (int q = 0; q < NV; ++q) fr[q] = fma(kf[q], BQO_FC[3], fr[q]);
-#pragma unroll
-    for (int q = 0; q < NV; ++q) p[q] = fma(BQO_FC[4], fr[q], BQO_FC[5]);
-#pragma unroll
-    for (int q = 0; q < NV; ++q) p[q] = fma(p[q], fr[q], BQO_FC[6]);
-#pragma unroll
-    for (int q = 0; q < NV; ++q) p[q] = fma(p[q], fr[q], BQO_FC[7]);
-#pragma unroll
-    for (int q = 0; q < NV; ++q) p[q] = fma(p[q], fr[q], 0.5);
-#pragma unroll
-    for (int q = 0; q < NV; ++q) p[q] = fma(p[q], fr[q], 1.0);
-#pragma unroll
-    for (int q = 0; q < NV; ++q) p[q] = fma(p[q], fr[q], 1.0);
-#pragma unroll
-    for (int q = 0; q < NV; ++q) {
-        n[q] = max(n[q], -32000);
-        double ev = p[q] * tab[n[q] & (BQO_EXP_TABLE - 1)];
-        e[q] = __hiloint2double(__double2hiint(ev) + ((n[q] >> 5) << 20), __double2loint(ev));
-        t1[q] = 1.0 + s[q];
-        poly[q] = fma(BQO_FC[8], r2[q], t1[q]);
-    }
-}
-
-// Leanest form, used by the stage-C evaluation loop.  The caller works in coordinates that are
-// pre-multiplied by sqrt(5) (BQO_PRESCALE), i.e. it passes q2 = 5 r^2, so that
+// NV independent evaluations in lock step (a single evaluation is one long dependent chain).
+// The caller works in coordinates pre-multiplied by sqrt(5), i.e. it passes q2 = 5 r^2, so that
 // s = sqrt5 r = sqrt(q2) needs no multiply.  Returns e = exp(-s) and t1 = 1 + s; with them
 //   k = (t1 + q2/3) e            (1 + sqrt5 r + 5/3 r^2 = t1 + q2/3)
 //   k'(r)/r = -(5/3) t1 e
 // so the caller keeps just two running sums per training point, sum t1 e and sum q2 e.
-// 23 FP64 instructions per evaluation including the distance and the two accumulations:
-//   sqrt 6 (the 1/(2 sqrt) estimate h is not refreshed: the last correction d*h is already
-//   2^-44 small, so h's 2^-22 accuracy suffices), exp 11, t1 1, distance 4, sums 2 - minus one.
+// q2 must be a normal number > 0 (callers start its accumulation at 1e-300).
 template <int NV>
 __device__ __forceinline__ void bqo_matern52_q_v(const double (&q2)[NV],
                                                  const double* __restrict__ tab, double (&e)[NV],
@@ -242,29 +133,29 @@ __device__ __forceinline__ void bqo_matern52_q_v(const double (&q2)[NV],
     for (int q = 0; q < NV; ++q) g[q] = fma(w[q], h[q], g[q]);  // s = sqrt(q2)
 #pragma unroll
     for (int q = 0; q < NV; ++q) {
-        double tk = fma(g[q], BQO_FC[1], magic);
+        double tk = fma(g[q], BQO_FC[0], magic);
         n[q] = __double2loint(tk);
         kf[q] = tk - magic;
     }
 #pragma unroll
-    for (int q = 0; q < NV; ++q) fr[q] = fma(kf[q], BQO_FC[2], -g[q]);
+    for (int q = 0; q < NV; ++q) fr[q] = fma(kf[q], BQO_FC[1], -g[q]);
 #pragma unroll
-    for (int q = 0; q < NV; ++q) fr[q] = fma(kf[q], BQO_FC[3], fr[q]);
+    for (int q = 0; q < NV; ++q) fr[q] = fma(kf[q], BQO_FC[2], fr[q]);
 #pragma unroll
-    for (int q = 0; q < NV; ++q) p[q] = fma(BQO_FC[4], fr[q], BQO_FC[5]);
+    for (int q = 0; q < NV; ++q) p[q] = fr[q] + 6.0;
 #pragma unroll
-    for (int q = 0; q < NV; ++q) p[q] = fma(p[q], fr[q], BQO_FC[6]);
+    for (int q = 0; q < NV; ++q) p[q] = fma(p[q], fr[q], 30.0);
 #pragma unroll
-    for (int q = 0; q < NV; ++q) p[q] = fma(p[q], fr[q], BQO_FC[7]);
+    for (int q = 0; q < NV; ++q) p[q] = fma(p[q], fr[q], 120.0);
 #pragma unroll
-    for (int q = 0; q < NV; ++q) p[q] = fma(p[q], fr[q], 0.5);
+    for (int q = 0; q < NV; ++q) p[q] = fma(p[q], fr[q], 360.0);
 #pragma unroll
-    for (int q = 0; q < NV; ++q) p[q] = fma(p[q], fr[q], 1.0);
+    for (int q = 0; q < NV; ++q) p[q] = fma(p[q], fr[q], 720.0);
 #pragma unroll
-    for (int q = 0; q < NV; ++q) p[q] = fma(p[q], fr[q], 1.0);
+    for (int q = 0; q < NV; ++q) p[q] = fma(p[q], fr[q], 720.0);
 #pragma unroll
     for (int q = 0; q < NV; ++q) {
-        n[q] = max(n[q], -32000);
+        n[q] = max(n[q], -32000);  // exp underflow: keep the exponent arithmetic in range
         double ev = p[q] * tab[n[q] & (BQO_EXP_TABLE - 1)];
         e[q] = __hiloint2double(__double2hiint(ev) + ((n[q] >> 5) << 20), __double2loint(ev));
         t1[q] = 1.0 + g[q];

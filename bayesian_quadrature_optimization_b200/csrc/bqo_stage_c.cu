@@ -215,7 +215,7 @@ __device__ __forceinline__ EvalPtrs eval_ptrs_from(const UnitCtx<DX, DW>& u) {
 //   PRE = true: u.xs already holds sqrt5 * X / ls (staged copy); false: X / ls, scaled on load.
 // Per training point only two sums over the W samples are kept, G = sum (1+s) e^-s and
 // H = sum q2 e^-s; then sum_m k = G + H/3 and sum_m k'(r)/r = -(5/3) G.
-template <int DX, int DW, bool PRE>
+template <int DX, int DW, bool PRE, int MT = 0>
 __device__ __forceinline__ void eval_ab_warp(const EvalPtrs& p, const UnitCtx<DX, DW>& u,
                                              const double* x, const double* __restrict__ ws,
                                              AbOut<DX>& o) {
@@ -226,7 +226,7 @@ __device__ __forceinline__ void eval_ab_warp(const EvalPtrs& p, const UnitCtx<DX
     double Sa = 0.0, Sb = 0.0, GA[DX], GB[DX];
 #pragma unroll
     for (int l = 0; l < DX; ++l) GA[l] = GB[l] = 0.0;
-    const int M = p.M;
+    const int M = (MT > 0) ? MT : p.M;
     for (int j = lane; j < p.n; j += 32) {
         double dxl[DX];
         double Dx = 1e-300;  // keeps q2 a normal positive number for the fast sqrt (k(0) = 1)
@@ -245,45 +245,54 @@ __device__ __forceinline__ void eval_ab_warp(const EvalPtrs& p, const UnitCtx<DX
                 xw[l] = p.xs[(DX + l) * p.ldx + j];
                 if (!PRE) xw[l] *= BQO_SQRT5;
             }
-            int m = 0;
-            for (; m + EVAL_NV <= M; m += EVAL_NV) {
+            // The W samples do not depend on j: hide that from the optimiser, otherwise the
+            // unrolled build hoists all 2M of them out of the j loop and spills them.
+            const double* wsj = ws;
+            asm volatile("" : "+l"(wsj));
+            // NV W samples go through the Matern stages together; G and H are accumulated directly
+            // (the loop is issue-bound, not latency-bound: no split accumulators).  With MT > 0
+            // the trip count is a compile-time constant: full unroll, W-sample offsets become
+            // immediates and the loop bookkeeping disappears.
+            auto step_nv = [&](int m) {
                 double q2v[EVAL_NV], ev[EVAL_NV], t1v[EVAL_NV];
 #pragma unroll
                 for (int q = 0; q < EVAL_NV; ++q) {
                     double q2 = Dx;
 #pragma unroll
                     for (int l = 0; l < DW; ++l) {
-                        double dw = ws[(m + q) * DW + l] - xw[l];
+                        double dw = wsj[(m + q) * DW + l] - xw[l];
                         q2 = fma(dw, dw, q2);
                     }
                     q2v[q] = q2;
                 }
                 bqo_matern52_q_v<EVAL_NV>(q2v, p.tab, ev, t1v);
-                double g0 = 0.0, g1 = 0.0, h0 = 0.0, h1 = 0.0;
 #pragma unroll
                 for (int q = 0; q < EVAL_NV; ++q) {
-                    if (q & 1) {
-                        g1 = fma(t1v[q], ev[q], g1);
-                        h1 = fma(q2v[q], ev[q], h1);
-                    } else {
-                        g0 = fma(t1v[q], ev[q], g0);
-                        h0 = fma(q2v[q], ev[q], h0);
-                    }
+                    G = fma(t1v[q], ev[q], G);
+                    H = fma(q2v[q], ev[q], H);
                 }
-                G += g0 + g1;
-                H += h0 + h1;
-            }
-            for (; m < M; ++m) {
+            };
+            auto step_1 = [&](int m) {
                 double q2v[1], ev[1], t1v[1];
                 q2v[0] = Dx;
 #pragma unroll
                 for (int l = 0; l < DW; ++l) {
-                    double dw = ws[m * DW + l] - xw[l];
+                    double dw = wsj[m * DW + l] - xw[l];
                     q2v[0] = fma(dw, dw, q2v[0]);
                 }
                 bqo_matern52_q_v<1>(q2v, p.tab, ev, t1v);
                 G = fma(t1v[0], ev[0], G);
                 H = fma(q2v[0], ev[0], H);
+            };
+            if (MT > 0) {
+#pragma unroll
+                for (int m = 0; m + EVAL_NV <= MT; m += EVAL_NV) step_nv(m);
+#pragma unroll
+                for (int m = MT - (MT % EVAL_NV); m < MT; ++m) step_1(m);
+            } else {
+                int m = 0;
+                for (; m + EVAL_NV <= M; m += EVAL_NV) step_nv(m);
+                for (; m < M; ++m) step_1(m);
             }
         } else {
             double q2v[1], ev[1], t1v[1];
@@ -486,7 +495,7 @@ struct RunState {  // per-warp optimiser state in shared memory (warp-uniform va
     double phi;
 };
 
-template <int DX, int DW, bool STAGE>
+template <int DX, int DW, bool STAGE, int MT>
 __global__ void __launch_bounds__(IM_WARPS * 32, 1)
     inner_maximize_kernel(bqo_stage_c pb, bqo_inner_opt opt, const double* __restrict__ z,
                           const double* __restrict__ starts, double* __restrict__ out_max,
@@ -583,7 +592,7 @@ __global__ void __launch_bounds__(IM_WARPS * 32, 1)
             for (int l = 0; l < DX; ++l) x[l] = ((v >> (DX - 1 - l)) & 1) ? pb.upper[l] : pb.lower[l];
         }
         AbOut<DX> o;
-        eval_ab_warp<DX, DW, STAGE>(ep, u, x, s_ws, o);
+        eval_ab_warp<DX, DW, STAGE, MT>(ep, u, x, s_ws, o);
         ++evals;
         if (lane == 0) {
             double* op = s_pre + (size_t)p * (2 + 2 * DX);
@@ -684,7 +693,7 @@ __global__ void __launch_bounds__(IM_WARPS * 32, 1)
                     decr = fma(S.g[l], t - S.x[l], decr);
                 }
                 AbOut<DX> o;
-                eval_ab_warp<DX, DW, STAGE>(ep, u, xn, s_ws, o);
+                eval_ab_warp<DX, DW, STAGE, MT>(ep, u, xn, s_ws, o);
                 ++evals;
                 phin = -(o.a + Z * o.b);
                 if (phin <= S.phi + c1 * decr) {
@@ -857,25 +866,29 @@ extern "C" int bqo_inner_maximize_batched(const bqo_stage_c* pb, const bqo_inner
     BQO_CHECK_ARG(grid64 < 2147483647LL, 1);
     const int grid = (int)grid64;
     if (n_evals) cudaMemsetAsync(n_evals, 0, sizeof(unsigned long long) * pb->n_units, cs);
+#define LAUNCH_IM_K(DXV, DWV, STG, MTV, SB)                                                      \
+    do {                                                                                         \
+        cudaFuncSetAttribute(inner_maximize_kernel<DXV, DWV, STG, MTV>,                          \
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SB));            \
+        inner_maximize_kernel<DXV, DWV, STG, MTV><<<grid, IM_WARPS * 32, (SB), cs>>>(            \
+            *pb, *opt, z, starts, out_max, out_arg, n_evals);                                    \
+    } while (0)
 #define LAUNCH_IM(DXV, DWV)                                                                      \
     do {                                                                                         \
         size_t sb = inner_smem_bytes(pb, opt, true, sizeof(RunState<DXV>));                      \
         if (sb <= 227 * 1024) {                                                                  \
-            cudaFuncSetAttribute(inner_maximize_kernel<DXV, DWV, true>,                          \
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);          \
-            inner_maximize_kernel<DXV, DWV, true><<<grid, IM_WARPS * 32, sb, cs>>>(              \
-                *pb, *opt, z, starts, out_max, out_arg, n_evals);                                \
+            /* M = 10 (N_SAMPLES of sbo/lib/expectations.py:7) gets the fully unrolled build */  \
+            if (DWV > 0 && pb->M == 10) LAUNCH_IM_K(DXV, DWV, true, (DWV > 0 ? 10 : 0), sb);     \
+            else LAUNCH_IM_K(DXV, DWV, true, 0, sb);                                             \
         } else {                                                                                 \
             sb = inner_smem_bytes(pb, opt, false, sizeof(RunState<DXV>));                        \
             if (sb > 227 * 1024) return -2;                                                      \
-            cudaFuncSetAttribute(inner_maximize_kernel<DXV, DWV, false>,                         \
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);          \
-            inner_maximize_kernel<DXV, DWV, false><<<grid, IM_WARPS * 32, sb, cs>>>(             \
-                *pb, *opt, z, starts, out_max, out_arg, n_evals);                                \
+            LAUNCH_IM_K(DXV, DWV, false, 0, sb);                                                 \
         }                                                                                        \
     } while (0)
     SC_DISPATCH(pb, LAUNCH_IM);
 #undef LAUNCH_IM
+#undef LAUNCH_IM_K
     BQO_RETURN_LAST_ERROR();
 }
 
