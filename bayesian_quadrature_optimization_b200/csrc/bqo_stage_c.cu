@@ -215,10 +215,14 @@ __device__ __forceinline__ EvalPtrs eval_ptrs_from(const UnitCtx<DX, DW>& u) {
 //   PRE = true: u.xs already holds sqrt5 * X / ls (staged copy); false: X / ls, scaled on load.
 // Per training point only two sums over the W samples are kept, G = sum (1+s) e^-s and
 // H = sum q2 e^-s; then sum_m k = G + H/3 and sum_m k'(r)/r = -(5/3) G.
-template <int DX, int DW, bool PRE, int MT = 0>
+// CMB = true evaluates F = a + Z b and grad F only, with ONE weight per training point,
+// w_j = wa_j - (Z/den) wb_j (`zd` = Z/den): half the accumulators, half the per-point FMAs and
+// ten registers less in the line-search evaluations of the inner maximiser.  F is returned in
+// o.a and grad F in o.ga (o.b = o.gb = 0).
+template <int DX, int DW, bool PRE, int MT = 0, bool CMB = false>
 __device__ __forceinline__ void eval_ab_warp(const EvalPtrs& p, const UnitCtx<DX, DW>& u,
                                              const double* x, const double* __restrict__ ws,
-                                             AbOut<DX>& o) {
+                                             AbOut<DX>& o, double zd = 0.0) {
     const int lane = threadIdx.x & 31;
     double xsc[DX];
 #pragma unroll
@@ -303,13 +307,21 @@ __device__ __forceinline__ void eval_ab_warp(const EvalPtrs& p, const UnitCtx<DX
         }
         const double ksum = fma(H, 1.0 / 3.0, G);
         const double wa = p.wa[j], wb = p.wb[j];
-        Sa = fma(ksum, wa, Sa);
-        Sb = fma(ksum, wb, Sb);
-        const double ua = G * wa, ub = G * wb;
+        if (CMB) {
+            const double w = fma(-zd, wb, wa);
+            Sa = fma(ksum, w, Sa);
+            const double uw = G * w;
 #pragma unroll
-        for (int l = 0; l < DX; ++l) {
-            GA[l] = fma(ua, dxl[l], GA[l]);
-            GB[l] = fma(ub, dxl[l], GB[l]);
+            for (int l = 0; l < DX; ++l) GA[l] = fma(uw, dxl[l], GA[l]);
+        } else {
+            Sa = fma(ksum, wa, Sa);
+            Sb = fma(ksum, wb, Sb);
+            const double ua = G * wa, ub = G * wb;
+#pragma unroll
+            for (int l = 0; l < DX; ++l) {
+                GA[l] = fma(ua, dxl[l], GA[l]);
+                GB[l] = fma(ub, dxl[l], GB[l]);
+            }
         }
     }
     // candidate term B(x, c): lane m evaluates W sample m
@@ -336,13 +348,28 @@ __device__ __forceinline__ void eval_ab_warp(const EvalPtrs& p, const UnitCtx<DX
 #pragma unroll
         for (int l = 0; l < DX; ++l) GC[l] = fma(gm, dxl[l], GC[l]);
     }
+    // d/dx: k'(r)/r * (x - X)/ls^2 = -(5/3) G * (dx'/sqrt5) / ls  with dx' the prescaled difference
+    const double gfac = -BQO_FIVE_THIRDS / BQO_SQRT5;
+    if (CMB) {
+        Sa = bqo_warp_sum(Sa);
+        Kc = bqo_warp_sum(Kc);
+        const double zc = zd * u.wc;
+        o.a = u.mean + u.scale * fma(zc, Kc, Sa);
+        o.b = 0.0;
+#pragma unroll
+        for (int l = 0; l < DX; ++l) {
+            double gs = bqo_warp_sum(GA[l]);
+            double gc = bqo_warp_sum(GC[l]);
+            o.ga[l] = u.scale * gfac * fma(zc, gc, gs) * u.inv_ls[l];
+            o.gb[l] = 0.0;
+        }
+        return;
+    }
     Sa = bqo_warp_sum(Sa);
     Sb = bqo_warp_sum(Sb);
     Kc = bqo_warp_sum(Kc);
     o.a = u.mean + u.scale * Sa;
     o.b = u.scale * (u.wc * Kc - Sb) * u.inv_den;
-    // d/dx: k'(r)/r * (x - X)/ls^2 = -(5/3) G * (dx'/sqrt5) / ls  with dx' the prescaled difference
-    const double gfac = -BQO_FIVE_THIRDS / BQO_SQRT5;
 #pragma unroll
     for (int l = 0; l < DX; ++l) {
         double ga = bqo_warp_sum(GA[l]) * gfac;
@@ -693,7 +720,7 @@ __global__ void __launch_bounds__(IM_WARPS * 32, 1)
                     decr = fma(S.g[l], t - S.x[l], decr);
                 }
                 AbOut<DX> o;
-                eval_ab_warp<DX, DW, STAGE, MT>(ep, u, xn, s_ws, o);
+                eval_ab_warp<DX, DW, STAGE, MT, true>(ep, u, xn, s_ws, o, Z * u.inv_den);
                 ++evals;
                 phin = -(o.a + Z * o.b);
                 if (phin <= S.phi + c1 * decr) {
