@@ -88,39 +88,47 @@ __device__ __forceinline__ double bqo_matern52_dr(double r, double r2) {
 // with the reference at 1e-9).
 #define BQO_EXP_TABLE 32
 
-// Constants that cannot be FP64 immediates live in constant memory so that DFMA reads them as
-// c[bank][off] operands; as literals ptxas re-materialised each with two UMOVs inside the loop
-// (27% of all issued instructions in the first profile, profiles/r01_inner_maximize_v0.md).
-static __constant__ double BQO_FC[3] = {
-    -46.16624130844683,       // 0: -32/ln2
-    -0.02166084938653512,     // 1: -(ln2/32) high 32 bits
-    -5.9631716539705866e-12,  // 2: -(ln2/32) low part
+// Coordinates of the evaluation loop are pre-multiplied by K = sqrt5 * 32 / ln2, so that for
+// u2 = sum (K dx)^2 the square root u = sqrt(u2) IS the exponent argument in units of ln2/32:
+//   exp(-sqrt5 r) = exp(-u c),  c = ln2/32;   m = round(u);   fr = -(u - m) c  (u - m exact)
+//   exp(-u c) = 2^-(m>>5) * T[m&31] * exp(fr),   T[j] = 2^(-j/32) / 720
+// i.e. the range reduction needs no multiplier constant and no two-part Cody-Waite step.
+#define BQO_PRESCALE 103.23085383134594      // sqrt(5) * 32 / ln(2)
+#define BQO_LN2_32 0.02166084939249829        // ln(2) / 32
+#define BQO_H_TO_K 0.00015639746546816451     // (ln2/32)^2 / 3 : sum k = G + this * H
+#define BQO_GRAD_FAC (-0.016145043897337067)  // -(5/3) / K   : d/dx = this * G * dx' / ls
+
+// The one constant that is not an FP64 immediate lives in constant memory so that DFMA/DMUL read
+// it as a c[bank][off] operand; as literals ptxas re-materialised each 64-bit constant with two
+// UMOVs inside the loop (27% of all issued instructions in the first profile).
+static __constant__ double BQO_FC[1] = {
+    -0.02166084939249829,  // 0: -ln2/32
 };
 
 __device__ __forceinline__ void bqo_exp_table_init(double* tab) {
     for (int j = threadIdx.x; j < BQO_EXP_TABLE; j += blockDim.x)
-        tab[j] = exp2((double)j / (double)BQO_EXP_TABLE) / 720.0;
+        tab[j] = exp2(-(double)j / (double)BQO_EXP_TABLE) / 720.0;
 }
 
 // NV independent evaluations in lock step (a single evaluation is one long dependent chain).
-// The caller works in coordinates pre-multiplied by sqrt(5), i.e. it passes q2 = 5 r^2, so that
-// s = sqrt5 r = sqrt(q2) needs no multiply.  Returns e = exp(-s) and t1 = 1 + s; with them
-//   k = (t1 + q2/3) e            (1 + sqrt5 r + 5/3 r^2 = t1 + q2/3)
-//   k'(r)/r = -(5/3) t1 e
-// so the caller keeps just two running sums per training point, sum t1 e and sum q2 e.
-// q2 must be a normal number > 0 (callers start its accumulation at 1e-300).
-template <int NV>
-__device__ __forceinline__ void bqo_matern52_q_v(const double (&q2)[NV],
-                                                 const double* __restrict__ tab, double (&e)[NV],
+// Input u2 = K^2 r^2 (a normal number > 0: callers start its accumulation at 1e-300).
+// Returns e = exp(-sqrt5 r) and u = K r (so sqrt5 r = u ln2/32); with them
+//   k = (1 + u c + u2 c^2/3) e,      k'(r)/r = -(5/3) (1 + u c) e,      c = ln2/32
+// so the caller keeps three running sums per training point, sum e, sum u e and sum u2 e, and
+// applies the constants once per point (no constant operand inside the W-sample loop).
+// `tab(j)` reads table entry j (a functor so that the caller can index its shared-memory array).
+// FP64 instructions per evaluation: sqrt 6, reduction 4, polynomial 6, table multiply 1, t1 1.
+template <int NV, class Tab>
+__device__ __forceinline__ void bqo_matern52_q_v(const double (&u2)[NV], Tab tab, double (&e)[NV],
                                                  double (&t1)[NV]) {
     double g[NV], h[NV], w[NV], kf[NV], fr[NV], p[NV];
-    int n[NV];
-    const double magic = 6755399441055744.0;  // 1.5 * 2^52
+    unsigned n[NV];
+    const double magic = 4503599627370496.0;  // 2^52: low word of (magic + u) = round(u) >= 0
 #pragma unroll
     for (int q = 0; q < NV; ++q) {
         double y;
-        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(q2[q]));
-        g[q] = q2[q] * y;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(u2[q]));
+        g[q] = u2[q] * y;
         h[q] = 0.5 * y;
     }
 #pragma unroll
@@ -128,19 +136,17 @@ __device__ __forceinline__ void bqo_matern52_q_v(const double (&q2)[NV],
 #pragma unroll
     for (int q = 0; q < NV; ++q) g[q] = fma(g[q], w[q], g[q]);
 #pragma unroll
-    for (int q = 0; q < NV; ++q) w[q] = fma(-g[q], g[q], q2[q]);
+    for (int q = 0; q < NV; ++q) w[q] = fma(-g[q], g[q], u2[q]);
 #pragma unroll
-    for (int q = 0; q < NV; ++q) g[q] = fma(w[q], h[q], g[q]);  // s = sqrt(q2)
+    for (int q = 0; q < NV; ++q) g[q] = fma(w[q], h[q], g[q]);  // u = sqrt(u2)
 #pragma unroll
     for (int q = 0; q < NV; ++q) {
-        double tk = fma(g[q], BQO_FC[0], magic);
-        n[q] = __double2loint(tk);
-        kf[q] = tk - magic;
+        double tk = magic + g[q];
+        n[q] = (unsigned)__double2loint(tk);
+        kf[q] = tk - magic;              // round(u) as a double (exact)
     }
 #pragma unroll
-    for (int q = 0; q < NV; ++q) fr[q] = fma(kf[q], BQO_FC[1], -g[q]);
-#pragma unroll
-    for (int q = 0; q < NV; ++q) fr[q] = fma(kf[q], BQO_FC[2], fr[q]);
+    for (int q = 0; q < NV; ++q) fr[q] = (g[q] - kf[q]) * BQO_FC[0];  // -(u - m) ln2/32
 #pragma unroll
     for (int q = 0; q < NV; ++q) p[q] = fr[q] + 6.0;
 #pragma unroll
@@ -155,10 +161,17 @@ __device__ __forceinline__ void bqo_matern52_q_v(const double (&q2)[NV],
     for (int q = 0; q < NV; ++q) p[q] = fma(p[q], fr[q], 720.0);
 #pragma unroll
     for (int q = 0; q < NV; ++q) {
-        n[q] = max(n[q], -32000);  // exp underflow: keep the exponent arithmetic in range
-        double ev = p[q] * tab[n[q] & (BQO_EXP_TABLE - 1)];
-        e[q] = __hiloint2double(__double2hiint(ev) + ((n[q] >> 5) << 20), __double2loint(ev));
-        t1[q] = 1.0 + g[q];
+        // one unsigned clamp covers exp underflow (u > 32000 -> 2^-1000) and any garbage low word
+        // from absurd arguments (u >= 2^51), keeping the exponent arithmetic in the normal range
+        n[q] = min(n[q], 32000u);
+        double ev = p[q] * tab((int)(n[q] & (BQO_EXP_TABLE - 1)));
+        // 2^-(m >> 5) into the exponent field: hi -= (m & ~31) * 2^15
+        int hi;
+        asm("mad.lo.s32 %0, %1, -32768, %2;"
+            : "=r"(hi)
+            : "r"((int)(n[q] & ~31u)), "r"(__double2hiint(ev)));
+        e[q] = __hiloint2double(hi, __double2loint(ev));
+        t1[q] = g[q];
     }
 }
 

@@ -20,6 +20,15 @@
 
 #define SC_MAX_D BQO_MAX_DIM
 
+// One dynamic shared-memory array for every kernel of this file.  Its first 32 doubles hold the
+// exp table of the fast path; declaring it at file scope lets ptxas fold the table's base
+// address into the LDS immediate.
+extern __shared__ __align__(16) double dyn_smem[];
+
+struct SmemExpTab {
+    __device__ __forceinline__ double operator()(int j) const { return dyn_smem[j]; }
+};
+
 // ---------------------------------------------------------------------------------------------
 // alpha_q[s][j] = q_s[task_j] alpha_s[j]   (PRODUCT), plain copy otherwise.
 __global__ void weight_alpha_kernel(const double* __restrict__ alpha, const double* __restrict__ qt,
@@ -226,7 +235,7 @@ __device__ __forceinline__ void eval_ab_warp(const EvalPtrs& p, const UnitCtx<DX
     const int lane = threadIdx.x & 31;
     double xsc[DX];
 #pragma unroll
-    for (int l = 0; l < DX; ++l) xsc[l] = (x[l] / u.ls[l]) * BQO_SQRT5;
+    for (int l = 0; l < DX; ++l) xsc[l] = (x[l] / u.ls[l]) * BQO_PRESCALE;
     double Sa = 0.0, Sb = 0.0, GA[DX], GB[DX];
 #pragma unroll
     for (int l = 0; l < DX; ++l) GA[l] = GB[l] = 0.0;
@@ -237,17 +246,17 @@ __device__ __forceinline__ void eval_ab_warp(const EvalPtrs& p, const UnitCtx<DX
 #pragma unroll
         for (int l = 0; l < DX; ++l) {
             double xj = p.xs[l * p.ldx + j];
-            if (!PRE) xj *= BQO_SQRT5;
+            if (!PRE) xj *= BQO_PRESCALE;
             dxl[l] = xsc[l] - xj;
             Dx = fma(dxl[l], dxl[l], Dx);
         }
-        double G = 0.0, H = 0.0;
+        double E0 = 0.0, E1 = 0.0, H = 0.0;  // sum e, sum u e, sum u2 e over the W samples
         if (DW > 0) {
             double xw[DW > 0 ? DW : 1];
 #pragma unroll
             for (int l = 0; l < DW; ++l) {
                 xw[l] = p.xs[(DX + l) * p.ldx + j];
-                if (!PRE) xw[l] *= BQO_SQRT5;
+                if (!PRE) xw[l] *= BQO_PRESCALE;
             }
             // The W samples do not depend on j: hide that from the optimiser, otherwise the
             // unrolled build hoists all 2M of them out of the j loop and spills them.
@@ -269,10 +278,11 @@ __device__ __forceinline__ void eval_ab_warp(const EvalPtrs& p, const UnitCtx<DX
                     }
                     q2v[q] = q2;
                 }
-                bqo_matern52_q_v<EVAL_NV>(q2v, p.tab, ev, t1v);
+                bqo_matern52_q_v<EVAL_NV>(q2v, SmemExpTab(), ev, t1v);
 #pragma unroll
                 for (int q = 0; q < EVAL_NV; ++q) {
-                    G = fma(t1v[q], ev[q], G);
+                    E0 += ev[q];
+                    E1 = fma(t1v[q], ev[q], E1);
                     H = fma(q2v[q], ev[q], H);
                 }
             };
@@ -284,8 +294,9 @@ __device__ __forceinline__ void eval_ab_warp(const EvalPtrs& p, const UnitCtx<DX
                     double dw = wsj[m * DW + l] - xw[l];
                     q2v[0] = fma(dw, dw, q2v[0]);
                 }
-                bqo_matern52_q_v<1>(q2v, p.tab, ev, t1v);
-                G = fma(t1v[0], ev[0], G);
+                bqo_matern52_q_v<1>(q2v, SmemExpTab(), ev, t1v);
+                E0 += ev[0];
+                E1 = fma(t1v[0], ev[0], E1);
                 H = fma(q2v[0], ev[0], H);
             };
             if (MT > 0) {
@@ -301,11 +312,13 @@ __device__ __forceinline__ void eval_ab_warp(const EvalPtrs& p, const UnitCtx<DX
         } else {
             double q2v[1], ev[1], t1v[1];
             q2v[0] = Dx;
-            bqo_matern52_q_v<1>(q2v, p.tab, ev, t1v);
-            G = t1v[0] * ev[0];
+            bqo_matern52_q_v<1>(q2v, SmemExpTab(), ev, t1v);
+            E0 = ev[0];
+            E1 = t1v[0] * ev[0];
             H = q2v[0] * ev[0];
         }
-        const double ksum = fma(H, 1.0 / 3.0, G);
+        const double G = fma(E1, BQO_LN2_32, E0);  // sum_m (1 + sqrt5 r_m) e_m
+        const double ksum = fma(H, BQO_H_TO_K, G);
         const double wa = p.wa[j], wb = p.wb[j];
         if (CMB) {
             const double w = fma(-zd, wb, wa);
@@ -334,22 +347,22 @@ __device__ __forceinline__ void eval_ab_warp(const EvalPtrs& p, const UnitCtx<DX
         q2v[0] = 1e-300;
 #pragma unroll
         for (int l = 0; l < DX; ++l) {
-            dxl[l] = xsc[l] - u.cs[l] * BQO_SQRT5;
+            dxl[l] = xsc[l] - u.cs[l] * BQO_PRESCALE;
             q2v[0] = fma(dxl[l], dxl[l], q2v[0]);
         }
 #pragma unroll
         for (int l = 0; l < DW; ++l) {
-            double dw = ws[m * DW + l] - u.cs[DX + l] * BQO_SQRT5;
+            double dw = ws[m * DW + l] - u.cs[DX + l] * BQO_PRESCALE;
             q2v[0] = fma(dw, dw, q2v[0]);
         }
-        bqo_matern52_q_v<1>(q2v, p.tab, ev, t1v);
-        const double gm = t1v[0] * ev[0];
-        Kc += fma(q2v[0] * ev[0], 1.0 / 3.0, gm);
+        bqo_matern52_q_v<1>(q2v, SmemExpTab(), ev, t1v);
+        const double gm = fma(t1v[0], BQO_LN2_32, 1.0) * ev[0];
+        Kc += fma(q2v[0] * ev[0], BQO_H_TO_K, gm);
 #pragma unroll
         for (int l = 0; l < DX; ++l) GC[l] = fma(gm, dxl[l], GC[l]);
     }
     // d/dx: k'(r)/r * (x - X)/ls^2 = -(5/3) G * (dx'/sqrt5) / ls  with dx' the prescaled difference
-    const double gfac = -BQO_FIVE_THIRDS / BQO_SQRT5;
+    const double gfac = BQO_GRAD_FAC;
     if (CMB) {
         Sa = bqo_warp_sum(Sa);
         Kc = bqo_warp_sum(Kc);
@@ -399,7 +412,6 @@ __global__ void __launch_bounds__(AB_WARPS * 32) sample_ab_kernel(bqo_stage_c pb
                                                                   const int32_t* __restrict__ pt_unit,
                                                                   const int32_t* __restrict__ pt_wset,
                                                                   int P, double* __restrict__ out) {
-    extern __shared__ double dyn_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = blockIdx.x * AB_WARPS + warp;
     bqo_exp_table_init(dyn_smem);
@@ -411,7 +423,7 @@ __global__ void __launch_bounds__(AB_WARPS * 32) sample_ab_kernel(bqo_stage_c pb
     u.tab = dyn_smem;
     if (DW > 0) {
         int wsi = pt_wset ? pt_wset[q] : 0;
-        scale_wset<DX, DW>(u, pb.wsets + (int64_t)wsi * pb.M * DW, ws, BQO_SQRT5);
+        scale_wset<DX, DW>(u, pb.wsets + (int64_t)wsi * pb.M * DW, ws, BQO_PRESCALE);
         __syncwarp();
     }
     double x[DX];
@@ -527,7 +539,6 @@ __global__ void __launch_bounds__(IM_WARPS * 32, 1)
     inner_maximize_kernel(bqo_stage_c pb, bqo_inner_opt opt, const double* __restrict__ z,
                           const double* __restrict__ starts, double* __restrict__ out_max,
                           double* __restrict__ out_arg, unsigned long long* __restrict__ n_evals) {
-    extern __shared__ double dyn_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int zc_per_unit = (opt.n_z + opt.z_per_cta - 1) / opt.z_per_cta;
     const int unit = blockIdx.x / zc_per_unit;
@@ -568,7 +579,7 @@ __global__ void __launch_bounds__(IM_WARPS * 32, 1)
         const double* gxs = s_u.xs;
         const double* gwa = s_u.wa;
         const double* gwb = s_u.wb;
-        for (int e = threadIdx.x; e < D * n; e += blockDim.x) s_xs[e] = gxs[e] * BQO_SQRT5;
+        for (int e = threadIdx.x; e < D * n; e += blockDim.x) s_xs[e] = gxs[e] * BQO_PRESCALE;
         for (int e = threadIdx.x; e < n; e += blockDim.x) {
             s_wa[e] = gwa[e];
             s_wb[e] = gwb[e];
@@ -595,7 +606,7 @@ __global__ void __launch_bounds__(IM_WARPS * 32, 1)
         // approximation: the objective of a run is a fixed smooth function)
         const double* wsrc = pb.wsets + (size_t)(pb.unit_c[unit] % pb.n_wsets) * M * DW;
         for (int e = threadIdx.x; e < M * DW; e += blockDim.x)
-            s_ws[e] = (wsrc[e] / u.ls[DX + (e % (DW > 0 ? DW : 1))]) * BQO_SQRT5;
+            s_ws[e] = (wsrc[e] / u.ls[DX + (e % (DW > 0 ? DW : 1))]) * BQO_PRESCALE;
     }
     if (threadIdx.x == 0) *s_counter = 0;
     const double* st = starts + (opt.starts_per_hyper ? (int64_t)pb.unit_k[unit] * n_starts * DX : 0);
@@ -928,7 +939,6 @@ __global__ void __launch_bounds__(AB_WARPS * 32)
     grad_vector_b_kernel(bqo_stage_c pb, const double* __restrict__ pts, int npts,
                          const int32_t* __restrict__ pt_wset, double* __restrict__ out,
                          int32_t* __restrict__ is_nan) {
-    extern __shared__ double dyn_smem[];
     constexpr int D = DX + DW;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t gp = (int64_t)blockIdx.x * AB_WARPS + warp;
