@@ -78,46 +78,78 @@ __device__ __forceinline__ double bqo_matern52_dr(double r, double r2) {
 //   sqrt : MUFU.RSQ64H seed (SFU pipe), one Goldschmidt step and one Newton correction; the
 //          1/(2 sqrt) estimate h is not refreshed (the last correction d*h is already 2^-44
 //          small, h's 2^-22 accuracy suffices);
-//   exp  : exp(-s) = 2^(n/32) exp(fr), n = round(-32 s / ln2), fr = -s - n ln2/32 by a two-part
-//          Cody-Waite reduction (|fr| <= ln2/64); exp(fr) by the degree-6 Taylor polynomial in
-//          MONIC Horner form (f+6)f+30)f+120)f+360)f+720)f+720 whose coefficients are exact
-//          FP64 immediates (no constant loads), with the common factor 1/720 folded into the
-//          32-entry table T[j] = 2^(j/32) / 720 kept in shared memory; 2^(n>>5) is applied to the
-//          exponent field with integer adds.
+//   exp  : table-driven.  With N = 2^BQO_EXP_BITS table entries per octave,
+//          exp(-s) = 2^-(m div N) * 2^-((m mod N)/N) * exp(fr),  m = round(s N / ln2),
+//          |fr| <= ln2 / (2N).  The larger the table the shorter the polynomial for exp(fr):
+//            N = 32   : degree 6, (ln2/64)^7/5040   = 1.2e-17
+//            N = 256  : degree 4, (ln2/512)^5/120   = 3.8e-17
+//            N = 2048 : degree 3, (ln2/4096)^4/24   = 3.4e-17   (16 KB of shared memory)
+//          all below half an ulp.  The polynomial is kept in MONIC Horner form, e.g.
+//          ((f+3)f+6)f+6 = 6 (1 + f + f^2/2 + f^3/6), whose coefficients are exact FP64 immediates
+//          (no constant loads); the common factor (1/6) is folded into the table
+//          T[j] = 2^(-j/N) / 6, and 2^-(m div N) goes into the exponent field with one IMAD.
 // Accuracy: about 1.8 ulp against libm (tests/test_gpu_parity.py compares the whole a/b path
 // with the reference at 1e-9).
-#define BQO_EXP_TABLE 32
+#ifndef BQO_EXP_BITS
+#define BQO_EXP_BITS 11
+#endif
+#define BQO_EXP_TABLE (1 << BQO_EXP_BITS)
+#if BQO_EXP_BITS >= 11
+#define BQO_EXP_DEGREE 3
+#define BQO_EXP_FOLD 6.0
+#elif BQO_EXP_BITS >= 8
+#define BQO_EXP_DEGREE 4
+#define BQO_EXP_FOLD 24.0
+#else
+#define BQO_EXP_DEGREE 6
+#define BQO_EXP_FOLD 720.0
+#endif
 
-// Coordinates of the evaluation loop are pre-multiplied by K = sqrt5 * 32 / ln2, so that for
-// u2 = sum (K dx)^2 the square root u = sqrt(u2) IS the exponent argument in units of ln2/32:
-//   exp(-sqrt5 r) = exp(-u c),  c = ln2/32;   m = round(u);   fr = -(u - m) c  (u - m exact)
-//   exp(-u c) = 2^-(m>>5) * T[m&31] * exp(fr),   T[j] = 2^(-j/32) / 720
+// Coordinates of the evaluation loop are pre-multiplied by K = sqrt5 * N / ln2, so that for
+// u2 = sum (K dx)^2 the square root u = sqrt(u2) IS the exponent argument in units of ln2/N:
+//   exp(-sqrt5 r) = exp(-u c),  c = ln2/N;   m = round(u);   fr = -(u - m) c  (u - m exact)
 // i.e. the range reduction needs no multiplier constant and no two-part Cody-Waite step.
-#define BQO_PRESCALE 103.23085383134594      // sqrt(5) * 32 / ln(2)
-#define BQO_LN2_32 0.02166084939249829        // ln(2) / 32
-#define BQO_H_TO_K 0.00015639746546816451     // (ln2/32)^2 / 3 : sum k = G + this * H
-#define BQO_GRAD_FAC (-0.016145043897337067)  // -(5/3) / K   : d/dx = this * G * dx' / ls
+#define BQO_LN2 0.693147180559945309417232121458
+#define BQO_PRESCALE (BQO_SQRT5 * (double)BQO_EXP_TABLE / BQO_LN2)  // K
+#define BQO_LN2_N (BQO_LN2 / (double)BQO_EXP_TABLE)                 // c = ln2 / N
+#define BQO_H_TO_K (BQO_LN2_N * BQO_LN2_N / 3.0)                    // sum k = G + this * H
+#define BQO_GRAD_FAC (-BQO_FIVE_THIRDS / BQO_PRESCALE)              // d/dx = this * G * dx' / ls
 
 // The one constant that is not an FP64 immediate lives in constant memory so that DFMA/DMUL read
 // it as a c[bank][off] operand; as literals ptxas re-materialised each 64-bit constant with two
 // UMOVs inside the loop (27% of all issued instructions in the first profile).
-static __constant__ double BQO_FC[1] = {
-    -0.02166084939249829,  // 0: -ln2/32
+static __constant__ double BQO_FC[4] = {
+    -BQO_LN2_N,                                      // 0: -c = -ln2/N
+    -3.0 / BQO_LN2_N,                                // 1: b2 }  6 exp(-c d) / (-c^3) =
+    6.0 / (BQO_LN2_N * BQO_LN2_N),                   // 2: b1 }    ((d + b2) d + b1) d + b0
+    -6.0 / (BQO_LN2_N * BQO_LN2_N * BQO_LN2_N),      // 3: b0 }  (degree 3, N = 2048)
 };
+// Degree-3 variant that skips the multiplication by -c: the polynomial is taken in d = u - m
+// itself, monic, with its three coefficients as uniform-register operands (one LDCU each per
+// training point), and the factor -c^3/6 goes into the table.
+#ifndef BQO_POLY_UR
+#define BQO_POLY_UR (BQO_EXP_DEGREE == 3)
+#endif
+#if BQO_POLY_UR
+#define BQO_TAB_FOLD (-(BQO_LN2_N * BQO_LN2_N * BQO_LN2_N) / 6.0)
+#else
+#define BQO_TAB_FOLD (1.0 / BQO_EXP_FOLD)
+#endif
 
 __device__ __forceinline__ void bqo_exp_table_init(double* tab) {
     for (int j = threadIdx.x; j < BQO_EXP_TABLE; j += blockDim.x)
-        tab[j] = exp2(-(double)j / (double)BQO_EXP_TABLE) / 720.0;
+        tab[j] = exp2(-(double)j / (double)BQO_EXP_TABLE) * BQO_TAB_FOLD;
 }
 
 // NV independent evaluations in lock step (a single evaluation is one long dependent chain).
 // Input u2 = K^2 r^2 (a normal number > 0: callers start its accumulation at 1e-300).
-// Returns e = exp(-sqrt5 r) and u = K r (so sqrt5 r = u ln2/32); with them
-//   k = (1 + u c + u2 c^2/3) e,      k'(r)/r = -(5/3) (1 + u c) e,      c = ln2/32
+// Returns e = exp(-sqrt5 r) and u = K r (so sqrt5 r = u ln2/N); with them
+//   k = (1 + u c + u2 c^2/3) e,      k'(r)/r = -(5/3) (1 + u c) e,      c = ln2/N
 // so the caller keeps three running sums per training point, sum e, sum u e and sum u2 e, and
 // applies the constants once per point (no constant operand inside the W-sample loop).
-// `tab(j)` reads table entry j (a functor so that the caller can index its shared-memory array).
-// FP64 instructions per evaluation: sqrt 6, reduction 4, polynomial 6, table multiply 1, t1 1.
+// `tab(m)` reads table entry m mod N (a functor so that the caller decides how the shared-memory
+// address is formed).
+// FP64 instructions per evaluation (N = 2048): sqrt 6, reduction 4, polynomial 3, table multiply 1.
 template <int NV, class Tab>
 __device__ __forceinline__ void bqo_matern52_q_v(const double (&u2)[NV], Tab tab, double (&e)[NV],
                                                  double (&t1)[NV]) {
@@ -141,12 +173,47 @@ __device__ __forceinline__ void bqo_matern52_q_v(const double (&u2)[NV], Tab tab
     for (int q = 0; q < NV; ++q) g[q] = fma(w[q], h[q], g[q]);  // u = sqrt(u2)
 #pragma unroll
     for (int q = 0; q < NV; ++q) {
+        // One unsigned clamp of the HIGH word of u (u > 0, so the word is monotone in u) bounds
+        // u below 2^(BITS+9) + 1: exp(-u c) stops at 2^-512, k <= 1e-150, instead of decaying
+        // further, the low word of magic + u can never wrap, and the exponent arithmetic below
+        // stays inside the normal range whatever the inputs (tiny length scales included).
+        unsigned uh = min((unsigned)__double2hiint(g[q]), (unsigned)((1023 + BQO_EXP_BITS + 9) << 20));
+        g[q] = __hiloint2double((int)uh, __double2loint(g[q]));
         double tk = magic + g[q];
         n[q] = (unsigned)__double2loint(tk);
         kf[q] = tk - magic;              // round(u) as a double (exact)
     }
+#if BQO_POLY_UR
 #pragma unroll
-    for (int q = 0; q < NV; ++q) fr[q] = (g[q] - kf[q]) * BQO_FC[0];  // -(u - m) ln2/32
+    for (int q = 0; q < NV; ++q) fr[q] = g[q] - kf[q];  // d = u - m
+#pragma unroll
+    for (int q = 0; q < NV; ++q) p[q] = fr[q] + BQO_FC[1];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) p[q] = fma(p[q], fr[q], BQO_FC[2]);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) p[q] = fma(p[q], fr[q], BQO_FC[3]);
+#else
+#pragma unroll
+    for (int q = 0; q < NV; ++q) fr[q] = (g[q] - kf[q]) * BQO_FC[0];  // -(u - m) ln2/N
+#endif
+#if BQO_POLY_UR
+#elif BQO_EXP_DEGREE == 3
+#pragma unroll
+    for (int q = 0; q < NV; ++q) p[q] = fr[q] + 3.0;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) p[q] = fma(p[q], fr[q], 6.0);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) p[q] = fma(p[q], fr[q], 6.0);
+#elif BQO_EXP_DEGREE == 4
+#pragma unroll
+    for (int q = 0; q < NV; ++q) p[q] = fr[q] + 4.0;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) p[q] = fma(p[q], fr[q], 12.0);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) p[q] = fma(p[q], fr[q], 24.0);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) p[q] = fma(p[q], fr[q], 24.0);
+#else
 #pragma unroll
     for (int q = 0; q < NV; ++q) p[q] = fr[q] + 6.0;
 #pragma unroll
@@ -159,17 +226,16 @@ __device__ __forceinline__ void bqo_matern52_q_v(const double (&u2)[NV], Tab tab
     for (int q = 0; q < NV; ++q) p[q] = fma(p[q], fr[q], 720.0);
 #pragma unroll
     for (int q = 0; q < NV; ++q) p[q] = fma(p[q], fr[q], 720.0);
+#endif
 #pragma unroll
     for (int q = 0; q < NV; ++q) {
-        // one unsigned clamp covers exp underflow (u > 32000 -> 2^-1000) and any garbage low word
-        // from absurd arguments (u >= 2^51), keeping the exponent arithmetic in the normal range
-        n[q] = min(n[q], 32000u);
-        double ev = p[q] * tab((int)(n[q] & (BQO_EXP_TABLE - 1)));
-        // 2^-(m >> 5) into the exponent field: hi -= (m & ~31) * 2^15
+        double ev = p[q] * tab(n[q]);
+        // 2^-(m div N) into the exponent field: hi -= (m - m mod N) * 2^20 / N
         int hi;
-        asm("mad.lo.s32 %0, %1, -32768, %2;"
+        asm("mad.lo.s32 %0, %1, %3, %2;"
             : "=r"(hi)
-            : "r"((int)(n[q] & ~31u)), "r"(__double2hiint(ev)));
+            : "r"((int)(n[q] & ~(unsigned)(BQO_EXP_TABLE - 1))), "r"(__double2hiint(ev)),
+              "n"(-(1 << (20 - BQO_EXP_BITS))));
         e[q] = __hiloint2double(hi, __double2loint(ev));
         t1[q] = g[q];
     }

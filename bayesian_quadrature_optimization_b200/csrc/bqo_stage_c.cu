@@ -20,13 +20,24 @@
 
 #define SC_MAX_D BQO_MAX_DIM
 
-// One dynamic shared-memory array for every kernel of this file.  Its first 32 doubles hold the
-// exp table of the fast path; declaring it at file scope lets ptxas fold the table's base
-// address into the LDS immediate.
+// One dynamic shared-memory array for every kernel of this file.  Its first BQO_EXP_TABLE doubles
+// hold the exp table of the fast path.
 extern __shared__ __align__(16) double dyn_smem[];
 
+// Table read T[m mod N] as LOP3 + IMAD + LDS: the address arithmetic is spelled in PTX because
+// nvcc otherwise canonicalises (m & (N-1)) * 8 + base into shift, mask and add (one more
+// instruction on the issue port per kernel evaluation).
 struct SmemExpTab {
-    __device__ __forceinline__ double operator()(int j) const { return dyn_smem[j]; }
+    unsigned base;  // shared-window address of dyn_smem[0]
+    __device__ __forceinline__ SmemExpTab()
+        : base((unsigned)__cvta_generic_to_shared(dyn_smem)) {}
+    __device__ __forceinline__ double operator()(unsigned m) const {
+        unsigned addr;
+        double t;
+        asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(addr) : "r"(m & (unsigned)(BQO_EXP_TABLE - 1)), "r"(base));
+        asm("ld.shared.f64 %0, [%1];" : "=d"(t) : "r"(addr));
+        return t;
+    }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -219,11 +230,12 @@ __device__ __forceinline__ EvalPtrs eval_ptrs_from(const UnitCtx<DX, DW>& u) {
 #endif
 
 // Warp-cooperative evaluation of a, b and their x-gradients at the raw point x.
-// Works in coordinates multiplied by sqrt(5) (q2 = 5 r^2, see bqo_matern52_q_v):
-//   `ws`: this evaluation's W samples times sqrt5 / ls_w, [M][DW];
-//   PRE = true: u.xs already holds sqrt5 * X / ls (staged copy); false: X / ls, scaled on load.
-// Per training point only two sums over the W samples are kept, G = sum (1+s) e^-s and
-// H = sum q2 e^-s; then sum_m k = G + H/3 and sum_m k'(r)/r = -(5/3) G.
+// Works in coordinates multiplied by K = sqrt5 N / ln2 (u2 = K^2 r^2, see bqo_matern52_q_v):
+//   `ws`: this evaluation's W samples times K / ls_w, [M][DW];
+//   PRE = true: u.xs already holds K * X / ls (staged copy); false: X / ls, scaled on load.
+// Per training point three sums over the W samples are kept, E0 = sum e, E1 = sum u e and
+// H = sum u2 e (e = exp(-sqrt5 r)); then with c = ln2/N, G = E0 + c E1 = sum (1 + sqrt5 r) e,
+// sum_m k = G + (c^2/3) H and sum_m k'(r)/r = -(5/3) G.
 // CMB = true evaluates F = a + Z b and grad F only, with ONE weight per training point,
 // w_j = wa_j - (Z/den) wb_j (`zd` = Z/den): half the accumulators, half the per-point FMAs and
 // ten registers less in the line-search evaluations of the inner maximiser.  F is returned in
@@ -317,7 +329,7 @@ __device__ __forceinline__ void eval_ab_warp(const EvalPtrs& p, const UnitCtx<DX
             E1 = t1v[0] * ev[0];
             H = q2v[0] * ev[0];
         }
-        const double G = fma(E1, BQO_LN2_32, E0);  // sum_m (1 + sqrt5 r_m) e_m
+        const double G = fma(E1, BQO_LN2_N, E0);  // sum_m (1 + sqrt5 r_m) e_m
         const double ksum = fma(H, BQO_H_TO_K, G);
         const double wa = p.wa[j], wb = p.wb[j];
         if (CMB) {
@@ -356,7 +368,7 @@ __device__ __forceinline__ void eval_ab_warp(const EvalPtrs& p, const UnitCtx<DX
             q2v[0] = fma(dw, dw, q2v[0]);
         }
         bqo_matern52_q_v<1>(q2v, SmemExpTab(), ev, t1v);
-        const double gm = fma(t1v[0], BQO_LN2_32, 1.0) * ev[0];
+        const double gm = fma(t1v[0], BQO_LN2_N, 1.0) * ev[0];
         Kc += fma(q2v[0] * ev[0], BQO_H_TO_K, gm);
 #pragma unroll
         for (int l = 0; l < DX; ++l) GC[l] = fma(gm, dxl[l], GC[l]);
@@ -942,10 +954,12 @@ __global__ void __launch_bounds__(AB_WARPS * 32)
     constexpr int D = DX + DW;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t gp = (int64_t)blockIdx.x * AB_WARPS + warp;
+    bqo_exp_table_init(dyn_smem);
+    __syncthreads();
     if (gp >= (int64_t)pb.n_units * npts) return;
     const int unit = (int)(gp / npts);
     const int M = (DW > 0) ? pb.M : 1;
-    double* ws = dyn_smem + warp * (M * (DW > 0 ? DW : 1));
+    double* ws = dyn_smem + BQO_EXP_TABLE + warp * (M * (DW > 0 ? DW : 1));
     UnitCtx<DX, DW> u;
     unit_ctx_init<DX, DW>(u, pb, unit);
     const int k = pb.unit_k[unit], c = pb.unit_c[unit];
@@ -961,40 +975,51 @@ __global__ void __launch_bounds__(AB_WARPS * 32)
     if (DW > 0) {
         // default: the W set of the unit's candidate, like the inner maximiser
         int wsi = pt_wset ? pt_wset[gp] : (c % pb.n_wsets);
-        scale_wset<DX, DW>(u, pb.wsets + (int64_t)wsi * pb.M * DW, ws, 1.0);
+        scale_wset<DX, DW>(u, pb.wsets + (int64_t)wsi * pb.M * DW, ws, BQO_PRESCALE);
         __syncwarp();
     }
+    // same fast kernel evaluation as eval_ab_warp: coordinates in units of K (bqo_common.cuh)
     double xsc[DX];
 #pragma unroll
-    for (int l = 0; l < DX; ++l) xsc[l] = pts[gp * DX + l] / u.ls[l];
+    for (int l = 0; l < DX; ++l) xsc[l] = (pts[gp * DX + l] / u.ls[l]) * BQO_PRESCALE;
     const double* V = u.wb + pb.n;  // rows 1..D of the unit: Sigma^-1 grad_l gamma (q-weighted)
     double Sb = 0.0, SV[D];
 #pragma unroll
     for (int l = 0; l < D; ++l) SV[l] = 0.0;
     for (int j = lane; j < u.n; j += 32) {
-        double Dx = 0.0;
+        double Dx = 1e-300;
 #pragma unroll
         for (int l = 0; l < DX; ++l) {
-            double df = xsc[l] - u.xs[l * u.ldx + j];
+            double df = xsc[l] - u.xs[l * u.ldx + j] * BQO_PRESCALE;
             Dx = fma(df, df, Dx);
         }
-        double ksum = 0.0;
+        double E0 = 0.0, E1 = 0.0, H = 0.0;
         if (DW > 0) {
             double xw[DW > 0 ? DW : 1];
 #pragma unroll
-            for (int l = 0; l < DW; ++l) xw[l] = u.xs[(DX + l) * u.ldx + j];
+            for (int l = 0; l < DW; ++l) xw[l] = u.xs[(DX + l) * u.ldx + j] * BQO_PRESCALE;
             for (int m = 0; m < M; ++m) {
-                double r2 = Dx;
+                double q2v[1], ev[1], t1v[1];
+                q2v[0] = Dx;
 #pragma unroll
                 for (int l = 0; l < DW; ++l) {
                     double dw = ws[m * DW + l] - xw[l];
-                    r2 = fma(dw, dw, r2);
+                    q2v[0] = fma(dw, dw, q2v[0]);
                 }
-                ksum += bqo_matern52(r2);
+                bqo_matern52_q_v<1>(q2v, SmemExpTab(), ev, t1v);
+                E0 += ev[0];
+                E1 = fma(t1v[0], ev[0], E1);
+                H = fma(q2v[0], ev[0], H);
             }
         } else {
-            ksum = bqo_matern52(Dx);
+            double q2v[1], ev[1], t1v[1];
+            q2v[0] = Dx;
+            bqo_matern52_q_v<1>(q2v, SmemExpTab(), ev, t1v);
+            E0 = ev[0];
+            E1 = t1v[0] * ev[0];
+            H = q2v[0] * ev[0];
         }
+        const double ksum = fma(H, BQO_H_TO_K, fma(E1, BQO_LN2_N, E0));
         Sb = fma(ksum, u.wb[j], Sb);
 #pragma unroll
         for (int l = 0; l < D; ++l) SV[l] = fma(ksum, V[(int64_t)l * pb.n + j], SV[l]);
@@ -1005,16 +1030,19 @@ __global__ void __launch_bounds__(AB_WARPS * 32)
     for (int l = 0; l < D; ++l) GC[l] = 0.0;
     for (int m = lane; m < M; m += 32) {
         double df[D];
-        double r2 = 0.0;
+        double q2v[1], ev[1], t1v[1];
+        q2v[0] = 1e-300;
 #pragma unroll
-        for (int l = 0; l < DX; ++l) df[l] = u.cs[l] - xsc[l];
+        for (int l = 0; l < DX; ++l) df[l] = u.cs[l] * BQO_PRESCALE - xsc[l];
 #pragma unroll
-        for (int l = 0; l < DW; ++l) df[DX + l] = u.cs[DX + l] - ws[m * DW + l];
+        for (int l = 0; l < DW; ++l) df[DX + l] = u.cs[DX + l] * BQO_PRESCALE - ws[m * DW + l];
 #pragma unroll
-        for (int l = 0; l < D; ++l) r2 = fma(df[l], df[l], r2);
-        double kk, g;
-        bqo_matern52_kg(r2, kk, g);
-        Kc += kk;
+        for (int l = 0; l < D; ++l) q2v[0] = fma(df[l], df[l], q2v[0]);
+        bqo_matern52_q_v<1>(q2v, SmemExpTab(), ev, t1v);
+        const double gm = fma(t1v[0], BQO_LN2_N, 1.0) * ev[0];
+        Kc += fma(q2v[0] * ev[0], BQO_H_TO_K, gm);
+        // k'(r)/r (c - p)/ls = -(5/3) gm (df'/K): the remaining 1/ls is applied below
+        const double g = BQO_GRAD_FAC * gm;
 #pragma unroll
         for (int l = 0; l < D; ++l) GC[l] = fma(g, df[l], GC[l]);
     }
@@ -1045,7 +1073,7 @@ extern "C" int bqo_grad_vector_b_batched(const bqo_stage_c* pb, const double* pt
     cudaStream_t cs = (cudaStream_t)stream;
     int64_t total = (int64_t)pb->n_units * npts;
     int grid = (int)((total + AB_WARPS - 1) / AB_WARPS);
-    size_t smem = sizeof(double) * AB_WARPS * (size_t)(pb->M > 0 ? pb->M : 1) * (pb->dw > 0 ? pb->dw : 1);
+    size_t smem = sizeof(double) * (BQO_EXP_TABLE + AB_WARPS * (size_t)(pb->M > 0 ? pb->M : 1) * (pb->dw > 0 ? pb->dw : 1));
 #define LAUNCH_GVB(DXV, DWV) \
     grad_vector_b_kernel<DXV, DWV><<<grid, AB_WARPS * 32, smem, cs>>>(*pb, pts, npts, pt_wset, out, is_nan)
     SC_DISPATCH(pb, LAUNCH_GVB);
@@ -1054,13 +1082,15 @@ extern "C" int bqo_grad_vector_b_batched(const bqo_stage_c* pb, const double* pt
 }
 
 // ---------------------------------------------------------------------------------------------
-// Monte-Carlo reduction over Z samples and hyper-samples; fixed order, one thread per output.
+// Monte-Carlo reduction over Z samples and hyper-samples; fixed order, one warp per output.
 __global__ void acq_reduce_kernel(const double* __restrict__ out_max, const double* __restrict__ gvb,
                                   const int32_t* __restrict__ is_nan, const double* __restrict__ z,
                                   const double* __restrict__ max_mean, int C, int S, int n_z,
                                   int dim_g, double* __restrict__ value,
                                   double* __restrict__ grad) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per output; lanes stride over the Z samples, fixed shuffle tree (bit-reproducible)
+    const int lane = threadIdx.x & 31;
+    int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int per = 1 + dim_g;
     if (idx >= C * per) return;
     int c = idx / per, q = idx % per;
@@ -1070,11 +1100,12 @@ __global__ void acq_reduce_kernel(const double* __restrict__ out_max, const doub
         for (int k = 0; k < S; ++k) {
             const double* mx = out_max + ((int64_t)c * S + k) * n_z;
             double s = 0.0;
-            for (int i = 0; i < n_z; ++i) s += mx[i];
+            for (int i = lane; i < n_z; i += 32) s += mx[i];
+            s = bqo_warp_sum(s);
             double mm = max_mean ? max_mean[k] : 0.0;
             acc += s / (double)n_z - mm;
         }
-        value[c] = acc / (double)S;
+        if (lane == 0) value[c] = acc / (double)S;
     } else if (grad != nullptr && gvb != nullptr) {
         int l = q - 1;
         bool bad = false;
@@ -1087,10 +1118,11 @@ __global__ void acq_reduce_kernel(const double* __restrict__ out_max, const doub
             }
             const double* gp = gvb + ((int64_t)u * n_z) * dim_g + l;
             double s = 0.0;
-            for (int i = 0; i < n_z; ++i) s = fma(gp[(int64_t)i * dim_g], z[i], s);
+            for (int i = lane; i < n_z; i += 32) s = fma(gp[(int64_t)i * dim_g], z[i], s);
+            s = bqo_warp_sum(s);
             acc += s / (double)n_z;
         }
-        grad[(int64_t)c * dim_g + l] = bad ? nan("") : acc / (double)S;
+        if (lane == 0) grad[(int64_t)c * dim_g + l] = bad ? nan("") : acc / (double)S;
     }
 }
 
@@ -1103,7 +1135,7 @@ extern "C" int bqo_acq_reduce(const double* out_max, const double* gvb, const in
     BQO_CHECK_ARG(C > 0 && S > 0 && n_z > 0 && dim_g >= 0, 6);
     BQO_CHECK_ARG(value != nullptr, 10);
     int total = C * (1 + dim_g);
-    acq_reduce_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+    acq_reduce_kernel<<<(total + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
         out_max, gvb, is_nan, z, max_mean, C, S, n_z, dim_g, value, grad);
     BQO_RETURN_LAST_ERROR();
 }
