@@ -75,9 +75,9 @@ __device__ __forceinline__ double bqo_matern52_dr(double r, double r2) {
 // every other instruction for one (tests/microbench/fp64_issue.cu), and the evaluation loop is
 // bound by exactly that port (profiles/r01_inner_maximize_v1.md).  So every instruction counts,
 // FP64 or not, and sqrt and exp are open-coded:
-//   sqrt : MUFU.RSQ64H seed (SFU pipe), one Goldschmidt step and one Newton correction; the
-//          1/(2 sqrt) estimate h is not refreshed (the last correction d*h is already 2^-44
-//          small, h's 2^-22 accuracy suffices);
+//   sqrt : MUFU.RSQ64H seed y (SFU pipe), h = y/2 by an integer exponent decrement, one
+//          Goldschmidt step and one Newton correction; h is not refreshed (the last correction
+//          d*h is already 2^-44 small, h's 2^-22 accuracy suffices);
 //   exp  : table-driven.  With N = 2^BQO_EXP_BITS table entries per octave,
 //          exp(-s) = 2^-(m div N) * 2^-((m mod N)/N) * exp(fr),  m = round(s N / ln2),
 //          |fr| <= ln2 / (2N).  The larger the table the shorter the polynomial for exp(fr):
@@ -127,6 +127,9 @@ static __constant__ double BQO_FC[4] = {
 // Degree-3 variant that skips the multiplication by -c: the polynomial is taken in d = u - m
 // itself, monic, with its three coefficients as uniform-register operands (one LDCU each per
 // training point), and the factor -c^3/6 goes into the table.
+#ifndef BQO_HALF_INT
+#define BQO_HALF_INT 1  // y/2 by an exponent decrement (1 issue cycle) instead of a DMUL (2)
+#endif
 #ifndef BQO_POLY_UR
 #define BQO_POLY_UR (BQO_EXP_DEGREE == 3)
 #endif
@@ -149,7 +152,7 @@ __device__ __forceinline__ void bqo_exp_table_init(double* tab) {
 // applies the constants once per point (no constant operand inside the W-sample loop).
 // `tab(m)` reads table entry m mod N (a functor so that the caller decides how the shared-memory
 // address is formed).
-// FP64 instructions per evaluation (N = 2048): sqrt 6, reduction 4, polynomial 3, table multiply 1.
+// FP64 instructions per evaluation (N = 2048): sqrt 5, reduction 3, polynomial 3, table multiply 1.
 template <int NV, class Tab>
 __device__ __forceinline__ void bqo_matern52_q_v(const double (&u2)[NV], Tab tab, double (&e)[NV],
                                                  double (&t1)[NV]) {
@@ -161,7 +164,11 @@ __device__ __forceinline__ void bqo_matern52_q_v(const double (&u2)[NV], Tab tab
         double y;
         asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(u2[q]));
         g[q] = u2[q] * y;
+#if BQO_HALF_INT
+        h[q] = __hiloint2double(__double2hiint(y) - 0x00100000, 0);  // y/2 on the integer pipe
+#else
         h[q] = 0.5 * y;
+#endif
     }
 #pragma unroll
     for (int q = 0; q < NV; ++q) w[q] = fma(-h[q], g[q], 0.5);
@@ -179,6 +186,7 @@ __device__ __forceinline__ void bqo_matern52_q_v(const double (&u2)[NV], Tab tab
         // stays inside the normal range whatever the inputs (tiny length scales included).
         unsigned uh = min((unsigned)__double2hiint(g[q]), (unsigned)((1023 + BQO_EXP_BITS + 9) << 20));
         g[q] = __hiloint2double((int)uh, __double2loint(g[q]));
+        // (F2I.F64 / I2F.F64 instead of the two DADDs measured 2.3% slower: profiles/r01_tuning_sweeps.md)
         double tk = magic + g[q];
         n[q] = (unsigned)__double2loint(tk);
         kf[q] = tk - magic;              // round(u) as a double (exact)

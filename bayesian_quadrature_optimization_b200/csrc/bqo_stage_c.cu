@@ -564,7 +564,7 @@ __global__ void __launch_bounds__(IM_WARPS * 32, 1)
     const int n_pre = n_starts + (opt.use_vertices ? NV : 0);
 
     // ---- shared memory carve-up -------------------------------------------------------------
-    double* s_tab = dyn_smem;                // [32] exp table
+    double* s_tab = dyn_smem;                // [BQO_EXP_TABLE] exp table
     double* sm = dyn_smem + BQO_EXP_TABLE;
     double* s_xs = sm;                       // STAGE: [D][n]
     double* s_wa = s_xs + (STAGE ? (size_t)D * n : 0);
