@@ -1,0 +1,218 @@
+"""GPU parity at the sizes BASELINE.json names.
+
+The oracle is run at these sizes only where it finishes in seconds (a handful of a/b evaluations,
+one LAPACK factorisation per hyper-sample); everything else is checked through size-independent
+properties: L L^T reproduces Sigma, the maximiser's value is reproduced by evaluating a + Z b at
+its argument, it dominates every start point and box vertex, the gradient of the log-likelihood
+agrees with central differences of the log-likelihood.
+"""
+import numpy as np
+import pytest
+
+from oracle import bqo_oracle as orc
+from tests.helpers import assert_close
+
+pytestmark = pytest.mark.gpu
+
+EPS = np.finfo(float).eps
+
+
+def _cond_rtol(Sigma, base=1e-9):
+    """Two correct factorisations of Sigma differ by about cond(Sigma) * eps (tests/helpers.py)."""
+    sv = np.linalg.svd(Sigma, compute_uv=False)
+    return max(base, 8.0 * (sv[0] / sv[-1]) * EPS)
+
+
+def _c3(n=2048, S=2, seed=0):
+    rng = np.random.RandomState(seed)
+    pts = np.concatenate([rng.uniform(0, 1, (n, 4)), rng.gamma(2.0, 1.0, (n, 2))], 1)
+    y = np.sin(pts.sum(1)) + 0.01 * rng.normal(0, 1, n)
+    base = np.array([1e-4, 0.0] + 4 * [0.3] + 2 * [2.0] + [1.0])
+    r2 = np.random.RandomState(2)
+    thetas = base[None, :] * (1.0 + 0.05 * r2.normal(0, 1, (S, base.size)))
+    thetas[:, 1] = 0.05 * r2.normal(0, 1, S)
+    return pts, y, thetas
+
+
+def test_c3_stage_b_c_against_oracle_at_n2048():
+    """North-star shape: Scaled(Matern52), d = 4 + 2, n = 2048, gamma W with 10 samples."""
+    from bayesian_quadrature_optimization_b200 import engine as E, _cabi
+    pts, y, thetas = _c3()
+    S = thetas.shape[0]
+    dx = 4
+    eng = E.GPEngine(_cabi.KIND_SCALED_MATERN52, 6)
+    eng.set_data(pts, y)
+    hb = eng.hypers(thetas)
+    wset = np.random.RandomState(4).gamma(2.0, 1.0, (10, 2))
+    lo, up = np.zeros(dx), np.ones(dx)
+    bq = E.BQEngine(hb, dx, wsets=wset, lower=lo, upper=up)
+    r5 = np.random.RandomState(5)
+    cands = np.concatenate([r5.uniform(0, 1, (2, 4)), r5.gamma(2.0, 1.0, (2, 2))], 1)
+    ub = bq.setup(cands)
+
+    spec = orc.KernelSpec(orc.SCALED_MATERN52, 6)
+    ogp = orc.OracleGP(spec, pts, y)
+    obq = orc.OracleBQ(ogp, list(range(dx)), orc.GAMMA)
+    rtols = []
+    for s in range(S):
+        th = thetas[s]
+        Sigma = spec.cov(th[2:], pts) + th[0] * np.eye(len(y))
+        rtols.append(_cond_rtol(Sigma))
+    # den of every unit
+    den = ub.den.cpu().numpy()
+    for s in range(S):
+        th = thetas[s]
+        for c in range(2):
+            par = obq.get_parameters_for_samples(cands[c:c + 1], th[0], th[1], th[2:])
+            assert_close(den[s, c], par["denominator"][0],
+                         rtol=rtols[s], what="den")
+    # a, b and gradients at a few points of every unit
+    xq = np.random.RandomState(7).uniform(0, 1, (3, dx))
+    P = xq.shape[0]
+    qpts, units = [], []
+    for s in range(S):
+        for c in range(2):
+            for p in range(P):
+                qpts.append(xq[p])
+                units.append(c * S + s)
+    got = bq.sample_ab(ub, np.array(qpts), np.array(units, dtype=np.int32)).cpu().numpy()
+    got = got.reshape(S, 2, P, -1)
+    for s in range(S):
+        th = thetas[s]
+        for c in range(2):
+            for p in range(P):
+                v = obq.compute_parameters_for_sample(xq[p], cands[c:c + 1], th[0], th[1], th[2:],
+                                                      w=wset)
+                gr = obq.compute_gradient_parameters_for_sample(xq[p], cands[c:c + 1], th[0], th[1],
+                                                                th[2:], w=wset)
+                want = np.concatenate([[v["a"][0], np.asarray(v["b"]).reshape(-1)[0]],
+                                       np.asarray(gr["a"]).reshape(-1),
+                                       np.asarray(gr["b"]).reshape(-1)])
+                assert_close(got[s, c, p], want, rtol=100 * rtols[s], atol=1e-9, what="ab n=2048")
+    # inner maximiser: properties at full size
+    zs = np.array([-1.3, 0.2, 1.7])
+    starts = np.random.RandomState(6).uniform(0, 1, (3, dx))
+    out_max, out_arg, n_evals = bq.inner_maximize(ub, zs, starts, count_evals=True)
+    out_max, out_arg = out_max.cpu().numpy(), out_arg.cpu().numpy()
+    assert np.all(out_arg >= 0.0) and np.all(out_arg <= 1.0)
+    assert int(n_evals.sum().item()) > 0
+    verts = np.array([[(v >> (dx - 1 - l)) & 1 for l in range(dx)] for v in range(1 << dx)], float)
+    probe = np.concatenate([starts, verts], 0)
+    for u in range(2 * S):
+        ab = bq.sample_ab(ub, probe, np.full(len(probe), u, dtype=np.int32)).cpu().numpy()
+        at = bq.sample_ab(ub, out_arg[u], np.full(len(zs), u, dtype=np.int32)).cpu().numpy()
+        for i, z in enumerate(zs):
+            # value reproduced at the returned argument (same device arithmetic: tight)
+            assert_close(at[i, 0] + z * at[i, 1], out_max[u, i], rtol=1e-11, atol=1e-12,
+                         what="value at argmax")
+            # an ascent method never ends below its start points; vertices are compared explicitly
+            assert out_max[u, i] >= np.max(ab[:, 0] + z * ab[:, 1]) - 1e-12
+    # and the oracle agrees with the device on the value at the device's maximiser
+    th = thetas[0]
+    v = obq.compute_parameters_for_sample(out_arg[0, 1], cands[0:1], th[0], th[1], th[2:], w=wset)
+    assert_close(v["a"][0] + zs[1] * np.asarray(v["b"]).reshape(-1)[0], out_max[0, 1],
+                 rtol=100 * rtols[0], atol=1e-9, what="oracle value at device argmax")
+    # gradient_vector_b at the maximisers
+    gvb, is_nan = bq.grad_vector_b(ub, out_arg)
+    assert not is_nan.cpu().numpy().any()
+    gb = obq.gradient_vector_b(cands[0:1], out_arg[0], th[0], th[1], th[2:], w=wset)
+    assert_close(gvb.cpu().numpy()[0], gb, rtol=1000 * rtols[0], atol=1e-8, what="gvb n=2048")
+
+
+def test_c4_shape_product_100_tasks_n4096():
+    """citi_bike_mt-shaped: Product(Matern52(4), Tasks(100, same_correlation)), weighted finite W."""
+    from scipy.stats import poisson
+    from bayesian_quadrature_optimization_b200 import engine as E, _cabi
+    n, dx, T, S = 4096, 4, 100, 2
+    rng = np.random.RandomState(1)
+    x = np.floor(rng.uniform(0, 10, (n, dx)) * 4) / 4.0
+    task = rng.randint(0, T, n).astype(float)
+    pts = np.concatenate([x, task[:, None]], 1)
+    y = np.sin(x.sum(1) / 3.0) + 0.02 * (task - 50.0) / 50.0 + 0.05 * rng.normal(0, 1, n)
+    weights = poisson.pmf(np.arange(T), 50)
+    weights = weights / weights.sum()
+    thetas = np.array([[0.05, 0.0, 2.0, 2.5, 3.0, 2.0, 0.0, -1.0],
+                       [0.04, 0.05, 2.2, 2.4, 2.7, 2.1, 0.1, -0.9]])
+    eng = E.GPEngine(_cabi.KIND_PRODUCT_TASKS, dx + 1, T, True)
+    eng.set_data(pts, y)
+    hb = eng.hypers(thetas).factorize()
+    assert np.all(hb.info == 0)
+    spec = orc.KernelSpec(orc.PRODUCT_TASKS, dx + 1, n_tasks=T, same_correlation=True)
+    ogp = orc.OracleGP(spec, pts, y)
+    want = [ogp.log_likelihood(t[0], t[1], t[2:]) for t in thetas]
+    assert_close(hb.log_likelihood().cpu().numpy(), want, rtol=1e-9, what="llh n=4096 T=100")
+    Sigma = hb.cov(add_noise=True)
+    rec = hb.L @ hb.L.transpose(1, 2)
+    assert ((rec - Sigma).norm() / Sigma.norm()).item() < 1e-13
+    # quadrature over the 100 weighted tasks
+    lo, up = np.zeros(dx), 10.0 * np.ones(dx)
+    bq = E.BQEngine(hb, dx, weights=weights, lower=lo, upper=up)
+    obq = orc.OracleBQ(ogp, list(range(dx)), orc.WEIGHTED_UNIFORM_FINITE, weights=weights,
+                       domain_random=np.arange(T).reshape(T, 1))
+    cands = np.concatenate([rng.uniform(0, 10, (2, dx)), np.array([[3.0], [77.0]])], 1)
+    ub = bq.setup(cands)
+    xq = rng.uniform(0, 10, (2, dx))
+    rt = [_cond_rtol(Sigma[s].cpu().numpy()) for s in range(S)]
+    qpts, units = [], []
+    for s in range(S):
+        for c in range(2):
+            for p in range(2):
+                qpts.append(xq[p])
+                units.append(c * S + s)
+    got = bq.sample_ab(ub, np.array(qpts), np.array(units, dtype=np.int32)).cpu().numpy()
+    got = got.reshape(S, 2, 2, -1)
+    for s in range(S):
+        th = thetas[s]
+        for c in range(2):
+            for p in range(2):
+                v = obq.compute_parameters_for_sample(xq[p], cands[c:c + 1], th[0], th[1], th[2:])
+                gr = obq.compute_gradient_parameters_for_sample(xq[p], cands[c:c + 1], th[0], th[1],
+                                                                th[2:])
+                want = np.concatenate([[v["a"][0], np.asarray(v["b"]).reshape(-1)[0]],
+                                       np.asarray(gr["a"]).reshape(-1),
+                                       np.asarray(gr["b"]).reshape(-1)])
+                assert_close(got[s, c, p], want, rtol=100 * rt[s], atol=1e-10, what="ab n=4096")
+    # the chosen task: argmax over the 100 tasks of the Bayesian-averaged EI at a fixed x
+    # (MultiTasks.choose_best_task_given_x, multi_task.py:82-95) -- index must be exact
+    xfix = rng.uniform(0, 10, dx)
+    cand_t = np.concatenate([np.repeat(xfix[None, :], T, 0), np.arange(T)[:, None].astype(float)], 1)
+    best = np.full(S, float(np.max(y)))
+    ei, _ = hb.ei(cand_t, best, grad=False)
+    ei = ei.cpu().numpy()
+    want_ei = np.stack([np.concatenate([orc.ei_evaluate(ogp, cand_t[t:t + 1], th[0], th[1], th[2:])
+                                        for t in range(T)]) for th in thetas])
+    assert_close(ei, want_ei, rtol=1e-7, atol=1e-14, what="EI over tasks")
+    assert int(np.argmax(ei.mean(0))) == int(np.argmax(want_ei.mean(0)))
+
+
+def test_c5_shape_cholesky_loglik_gradient_n8192():
+    """Scaling-sweep shape: n = 8192.  Factor reconstruction, log-likelihood against LAPACK, and
+    the analytic gradient against central differences of the device log-likelihood."""
+    from bayesian_quadrature_optimization_b200 import engine as E, _cabi
+    pts, y, thetas = _c3(n=8192, S=1, seed=3)
+    eng = E.GPEngine(_cabi.KIND_SCALED_MATERN52, 6)
+    eng.set_data(pts, y)
+    hb = eng.hypers(thetas)
+    Sigma = hb.cov(add_noise=True)
+    hb.factorize()
+    assert np.all(hb.info == 0)
+    rec = hb.L @ hb.L.transpose(1, 2)
+    assert ((rec - Sigma).norm() / Sigma.norm()).item() < 1e-13
+    assert (hb.L.triu(1).abs().max().item()) == 0.0  # strict upper triangle zeroed like dpotrf clean=1
+    spec = orc.KernelSpec(orc.SCALED_MATERN52, 6)
+    ogp = orc.OracleGP(spec, pts, y)
+    th = thetas[0]
+    assert_close(hb.log_likelihood().cpu().numpy()[0], ogp.log_likelihood(th[0], th[1], th[2:]),
+                 rtol=1e-9, what="llh n=8192")
+    grad = hb.grad_log_likelihood().cpu().numpy()[0]
+    del hb, Sigma, rec
+    # central differences in three coordinates: noise, one length scale, sigma2
+    for j, h in [(0, 1e-7), (3, 1e-5), (8, 1e-5)]:
+        tp, tm = th.copy(), th.copy()
+        tp[j] += h
+        tm[j] -= h
+        hb2 = eng.hypers(np.stack([tp, tm])).factorize()
+        ll = hb2.log_likelihood().cpu().numpy()
+        fd = (ll[0] - ll[1]) / (2 * h)
+        assert_close(grad[j], fd, rtol=2e-4, atol=1e-4, what="d llh / d theta[%d]" % j)
+        del hb2
