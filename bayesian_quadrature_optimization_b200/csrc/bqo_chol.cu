@@ -55,6 +55,9 @@ __device__ int potrf_block_smem(double* Ls, int nv, int* flag_sm) {
 // then solves its 64 rows of the panel, X L11^T = A21, one thread per row with L11 broadcast
 // from shared memory.  The diagonal tile's CTA stores the factor in `diag_scratch` instead of in
 // place: the other CTAs of this launch still read the unfactored block from A.
+// (Two right-looking rewrites were measured and dropped: rows in registers, fully unrolled --
+// 16 000 straight-line instructions, instruction-fetch bound at 95 us; tiles in shared memory
+// with rolled loops -- shared-memory latency and bank conflicts, 113 us; this version: 72-90 us.)
 __global__ void __launch_bounds__(128) potrf_panel_kernel(double* __restrict__ A, int n, int k0,
                                                           int* __restrict__ info,
                                                           double* __restrict__ diag_scratch) {
@@ -271,8 +274,146 @@ __global__ void __launch_bounds__(128) trsm_kernel(const double* __restrict__ L,
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Few right-hand sides (alpha = Sigma^-1 (y - mean): m = 1): the tile path above would leave one
+// CTA per matrix walking 2 x 32 block columns with a 64x64x64 DMMA product and a serial
+// substitution each (6 ms for 20 matrices of n = 2048).  A vector solve is bandwidth work: one
+// CTA per (right-hand side, matrix) keeps the vector in shared memory and streams L once per
+// direction with coalesced row reads:
+//   forward  (L y = b)   left-looking : rows of block kb take dot products with y[0:k0]
+//                                       (warp per row group, lanes along the row);
+//   backward (L^T x = y) right-looking: after block kb is solved, y[0:k0] -= L[kb, 0:k0]^T x[kb]
+//                                       (thread per column, rows of L read contiguously).
+// The 64x64 diagonal systems are solved by one warp with shuffles (reciprocal diagonal).
+#define TRSV_THREADS 512
+#define TRSV_WARPS (TRSV_THREADS / 32)
+#define TRSV_ROWS (NB / TRSV_WARPS)  // rows of a block handled by one warp
+
+template <bool FORWARD>
+__global__ void __launch_bounds__(TRSV_THREADS) trsv_kernel(const double* __restrict__ L, int n,
+                                                            double* __restrict__ Bt, int m) {
+    extern __shared__ double dyn_smem[];
+    double* xs = dyn_smem;                         // [nb * NB] the vector (zero padded)
+    const int nb = (n + NB - 1) / NB;
+    double* Ls = xs + (size_t)nb * NB;             // [NB][LDT] diagonal block
+    double* rd = Ls + NB * LDT;                    // [NB] reciprocal diagonal
+    const int s = blockIdx.y;
+    const double* Lm = L + (int64_t)s * n * n;
+    double* b = Bt + ((int64_t)s * m + blockIdx.x) * n;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int i = t; i < nb * NB; i += TRSV_THREADS) xs[i] = (i < n) ? b[i] : 0.0;
+    __syncthreads();
+    for (int kb = FORWARD ? 0 : nb - 1; FORWARD ? (kb < nb) : (kb >= 0); kb += FORWARD ? 1 : -1) {
+        const int k0 = kb * NB;
+        const int kv = (n - k0 < NB) ? n - k0 : NB;
+        // diagonal block (and the reciprocals of its diagonal) into shared memory
+        for (int e = t; e < NB * NB; e += TRSV_THREADS) {
+            int r = e / NB, c = e % NB;
+            double v = 0.0;
+            if (r < kv && c <= r) v = Lm[(int64_t)(k0 + r) * n + (k0 + c)];
+            Ls[r * LDT + c] = v;
+            if (r == c) rd[r] = (r < kv) ? 1.0 / v : 1.0;
+        }
+        if (FORWARD && k0 > 0) {
+            // rows k0 + warp*TRSV_ROWS + q: acc_q = sum_{c < k0} L[row][c] y[c]
+            double acc[TRSV_ROWS];
+#pragma unroll
+            for (int q = 0; q < TRSV_ROWS; ++q) acc[q] = 0.0;
+            const int rbase = k0 + warp * TRSV_ROWS;
+            // k0 is a multiple of 64: two columns per lane and trip, no bounds checks; the loads
+            // of four trips are issued together (the walk is latency bound otherwise)
+            const double* lrow[TRSV_ROWS];
+#pragma unroll
+            for (int q = 0; q < TRSV_ROWS; ++q) {
+                const int row = (rbase + q < n) ? rbase + q : n - 1;  // clamped rows are discarded
+                lrow[q] = Lm + (int64_t)row * n;
+            }
+#pragma unroll 4
+            for (int c = lane; c < k0; c += 64) {
+                const double x0 = xs[c], x1 = xs[c + 32];
+#pragma unroll
+                for (int q = 0; q < TRSV_ROWS; ++q) {
+                    acc[q] = fma(lrow[q][c], x0, acc[q]);
+                    acc[q] = fma(lrow[q][c + 32], x1, acc[q]);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < TRSV_ROWS; ++q) {
+                double a = bqo_warp_sum(acc[q]);
+                // rows >= k0 are not read by the dots above
+                if (lane == 0 && rbase + q < n) xs[rbase + q] -= a;
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // lanes own entries lane and lane + 32 of the block
+            double v0 = xs[k0 + lane], v1 = xs[k0 + lane + 32];
+            if (FORWARD) {
+                for (int j = 0; j < kv; ++j) {
+                    double cand = ((j < 32) ? v0 : v1) * rd[j];
+                    const double yj = __shfl_sync(0xffffffffu, cand, j & 31);
+                    if (lane == (j & 31)) {
+                        if (j < 32) v0 = yj; else v1 = yj;
+                    }
+                    if (lane > j) v0 = fma(-Ls[lane * LDT + j], yj, v0);
+                    if (lane + 32 > j) v1 = fma(-Ls[(lane + 32) * LDT + j], yj, v1);
+                }
+            } else {
+                for (int j = kv - 1; j >= 0; --j) {
+                    double cand = ((j < 32) ? v0 : v1) * rd[j];
+                    const double xj = __shfl_sync(0xffffffffu, cand, j & 31);
+                    if (lane == (j & 31)) {
+                        if (j < 32) v0 = xj; else v1 = xj;
+                    }
+                    // (L^T)[c][j] = L[j][c] for c < j: row j of the block, contiguous in c
+                    if (lane < j) v0 = fma(-Ls[j * LDT + lane], xj, v0);
+                    if (lane + 32 < j) v1 = fma(-Ls[j * LDT + lane + 32], xj, v1);
+                }
+            }
+            xs[k0 + lane] = v0;
+            xs[k0 + lane + 32] = v1;
+        }
+        __syncthreads();
+        if (!FORWARD && k0 > 0) {
+            // y[c] -= sum_j L[k0 + j][c] x[k0 + j] for every column c < k0
+            for (int c = t; c < k0; c += TRSV_THREADS) {
+                double a0 = 0.0, a1 = 0.0;
+                const double* lc = Lm + (int64_t)k0 * n + c;
+                int j = 0;
+#pragma unroll 8
+                for (; j + 1 < kv; j += 2) {
+                    a0 = fma(lc[(int64_t)j * n], xs[k0 + j], a0);
+                    a1 = fma(lc[(int64_t)(j + 1) * n], xs[k0 + j + 1], a1);
+                }
+                if (j < kv) a0 = fma(lc[(int64_t)j * n], xs[k0 + j], a0);
+                xs[c] -= a0 + a1;
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = t; i < n; i += TRSV_THREADS) b[i] = xs[i];
+}
+
+// The vector path reads L once per right-hand side (n^2 x 8 bytes per direction), the tile path
+// once per 64 of them but needs ~6 ms of serial block steps at n = 2048: cross-over near 500 vectors.
+#define TRSV_MAX_VECTORS 512
+static size_t trsv_smem_bytes(int n) {
+    const int nb = (n + NB - 1) / NB;
+    return ((size_t)nb * NB + (size_t)NB * LDT + NB) * sizeof(double);
+}
+
 static int potrs_launch(const double* L, int n, int S, double* Bt, int m, int identity_rhs,
                         cudaStream_t cs, bool forward_only = false) {
+    if ((int64_t)m * S <= TRSV_MAX_VECTORS && m <= 65535 && !identity_rhs && !forward_only &&
+        trsv_smem_bytes(n) <= 200 * 1024) {
+        const size_t sb = trsv_smem_bytes(n);
+        cudaFuncSetAttribute(trsv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
+        cudaFuncSetAttribute(trsv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
+        dim3 grid(m, S);
+        trsv_kernel<true><<<grid, TRSV_THREADS, sb, cs>>>(L, n, Bt, m);
+        trsv_kernel<false><<<grid, TRSV_THREADS, sb, cs>>>(L, n, Bt, m);
+        return (int)cudaGetLastError();
+    }
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute(trsm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -298,27 +439,106 @@ extern "C" int bqo_potrs_batched(const double* L, int32_t n, int32_t S, double* 
     return potrs_launch(L, n, S, Bt, m, 0, (cudaStream_t)stream);
 }
 
-static int trsm_forward_launch(const double* L, int n, int S, double* Bt, int m, int identity_rhs,
-                               cudaStream_t cs) {
-    return potrs_launch(L, n, S, Bt, m, identity_rhs, cs, true);
-}
-
+// ---------------------------------------------------------------------------------------------
 // Internal: Sigma^{-1} = L^-T L^-1 (used by the log-likelihood gradient).
+//
+// W = L^-1 is built by recursive doubling so that all but n*64^2 of its n^3/3 flops are DMMA tile
+// products (a column-walking triangular solve on the identity is a serial chain of 32 small
+// steps per CTA and ran at 7 TFLOP/s):
+//   level 0 : the 64x64 diagonal blocks are inverted in shared memory (one thread per column);
+//   level b = 64, 128, ...: for every aligned pair of b x b diagonal blocks
+//       [ L11  0  ]^-1   [ W11              0  ]
+//       [ L21 L22 ]    = [ -W22 L21 W11    W22 ],   T = L21 W11, then W21 = -W22 T,
+//     two launches per level; the triangular zeros of W11 / W22 shorten the K ranges.
+// Then Inv = W^T W on lower tiles (mirrored on store), K range from the tile's first row.
 int bqo_internal_inverse_from_chol(const double* L, int n, int S, double* Inv, double* Wbuf,
                                    cudaStream_t cs);
 
-__global__ void set_identity_kernel(double* __restrict__ A, int n) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    int i = blockIdx.y;
-    int s = blockIdx.z;
-    if (j < n) A[((int64_t)s * n + i) * n + j] = (i == j) ? 1.0 : 0.0;
+__global__ void __launch_bounds__(NB) tri_inv_diag_kernel(const double* __restrict__ L, int n,
+                                                          double* __restrict__ W) {
+    extern __shared__ double dyn_smem[];
+    double* Ls = dyn_smem;
+    double* Ws = Ls + NB * LDT;
+    const int s = blockIdx.y;
+    const int k0 = blockIdx.x * NB;
+    const int kv = (n - k0 < NB) ? n - k0 : NB;
+    const double* Lm = L + (int64_t)s * n * n;
+    double* Wm = W + (int64_t)s * n * n;
+    const int t = threadIdx.x;
+    for (int e = t; e < NB * NB; e += NB) {
+        int r = e / NB, c = e % NB;
+        Ls[r * LDT + c] = (r < kv && c <= r) ? Lm[(int64_t)(k0 + r) * n + (k0 + c)] : 0.0;
+        Ws[r * LDT + c] = 0.0;
+    }
+    __syncthreads();
+    if (t < kv) {
+        // column t of the inverse: forward substitution on the unit vector e_t
+        Ws[t * LDT + t] = 1.0 / Ls[t * LDT + t];
+        for (int i = t + 1; i < kv; ++i) {
+            double a0 = 0.0, a1 = 0.0;
+            int k = t;
+            for (; k + 1 < i; k += 2) {
+                a0 = fma(Ls[i * LDT + k], Ws[k * LDT + t], a0);
+                a1 = fma(Ls[i * LDT + k + 1], Ws[(k + 1) * LDT + t], a1);
+            }
+            if (k < i) a0 = fma(Ls[i * LDT + k], Ws[k * LDT + t], a0);
+            Ws[i * LDT + t] = -(a0 + a1) / Ls[i * LDT + i];
+        }
+    }
+    __syncthreads();
+    for (int e = t; e < NB * NB; e += NB) {
+        int r = e / NB, c = e % NB;
+        if (r < kv && c < kv) Wm[(int64_t)(k0 + r) * n + (k0 + c)] = Ws[r * LDT + c];
+    }
 }
 
-// Inv = W^T W with W = L^-1 held right-hand-side-major (Wt[r][i] = W[i][r], zero for i < r):
-// Inv[a][b] = sum_{i >= max(a,b)} Wt[a][i] Wt[b][i].  Lower tiles only, K range starts at the
-// tile's first row (the skipped part of W is zero); each tile is also stored transposed so that
-// Inv comes out full and symmetric.  n^3/3 flops instead of the n^3 of a backward solve.
-__global__ void __launch_bounds__(128) inv_syrk_kernel(const double* __restrict__ Wt, int n,
+// PASS 1: T[R, C] = L[R, C] W[C, C];  PASS 2: W[R, C] = -W[R, R] T[R, C]
+// for the pair whose top-left block starts at o = pair * 2b: C = [o, o+b), R = [o+b, o+2b).
+// grid = (b/64 column tiles, b/64 row tiles, pairs * S).
+template <int PASS>
+__global__ void __launch_bounds__(128) tri_inv_level_kernel(const double* __restrict__ L,
+                                                            double* __restrict__ W,
+                                                            double* __restrict__ T, int n, int b,
+                                                            int pairs) {
+    extern __shared__ double dyn_smem[];
+    double* Asm = dyn_smem;
+    double* Bsm = Asm + BQO_OPER_TILE_DOUBLES;
+    const int s = blockIdx.z / pairs;
+    const int pair = blockIdx.z % pairs;
+    const int o = pair * 2 * b;
+    const int i0 = o + b + blockIdx.y * NB;
+    const int j0 = o + blockIdx.x * NB;
+    if (i0 >= n) return;
+    const int ri = (n - i0 < NB) ? n - i0 : NB;
+    const int rj = NB;  // o + b < n, so every column of C exists
+    const double* Lm = L + (int64_t)s * n * n;
+    double* Wm = W + (int64_t)s * n * n;
+    double* Tm = T + (int64_t)s * n * n;
+    BqoAcc acc;
+    acc.zero();
+    if (PASS == 1) {
+        // sum over k in [j0, o+b): W11 is lower triangular, W[k][j] = 0 for k < j
+        bqo_gemm_tile<true, false>(acc, Lm + (int64_t)i0 * n + j0, n, ri,
+                                   Wm + (int64_t)j0 * n + j0, n, rj, o + b - j0, Asm, Bsm);
+        bqo_acc_foreach(acc, [&](int r, int c, double& v) {
+            if (r < ri) Tm[(int64_t)(i0 + r) * n + (j0 + c)] = v;
+        });
+    } else {
+        // sum over k in [o+b, i0+64): W22 is lower triangular, W[i][k] = 0 for k > i
+        const int kend = (i0 + NB < n) ? i0 + NB : n;
+        bqo_gemm_tile<true, false>(acc, Wm + (int64_t)i0 * n + (o + b), n, ri,
+                                   Tm + (int64_t)(o + b) * n + j0, n, rj, kend - (o + b), Asm, Bsm);
+        bqo_acc_foreach(acc, [&](int r, int c, double& v) {
+            if (r < ri) Wm[(int64_t)(i0 + r) * n + (j0 + c)] = -v;
+        });
+    }
+}
+
+// Inv = W^T W with W = L^-1 row-major lower triangular:
+// Inv[a][b] = sum_{i >= max(a,b)} W[i][a] W[i][b].  Lower tiles only, K range starts at the
+// tile's first row (W vanishes above it; the diagonal blocks carry explicit zeros); each tile
+// is also stored transposed so that Inv comes out full and symmetric.
+__global__ void __launch_bounds__(128) inv_syrk_kernel(const double* __restrict__ W, int n,
                                                        double* __restrict__ Inv) {
     extern __shared__ double dyn_smem[];
     double* Asm = dyn_smem;
@@ -326,15 +546,15 @@ __global__ void __launch_bounds__(128) inv_syrk_kernel(const double* __restrict_
     const int s = blockIdx.z;
     const int ba = blockIdx.y, bb = blockIdx.x;
     if (bb > ba) return;
-    const double* W = Wt + (int64_t)s * n * n;
+    const double* Wm = W + (int64_t)s * n * n;
     double* Iv = Inv + (int64_t)s * n * n;
     const int a0 = ba * NB, b0 = bb * NB;
     const int ra = (n - a0 < NB) ? n - a0 : NB;
     const int rb = (n - b0 < NB) ? n - b0 : NB;
     BqoAcc acc;
     acc.zero();
-    bqo_gemm_tile<true, true>(acc, W + (int64_t)a0 * n + a0, n, ra, W + (int64_t)b0 * n + a0, n, rb,
-                              n - a0, Asm, Bsm);
+    bqo_gemm_tile<false, false>(acc, Wm + (int64_t)a0 * n + a0, n, ra, Wm + (int64_t)a0 * n + b0, n,
+                                rb, n - a0, Asm, Bsm);
     bqo_acc_foreach(acc, [&](int r, int c, double& v) {
         if (r < ra && c < rb) {
             Iv[(int64_t)(a0 + r) * n + (b0 + c)] = v;
@@ -343,16 +563,26 @@ __global__ void __launch_bounds__(128) inv_syrk_kernel(const double* __restrict_
     });
 }
 
-static int trsm_forward_launch(const double* L, int n, int S, double* Bt, int m, int identity_rhs,
-                               cudaStream_t cs);
-
 int bqo_internal_inverse_from_chol(const double* L, int n, int S, double* Inv, double* Wbuf,
                                    cudaStream_t cs) {
-    dim3 zg((n + 255) / 256, n, S);
-    set_identity_kernel<<<zg, 256, 0, cs>>>(Wbuf, n);
-    int rc = trsm_forward_launch(L, n, S, Wbuf, n, 1, cs);
-    if (rc) return rc;
     const int nb = (n + NB - 1) / NB;
+    const size_t smem_diag = 2 * (size_t)NB * LDT * sizeof(double);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(tri_inv_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem_diag);
+        attr_done = true;
+    }
+    dim3 dg(nb, S);
+    tri_inv_diag_kernel<<<dg, NB, smem_diag, cs>>>(L, n, Wbuf);
+    for (int b = NB; b < n; b *= 2) {
+        const int pairs = (n + 2 * b - 1) / (2 * b);
+        if ((int64_t)pairs * S > 65535) return -3;
+        dim3 lg(b / NB, b / NB, pairs * S);
+        // Inv doubles as the scratch T of the levels; the final product overwrites all of it
+        tri_inv_level_kernel<1><<<lg, 128, SMEM_SYRK, cs>>>(L, Wbuf, Inv, n, b, pairs);
+        tri_inv_level_kernel<2><<<lg, 128, SMEM_SYRK, cs>>>(L, Wbuf, Inv, n, b, pairs);
+    }
     dim3 sg(nb, nb, S);
     inv_syrk_kernel<<<sg, 128, SMEM_SYRK, cs>>>(Wbuf, n, Inv);
     return (int)cudaGetLastError();

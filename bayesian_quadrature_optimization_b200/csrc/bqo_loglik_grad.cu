@@ -6,8 +6,9 @@
 // which the reference evaluates with one n x n dpotrs and one n x n x n product PER parameter.
 // Here Sigma^-1 is formed once per hyper-sample (potrs on the identity) and every parameter
 // derivative is the Frobenius product <alpha alpha^T - Sigma^-1, dK_j>, with dK_j generated on the
-// fly in registers from the same pairwise distance (never stored).  Partial sums are written
-// per CTA and added in a fixed order, so the result is bit-reproducible.
+// fly in registers from the same pairwise distance (never stored), over the lower triangle of
+// tiles only.  Partial sums are written per CTA and added in a fixed order, so the result is
+// bit-reproducible.
 #include "bqo_common.cuh"
 
 int bqo_internal_inverse_from_chol(const double* L, int n, int S, double* Inv, double* Wbuf,
@@ -39,7 +40,10 @@ __global__ void __launch_bounds__(256)
     double acc[LG_MAX_ACC];
     for (int q = 0; q < nacc; ++q) acc[q] = 0.0;
     const bool general_tasks = (d.kind == BQO_KIND_PRODUCT_TASKS) && !d.same_corr;
-    if (j < n) {
+    // M and every dK_j are symmetric: only tiles on or below the diagonal are visited, the
+    // strictly lower ones with weight 2 (the task-pair sums are used symmetrised downstream).
+    const double wsym = (blockIdx.x < blockIdx.y) ? 2.0 : 1.0;
+    if (j < n && blockIdx.x <= blockIdx.y) {
         double xj[BQO_MAX_DIM];
         for (int l = 0; l < dm; ++l) xj[l] = xs[(int64_t)l * n + j];
         const double aj = al[j];
@@ -47,7 +51,7 @@ __global__ void __launch_bounds__(256)
         for (int ii = 0; ii < 4; ++ii) {
             const int i = i0 + ii;
             if (i >= n) break;
-            const double Mij = al[i] * aj - inv[(int64_t)i * n + j];
+            const double Mij = wsym * (al[i] * aj - inv[(int64_t)i * n + j]);
             double df[BQO_MAX_DIM];
             double r2 = 0.0;
             for (int l = 0; l < dm; ++l) {

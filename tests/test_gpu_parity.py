@@ -56,6 +56,27 @@ def test_cholesky_loglik_and_gradient(golden, name):
                  what="grad llh")
 
 
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 130, 257, 300, 517])
+def test_loglik_gradient_ragged_sizes(n):
+    """Sizes that are not multiples of the 64-wide tiles (and of the doubling blocks of the
+    triangular inverse) against the oracle's grad_log_likelihood."""
+    from bayesian_quadrature_optimization_b200 import engine as E, _cabi
+    rng = np.random.RandomState(n)
+    pts = np.concatenate([rng.uniform(0, 1, (n, 2)), rng.randint(0, 3, (n, 1)).astype(float)], 1)
+    y = np.sin(3 * pts[:, 0]) + pts[:, 2] + 0.1 * rng.normal(0, 1, n)
+    thetas = np.array([[0.05, 0.1, 0.4, 0.6, 0.1, -0.3, 0.2, 0.0, -0.5, 0.3],
+                       [0.02, -0.1, 0.5, 0.3, 0.0, 0.1, -0.2, 0.3, 0.2, -0.1]])
+    eng = E.GPEngine(_cabi.KIND_PRODUCT_TASKS, 3, 3, False)
+    eng.set_data(pts, y)
+    hb = eng.hypers(thetas).factorize()
+    assert np.all(hb.info == 0)
+    spec = orc.KernelSpec(orc.PRODUCT_TASKS, 3, n_tasks=3, same_correlation=False)
+    ogp = orc.OracleGP(spec, pts, y)
+    want = np.stack([ogp.grad_log_likelihood(t[0], t[1], t[2:]) for t in thetas])
+    assert_close(hb.grad_log_likelihood().cpu().numpy(), want, rtol=1e-8, atol=1e-9,
+                 what="grad llh n=%d" % n)
+
+
 @pytest.mark.parametrize("name", CASES)
 def test_posterior_and_ei(golden, name):
     g = golden(name)
