@@ -98,6 +98,7 @@ SIGNATURES = {
         C.c_int,
         [_KD, _P, _I, _P, _P, _I, _P, _I, _P, C.POINTER(_I), C.POINTER(_D), _P],
     ),
+    "bqo_chol_append_batched": (C.c_int, [_P, _I, _I, _P, _P, _P, _P, _P]),
     "bqo_alpha_batched": (C.c_int, [_P, _L, _P, _I, _I, _P, _P, _P]),
     "bqo_loglik_batched": (C.c_int, [_P, _L, _P, _P, _P, _I, _I, _P, _P]),
     "bqo_loglik_grad_workspace_bytes": (_L, [_I, _I]),

@@ -404,14 +404,14 @@ static size_t trsv_smem_bytes(int n) {
 
 static int potrs_launch(const double* L, int n, int S, double* Bt, int m, int identity_rhs,
                         cudaStream_t cs, bool forward_only = false) {
-    if ((int64_t)m * S <= TRSV_MAX_VECTORS && m <= 65535 && !identity_rhs && !forward_only &&
+    if ((int64_t)m * S <= TRSV_MAX_VECTORS && m <= 65535 && !identity_rhs &&
         trsv_smem_bytes(n) <= 200 * 1024) {
         const size_t sb = trsv_smem_bytes(n);
         cudaFuncSetAttribute(trsv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
         cudaFuncSetAttribute(trsv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
         dim3 grid(m, S);
         trsv_kernel<true><<<grid, TRSV_THREADS, sb, cs>>>(L, n, Bt, m);
-        trsv_kernel<false><<<grid, TRSV_THREADS, sb, cs>>>(L, n, Bt, m);
+        if (!forward_only) trsv_kernel<false><<<grid, TRSV_THREADS, sb, cs>>>(L, n, Bt, m);
         return (int)cudaGetLastError();
     }
     static bool attr_done = false;
@@ -679,6 +679,71 @@ extern "C" int bqo_chol_cov_batched(const bqo_kernel_desc* desc, const double* h
     cudaFreeAsync(info_d, cs);
     e = cudaGetLastError();
     return rc ? rc : (int)e;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Appending one training point to S factors (the reference refactorises, see
+// the TODO at sbo/models/gp_fitting_gaussian.py:506-508):
+//   Sigma' = [ Sigma  k ]      L' = [ L    0      ]    L l = k,   lambda = sqrt(kappa - l.l)
+//            [ k^T  kappa ]         [ l^T  lambda ]
+// O(n^2) per factor instead of n^3/3.  `knew` is the new row of Sigma' ([S][n+1], noise and any
+// jitter of the old factor included in its last entry by the caller).
+__global__ void chol_append_copy_kernel(const double* __restrict__ Lold, int n,
+                                        double* __restrict__ Lnew) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y, s = blockIdx.z;
+    const int n1 = n + 1;
+    if (j >= n1) return;
+    double v = 0.0;
+    if (i < n && j < n) v = Lold[((int64_t)s * n + i) * n + j];
+    Lnew[((int64_t)s * n1 + i) * n1 + j] = v;
+}
+
+__global__ void chol_append_row_kernel(const double* __restrict__ lrow, const double* __restrict__ knew,
+                                       int n, double* __restrict__ Lnew, int* __restrict__ info) {
+    __shared__ double red[32];
+    const int s = blockIdx.x;
+    const int n1 = n + 1;
+    const double* l = lrow + (int64_t)s * n;
+    double* dst = Lnew + ((int64_t)s * n1 + n) * n1;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double v = l[i];
+        dst[i] = v;
+        acc = fma(v, v, acc);
+    }
+    const double ll = bqo_block_sum(acc, red);
+    if (threadIdx.x == 0) {
+        const double d = knew[(int64_t)s * n1 + n] - ll;
+        if (d > 0.0) {
+            dst[n] = sqrt(d);
+            info[s] = 0;
+        } else {
+            dst[n] = 0.0;
+            info[s] = n1;  // like dpotrf: order of the leading minor that is not positive definite
+        }
+    }
+}
+
+extern "C" int bqo_chol_append_batched(const double* L_old, int32_t n, int32_t S, const double* knew,
+                                       double* L_new, int32_t* info, void* workspace, void* stream) {
+    BQO_CHECK_ARG(L_old != nullptr, 1);
+    BQO_CHECK_ARG(n > 0, 2);
+    BQO_CHECK_ARG(S > 0 && S <= 65535, 3);
+    BQO_CHECK_ARG(knew != nullptr, 4);
+    BQO_CHECK_ARG(L_new != nullptr, 5);
+    BQO_CHECK_ARG(info != nullptr, 6);
+    BQO_CHECK_ARG(workspace != nullptr, 7);  // S * n doubles
+    cudaStream_t cs = (cudaStream_t)stream;
+    double* lrow = (double*)workspace;
+    cudaMemcpy2DAsync(lrow, sizeof(double) * n, knew, sizeof(double) * (n + 1), sizeof(double) * n, S,
+                      cudaMemcpyDeviceToDevice, cs);
+    int rc = potrs_launch(L_old, n, S, lrow, 1, 0, cs, true);  // forward solve only: L l = k
+    if (rc) return rc;
+    dim3 cg((n + 1 + 255) / 256, n + 1, S);
+    chol_append_copy_kernel<<<cg, 256, 0, cs>>>(L_old, n, L_new);
+    chol_append_row_kernel<<<S, 256, 0, cs>>>(lrow, knew, n, L_new, info);
+    BQO_RETURN_LAST_ERROR();
 }
 
 // ---------------------------------------------------------------------------------------------

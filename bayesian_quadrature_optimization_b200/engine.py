@@ -155,6 +155,36 @@ class HyperBatch(object):
                                         ptr(eng.y), ptr(self.alpha), _stream()), "bqo_alpha_batched")
         return self
 
+    def appended(self, eng2: GPEngine) -> "HyperBatch":
+        """The same hyper-samples on `eng2`, whose training set is this engine's plus ONE point
+        appended last: every factor is extended in O(n^2) (bqo_chol_append_batched) instead of
+        refactorised in O(n^3); alpha is recomputed with two vector solves.  Falls back to a
+        full factorisation when an extended matrix is not positive definite."""
+        eng = self.eng
+        if self.L is None or eng2.n != eng.n + 1:
+            raise ValueError("appended() needs a factorised batch and exactly one new point")
+        n, S = eng.n, self.S
+        hb2 = HyperBatch(eng2, self.theta)
+        knew = hb2.cross_cov(eng2.X[n:n + 1]).reshape(S, n + 1).clone()
+        extra = self.theta[:, 0] + eng.to_device(self.jitter)
+        if eng2.noise_obs is not None:
+            extra = extra + eng2.noise_obs[n]
+        knew[:, n] += extra
+        L_new = eng2.empty(S, n + 1, n + 1)
+        info = torch.zeros(S, dtype=I32, device=eng.device)
+        work = eng2.empty(S * n)
+        check(eng.lib.bqo_chol_append_batched(ptr(self.L), n, S, ptr(knew), ptr(L_new), ptr(info),
+                                              ptr(work), _stream()), "bqo_chol_append_batched")
+        if bool(info.any().item()):
+            return hb2.factorize()
+        hb2.L = L_new
+        hb2.info = np.zeros(S, dtype=np.int32)
+        hb2.jitter = self.jitter.copy()
+        hb2.alpha = eng2.empty(S, n + 1)
+        check(eng.lib.bqo_alpha_batched(ptr(hb2.hyp), eng2.hyp_stride, ptr(hb2.L), n + 1, S,
+                                        ptr(eng2.y), ptr(hb2.alpha), _stream()), "bqo_alpha_batched")
+        return hb2
+
     def solve(self, Bt):
         """Sigma_s^-1 applied to Bt[S][m][n] in place."""
         eng = self.eng

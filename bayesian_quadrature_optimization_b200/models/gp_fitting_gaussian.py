@@ -254,13 +254,27 @@ class GPFittingGaussian(object):
         self.kernel.update_value_parameters(vector[2:])
 
     def add_points_evaluations(self, point, evaluation, var_noise_eval=None):
-        """:492-511: append data, invalidate every cached factor."""
+        """:492-511: append data.  The reference drops its cached factors here (TODO at :506-508);
+        when exactly one point arrives, the device-resident factors of every cached hyper-sample
+        batch are extended in O(n^2) instead (HyperBatch.appended), so hyper-parameters that are
+        used again after the update (fixed / MLE parameters, the current slice-sampling state)
+        need no new O(n^3) factorisation."""
+        point = np.asarray(point, dtype=float).reshape(-1, self._dim)
         self.data['points'] = np.append(self.data['points'], point, axis=0)
         self.data['evaluations'] = np.append(self.data['evaluations'], evaluation)
         if var_noise_eval is not None:
             self.data['var_noise'] = np.append(self.data['var_noise'], var_noise_eval)
+        old_cache, old_eng = self._hb_cache, self._eng
         self.clean_cache()
         self._eng = None
+        if point.shape[0] == 1 and old_eng is not None and self.incremental_updates:
+            factored = [(k, hb) for k, hb in old_cache.items() if hb.L is not None]
+            if factored:
+                eng2 = self._engine()
+                for key, hb in factored:
+                    self._hb_cache[key] = hb.appended(eng2)
+
+    incremental_updates = True  # class-level switch (tests compare both paths)
 
     def clean_cache(self):
         self._hb_cache = OrderedDict()
@@ -523,3 +537,189 @@ class GPFittingGaussian(object):
         samples_return = samples[::self.thinning + 1]
         self.samples_parameters += samples_return
         return samples_return
+
+    def sample_parameters_posterior(self, n_samples, random_seed=None, start_point=None):
+        """:917-931 -> np.array(n_samples, n_parameters)."""
+        if random_seed is not None:
+            np.random.seed(random_seed)
+        samples = self.sample_parameters(n_samples, start_point=start_point)
+        return np.concatenate(samples).reshape(len(samples), len(samples[0]))
+
+    # -- maximum likelihood (a16) -------------------------------------------------------------------
+    @property
+    def get_bounds_parameters(self):
+        """:933-944: [(low, up)] for [var_noise, mean, kernel parameters]; length scales and
+        sigma2 are positive (matern52.py:150-151, scaled_kernel.py:150-152), task parameters free."""
+        from ..lib.constant import SMALLEST_POSITIVE_NUMBER
+        bounds = list(self.var_noise.bounds) if self.var_noise.bounds else [(None, None)]
+        bounds += list(self.mean.bounds) if self.mean.bounds else [(None, None)]
+        dm = self._dim - 1 if self._kind == _cabi.KIND_PRODUCT_TASKS else self._dim
+        bounds += dm * [(SMALLEST_POSITIVE_NUMBER, None)]
+        n_rest = self.dimension_parameters - 2 - dm
+        if self._kind == _cabi.KIND_SCALED_MATERN52:
+            bounds += [(SMALLEST_POSITIVE_NUMBER, None)]
+        else:
+            bounds += n_rest * [(None, None)]
+        return bounds
+
+    def objective_llh(self, params):
+        """:946-960: log-likelihood, or -inf when the factorisation fails."""
+        try:
+            return self.log_likelihood(params[0], params[1], params[2:])
+        except (linalg.LinAlgError, ZeroDivisionError, ValueError):
+            return -np.inf
+
+    def grad_llh(self, params):
+        """:962-973: gradient clipped to the finite range."""
+        from ..lib.constant import SMALLEST_NUMBER, LARGEST_NUMBER
+        return np.clip(self.grad_log_likelihood(params[0], params[1], params[2:]),
+                       SMALLEST_NUMBER, LARGEST_NUMBER)
+
+    def mle_parameters(self, start=None, random_seed=None):
+        """:975-1011 -> {'solution', 'optimal_value', 'gradient', 'warnflag', 'task', 'nit',
+        'funcalls'}: L-BFGS-B (scipy, as Optimization.optimize, sbo/lib/optimization.py:87-155)
+        on the GPU log-likelihood and its GPU gradient."""
+        from scipy.optimize import fmin_l_bfgs_b
+        if random_seed is not None:
+            np.random.seed(random_seed)
+        if start is None:
+            start = self.sample_parameters_posterior(1)[0, :]
+        opt = fmin_l_bfgs_b(lambda x: -1.0 * self.objective_llh(x), np.asarray(start, dtype=float),
+                            fprime=lambda x: -1.0 * self.grad_llh(x),
+                            bounds=self.get_bounds_parameters)
+        return {'solution': opt[0], 'optimal_value': -1.0 * opt[1], 'gradient': -1.0 * opt[2]['grad'],
+                'warnflag': opt[2]['warnflag'], 'task': opt[2]['task'], 'nit': opt[2]['nit'],
+                'funcalls': opt[2]['funcalls']}
+
+    def fit_gp_regression(self, start=None, random_seed=None):
+        """:1013-1038: MLE, then the model takes the optimum as its parameter values."""
+        if random_seed is not None:
+            np.random.seed(random_seed)
+        results = self.mle_parameters(start=start)
+        sol = results['solution']
+        self.update_value_parameters(sol)
+        self.kernel_values = list(sol[2:])
+        self.mean_value = list(sol[1:2])
+        self.var_noise_value = list(sol[0:1])
+        return self
+
+    # -- (de)serialisation: the reference's JSON wire format (f4) --------------------------------------
+    @staticmethod
+    def convert_from_numpy_to_list(data_as_np):
+        """:537-556."""
+        data = {'points': [list(p) for p in np.asarray(data_as_np['points'])],
+                'evaluations': list(np.asarray(data_as_np['evaluations']))}
+        vn = data_as_np.get('var_noise')
+        data['var_noise'] = list(vn) if vn is not None else []
+        return data
+
+    def serialize(self):
+        """:578-620: same keys as the reference, so existing gp_models/*.json files load."""
+        samples_parameters = [list(p) for p in self.samples_parameters]
+        if self.start_point_sampler is None:
+            self.start_point_sampler = []
+        return {
+            'type_kernel': self.type_kernel,
+            'training_data': self.training_data,
+            'dimensions': self.dimensions,
+            'kernel_values': list(self.kernel_values),
+            'mean_value': list(self.mean_value),
+            'var_noise_value': list(self.var_noise_value),
+            'thinning': self.thinning,
+            'n_burning': self.n_burning,
+            'max_steps_out': self.max_steps_out,
+            'data': self.convert_from_numpy_to_list(self.data),
+            'bounds_domain': self.bounds if self.bounds is not None else [],
+            'type_bounds': self.type_bounds,
+            'name_model': self.name_model,
+            'training_name': self.training_name if self.training_name is not None else '',
+            'problem_name': self.problem_name if self.problem_name is not None else '',
+            'same_correlation': self.additional_kernel_parameters.get(SAME_CORRELATION, False),
+            'start_point_sampler': list(self.start_point_sampler),
+            'samples_parameters': samples_parameters,
+        }
+
+    @classmethod
+    def deserialize(cls, s, use_only_training_points=True, **extra):
+        """:622-635.  `noise` is not part of the reference's wire format (its constructor default
+        applies); pass it through `extra` when the model was built with noise=True."""
+        kwargs = dict(s)
+        kwargs.update(extra)
+        model = cls(**kwargs)
+        if use_only_training_points:
+            model.data = model.convert_from_list_to_numpy(model.training_data)
+            model._eng = None
+            model.clean_cache()
+        return model
+
+    # -- maximisation of the posterior mean (a38, GP version) ---------------------------------------------
+    def optimize_posterior_mean(self, start=None, random_seed=None, minimize=False, n_restarts=100,
+                                n_best_restarts=10, parallel=True, n_treads=0, var_noise=None,
+                                mean=None, parameters_kernel=None, n_samples_parameters=0,
+                                start_new_chain=False, method_opt=None, maxepoch=10,
+                                candidate_solutions=None, candidate_values=None):
+        """:1373-1541 -> {'solution': np.array(d), 'optimal_value': np.array([value])}.
+
+        All restarts climb the posterior mean together on the device: with fixed
+        hyper-parameters 100 Adam steps on mu_n(x) and its gradient (the reference runs L-BFGS-B
+        per start), with n_samples_parameters > 0 `maxepoch` steps on the mean over the last
+        DEFAULT_N_PARAMETERS hyper-samples.  Task coordinates (type_bounds == 1) are kept fixed
+        at the start point's task, as L-BFGS-B does with their [t, t] style bounds."""
+        import torch
+        from ..lib.batched_ascent import batched_adam_ascent
+        from ..lib.constant import DEFAULT_N_PARAMETERS
+        from ..services.domain import DomainService
+        if candidate_solutions is not None and len(candidate_solutions) == 0:
+            candidate_solutions = None
+        if random_seed is not None:
+            np.random.seed(random_seed)
+        if start_new_chain and n_samples_parameters > 0:
+            self.start_new_chain()
+            self.sample_parameters(DEFAULT_N_PARAMETERS)
+        if n_samples_parameters == 0:
+            vn, mu, pk = self._defaults(var_noise, mean, parameters_kernel)
+            thetas = np.concatenate([[vn, mu], pk]).reshape(1, -1)
+        else:
+            thetas = np.array(self.samples_parameters[-DEFAULT_N_PARAMETERS:])
+        hb = self.hyper_batch(thetas).factorize(max_tries=7)
+        for s in range(hb.S):
+            self._raise_info(int(hb.info[s]))
+        dim_m = hb.eng.desc.dim_m
+
+        def averaged(p):
+            post = hb.posterior(p, var=False, grad=True)
+            g = post['grad_mean'].mean(dim=0)
+            if g.shape[1] < p.shape[1]:  # task coordinate: no gradient
+                pad = g.new_zeros(g.shape[0], p.shape[1] - g.shape[1])
+                g = torch.cat([g, pad], dim=1)
+            return post['mean'].mean(dim=0), g
+
+        if start is None:
+            start = np.array(DomainService.get_points_domain(n_restarts, self.bounds,
+                                                             type_bounds=self.type_bounds))
+            if start.shape[0] > n_best_restarts > 0:
+                values = averaged(hb.eng.to_device(start))[0].cpu().numpy()
+                start = start[np.argsort(values, kind='stable')[-n_best_restarts:]]
+        else:
+            start = np.asarray(start, dtype=float).reshape(1, -1)
+        lower = np.array([b[0] for b in self.bounds], dtype=float)
+        upper = np.array([b[-1] for b in self.bounds], dtype=float)
+        for l, tb in enumerate(self.type_bounds):
+            if tb == 1:  # finite set: the coordinate does not move
+                lower[l], upper[l] = -np.inf, np.inf
+        sign = -1.0 if minimize else 1.0
+        ends, values = batched_adam_ascent(
+            hb.eng, averaged, start, lower, upper,
+            maxepoch=maxepoch if n_samples_parameters > 0 else 100, sign=sign)
+        ind = int(np.argmax(sign * values))
+        result = {'solution': ends[ind], 'optimal_value': np.array([values[ind]])}
+        if candidate_solutions is not None:
+            cand = np.array([list(c) for c in candidate_solutions], dtype=float)
+            cvals = averaged(hb.eng.to_device(cand))[0].cpu().numpy()
+            j = int(np.argmax(cvals))
+            if cvals[j] > np.max(sign * values):
+                result = {'solution': cand[j], 'optimal_value': np.array([cvals[j]])}
+        if not hasattr(self, 'optimization_results'):
+            self.optimization_results = []
+        self.optimization_results.append(result)
+        return result

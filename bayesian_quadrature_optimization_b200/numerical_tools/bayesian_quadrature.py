@@ -18,8 +18,9 @@ from .. import _cabi
 from ..engine import BQEngine
 from ..lib.constant import (
     UNIFORM_FINITE, WEIGHTED_UNIFORM_FINITE, GAMMA, EXPONENTIAL, TASKS, BAYESIAN_QUADRATURE,
-    N_SAMPLES_W,
+    N_SAMPLES_W, DEFAULT_N_PARAMETERS,
 )
+from ..services.domain import DomainService
 
 
 class BayesianQuadrature(object):
@@ -244,6 +245,106 @@ class BayesianQuadrature(object):
         point = np.asarray(point, dtype=float).reshape((1, -1))
         return self.gradient_posterior_mean(point, var_noise=var_noise, mean=mean,
                                             parameters_kernel=parameters_kernel)
+
+    # -- maximisation of the posterior mean of G ----------------------------------------------------------
+    def _averaged_mean_and_grad(self, bq, ub, pts):
+        """mean over the hyper-samples of (mu_k(x), grad mu_k(x)) for every row of `pts`
+        (device tensors): one sample_ab launch over R x S (point, hyper-sample) pairs."""
+        S = bq.hb.S
+        dx = len(self.x_domain)
+        pts = bq.eng.to_device(pts).reshape(-1, dx)
+        R = int(pts.shape[0])
+        rep = pts.repeat_interleave(S, dim=0).contiguous()
+        units = np.tile(np.arange(S, dtype=np.int32), R)
+        wset = np.zeros(R * S, dtype=np.int32) if self.w_sets is not None else None
+        out = bq.sample_ab(ub, rep, units, wset).reshape(R, S, -1)
+        return out[:, :, 0].mean(dim=1), out[:, :, 2:2 + dx].mean(dim=1)
+
+    def optimize_posterior_mean(self, start=None, random_seed=None, minimize=False, n_restarts=1000,
+                                n_best_restarts=100, parallel=True, n_treads=0, var_noise=None,
+                                mean=None, parameters_kernel=None, n_samples_parameters=0,
+                                start_new_chain=False, method_opt=None, maxepoch=10,
+                                candidate_solutions=None, candidate_values=None):
+        """:693-910 -> {'solution': np.array(d_x), 'optimal_value': np.array([value])} (the
+        reference's callers read optimal_value[0], bayesian_global_optimization.py:281)
+
+        Same arguments and bookkeeping (`optimal_solutions`, `max_mean`) as the reference.  With
+.
+
+        With fixed hyper-parameters the device quasi-Newton maximiser climbs the posterior mean of G
+        (the stage-C objective a(x) with Z = 0) from every start in one launch; with
+        n_samples_parameters > 0 the objective is the mean over the last DEFAULT_N_PARAMETERS
+        hyper-samples (BayesianEvaluations, sbo/bayesian/bayesian_evaluations.py:9-44) and all
+        restarts take `maxepoch` Adam steps together on its exact gradient (the reference feeds
+        Adam one slice sample per gradient, :662-676)."""
+        import itertools
+        from ..lib.batched_ascent import batched_adam_ascent
+        if candidate_solutions is not None and len(candidate_solutions) == 0:
+            candidate_solutions = None
+        if random_seed is not None:
+            np.random.seed(random_seed)
+        if start_new_chain and n_samples_parameters > 0:
+            self.gp.start_new_chain()
+            self.gp.sample_parameters(DEFAULT_N_PARAMETERS)
+        bounds_x = self.bounds_x()
+        dim_x = len(bounds_x)
+        vertex = None
+        if dim_x < 7 and self.simplex_domain is None:
+            vertex = [list(p) for p in itertools.product(*bounds_x)]
+        if n_samples_parameters == 0:
+            theta = self._theta(var_noise, mean, parameters_kernel)
+            thetas = theta.reshape(1, -1)
+            index_cache = (theta[0], theta[1], tuple(theta[2:]))
+        else:
+            thetas = np.array(self.gp.samples_parameters[-DEFAULT_N_PARAMETERS:])
+            index_cache = 'mc_mean'
+        bq = self.engine_for(thetas)
+        ub = bq.setup(self._dummy_candidate())
+        sign = -1.0 if minimize else 1.0
+
+        def averaged(p):
+            return self._averaged_mean_and_grad(bq, ub, p)
+
+        if start is None:
+            start_points = DomainService.get_points_domain(
+                n_restarts + 1, bounds_x, type_bounds=len(self.x_domain) * [0], simplex_domain=None)
+            prev = self.optimal_solutions.get(index_cache)
+            if prev is not None and len(prev) > 0:
+                start = np.array([prev[-1]['solution']] + start_points[0:-1])
+            else:
+                start = np.array(start_points)
+            if start.shape[0] > n_best_restarts > 0:
+                values = averaged(start)[0].cpu().numpy()
+                keep = np.argsort(values, kind='stable')[-n_best_restarts:]
+                start = start[keep]
+        else:
+            start = np.asarray(start, dtype=float).reshape(1, -1)
+        lower = np.array([b[0] for b in bounds_x], dtype=float)
+        upper = np.array([b[-1] for b in bounds_x], dtype=float)
+        if n_samples_parameters == 0 and not minimize:
+            mx, arg, _ = bq.inner_maximize(ub, np.zeros(1), start, maxiter=100, factr=1e7,
+                                           use_vertices=False)
+            # the kernel already keeps the best run over the starts (np.argmax over restarts)
+            ends = arg.cpu().numpy()[0, 0:1]
+            values = mx.cpu().numpy()[0, 0:1]
+        else:
+            ends, values = batched_adam_ascent(bq.eng, averaged, start, lower, upper,
+                                               maxepoch=maxepoch if n_samples_parameters > 0 else 100,
+                                               sign=sign)
+        score = sign * values
+        ind = int(np.argmax(score))
+        solution, value = ends[ind], float(values[ind])
+        max_ = float(np.max(score))
+        if candidate_solutions is not None or vertex is not None:
+            cand = [list(c) for c in (candidate_solutions or [])] + (vertex or [])
+            cvals = averaged(np.array(cand, dtype=float))[0].cpu().numpy()
+            j = int(np.argmax(cvals))
+            if cvals[j] > max_:  # (the reference compares the raw values, also when minimising)
+                solution, value = np.array(cand[j], dtype=float), float(cvals[j])
+        result = {'solution': np.asarray(solution, dtype=float), 'optimal_value': np.array([value])}
+        self.optimal_solutions.setdefault(index_cache, []).append(result)
+        self.max_mean[index_cache] = max_
+        return result
 
     # -- per-candidate quantities --------------------------------------------------------------------
     def get_parameters_for_samples(self, cache, candidate_point, parameters_kernel, var_noise, mean,

@@ -35,31 +35,6 @@ def _evaluate(function, point, noise, n_samples_noise):
     return float(out[0] if isinstance(out, (list, tuple, np.ndarray)) else out), None
 
 
-def _optimize_posterior_mean(gp, quadrature, bounds_x, n_restarts):
-    """max_x of the posterior mean of the objective, Bayesian-averaged over the hyper-samples
-    (BayesianQuadrature.optimize_posterior_mean, bayesian_quadrature.py:693-910; GP version
-    gp_fitting_gaussian.py:1373-1541).  On the device: the inner maximiser with Z = 0 from
-    n_restarts + 1 starts and the box vertices, once per hyper-sample; the averaged mean is then
-    compared at those optima."""
-    thetas = np.array(gp.samples_parameters[-DEFAULT_N_PARAMETERS:])
-    starts = np.array(DomainService.get_points_domain(n_restarts + 1, bounds_x,
-                                                      type_bounds=len(bounds_x) * [0]))
-    if quadrature is not None:
-        bq = quadrature.engine_for(thetas)
-        ub = bq.setup(quadrature._dummy_candidate())
-        _, arg, _ = bq.inner_maximize(ub, np.zeros(1), starts, maxiter=100, factr=1e7,
-                                      use_vertices=len(bounds_x) < 7)
-        cands = np.unique(arg.cpu().numpy()[:, 0], axis=0)
-        mean, _ = bq.quadrature_posterior(cands, var=False)
-        avg = mean.mean(dim=0).cpu().numpy()
-    else:
-        hb = gp.hyper_batch(thetas)
-        cands = np.concatenate([starts, gp.data['points']], axis=0)
-        avg = hb.posterior(cands, var=False)['mean'].mean(dim=0).cpu().numpy()
-    i = int(np.argmax(avg))
-    return {'solution': cands[i], 'optimal_value': float(avg[i])}
-
-
 def bgo(objective_function, bounds_domain_x, integrand_function=None, simplex_domain=None,
         noise=False, n_samples_noise=0, bounds_domain_w=None, type_bounds=None, distribution=None,
         parameters_distribution=None, name_method='bqo', n_iterations=50, type_kernel=None,
@@ -128,6 +103,9 @@ def bgo(objective_function, bounds_domain_x, integrand_function=None, simplex_do
         simplex_domain=simplex_domain, problem_name=problem_name or 'user_problem', device=device,
         **kernel_parameters)
 
+    if mle:  # GPFittingService.get_gp(..., mle=True): maximum-likelihood parameter values
+        gp_model.fit_gp_regression(random_seed=random_seed)
+
     quadrature = None
     if name_method == SBO_METHOD:
         quadrature = BayesianQuadrature(gp_model, x_domain, distribution,
@@ -163,11 +141,12 @@ def bgo(objective_function, bounds_domain_x, integrand_function=None, simplex_do
                                         var_noise_eval=None if s2 is None else np.array([s2]))
         acquisition_function.clean_cache()
 
-    if len(gp_model.samples_parameters) < DEFAULT_N_PARAMETERS:
-        gp_model.start_new_chain()
-        gp_model.sample_parameters(DEFAULT_N_PARAMETERS)
-    bounds_x = [list(b) for b in bounds_domain_x]
-    optimize_mean = _optimize_posterior_mean(gp_model, quadrature, bounds_x, n_restarts_mean)
+    # maximise the posterior mean of the objective (bayesian_global_optimization.py:365-372)
+    model = quadrature if quadrature is not None else gp_model
+    optimize_mean = model.optimize_posterior_mean(
+        minimize=False, n_restarts=n_restarts_mean, n_best_restarts=n_best_restarts_mean,
+        n_samples_parameters=n_samples_parameters_mean, start_new_chain=True,
+        maxepoch=maxepoch_mean)
     optimal_value = _evaluate(objective_function, optimize_mean['solution'][0:dim_x], noise,
                               n_samples_noise)[0]
     return {'optimal_solution': np.asarray(optimize_mean['solution'])[0:dim_x],

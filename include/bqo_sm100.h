@@ -121,6 +121,14 @@ int bqo_chol_cov_batched(const bqo_kernel_desc* desc, const double* hyp, int32_t
                          const double* Xs, const int32_t* tid, int32_t n, const double* noise_obs,
                          int32_t max_tries, double* L, int32_t* info_host,
                          double* jitter_used_host, void* stream);
+/* Append one training point to S factors in O(n^2) each (the "updated cache in a smart way" TODO of
+ * add_points_evaluations, sbo/models/gp_fitting_gaussian.py:492-511, which refactorises instead).
+ * knew[s][0..n) = Sigma'_s(new, old points), knew[s][n] = Sigma'_s(new, new) including noise (and the
+ * jitter of the old factor, if any).  L_new: [S][n+1][n+1], lower, strict upper triangle zero.
+ * info[s] = 0, or n+1 when the extended matrix is not positive definite (device array).
+ * workspace: S*n doubles. */
+int bqo_chol_append_batched(const double* L_old, int32_t n, int32_t S, const double* knew,
+                            double* L_new, int32_t* info, void* workspace, void* stream);
 /* alpha[s] = Sigma_s^{-1} (y - mean_s)  (sbo/models/gp_fitting_gaussian.py:1241-1244). */
 int bqo_alpha_batched(const double* hyp, int64_t hyp_stride, const double* L, int32_t n, int32_t S,
                       const double* y, double* alpha, void* stream);

@@ -260,3 +260,128 @@ def test_bgo_end_to_end_small():
               thinning=1, n_burning=2, max_steps_out=10, n_restarts=3, n_samples_parameters=2,
               maxepoch=2, n_restarts_mean=10)
     assert 0.0 <= sol["optimal_solution"][0] <= 1.0 and np.isfinite(sol["optimal_value"])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_optimize_posterior_mean_quadrature_and_gp(golden, name):
+    """a38: the maximisers return the reference's dict, stay in the box, dominate every start
+    point / vertex, and their value is the oracle's posterior mean at the returned solution."""
+    import itertools
+    g = golden(name)
+    gp, bq = _models(g)
+    spec, ogp, obq = oracle_from_golden(g)
+    th = g["thetas"][0]
+    w = g["wset"] if "wset" in g else None
+    dx = int(g["dx"])
+    np.random.seed(3)
+    res = bq.optimize_posterior_mean(n_restarts=8, n_best_restarts=4, var_noise=th[0], mean=th[1],
+                                     parameters_kernel=th[2:])
+    sol, val = res["solution"], res["optimal_value"]
+    assert sol.shape == (dx,) and np.asarray(val).shape == (1,)
+    bx = bq.bounds_x()
+    assert all(bx[l][0] - 1e-12 <= sol[l] <= bx[l][-1] + 1e-12 for l in range(dx))
+    want = obq.compute_posterior_parameters(sol.reshape(1, -1), th[0], th[1], th[2:],
+                                            only_mean=True, w=w)["mean"]
+    assert_close(val, np.asarray(want).reshape(-1), rtol=cond_rtol(g, 0), atol=1e-10,
+                 what="posterior mean at the optimum")
+    verts = np.array(list(itertools.product(*bx)), dtype=float)
+    vmean = bq.compute_posterior_parameters(verts, th[0], th[1], th[2:], only_mean=True)["mean"]
+    assert val[0] >= np.max(vmean) - 1e-10
+    key = (th[0], th[1], tuple(th[2:]))
+    assert bq.optimal_solutions[key][-1] is res and key in bq.max_mean
+    # Bayesian average over the hyper-samples
+    gp.samples_parameters = [t.copy() for t in g["thetas"]]
+    res2 = bq.optimize_posterior_mean(n_restarts=6, n_best_restarts=3, n_samples_parameters=5,
+                                      maxepoch=15)
+    sol2 = res2["solution"]
+    want2 = np.mean([obq.compute_posterior_parameters(sol2.reshape(1, -1), t[0], t[1], t[2:],
+                                                      only_mean=True, w=w)["mean"][0]
+                     for t in g["thetas"]])
+    assert_close(res2["optimal_value"][0], want2, rtol=max(cond_rtol(g, s) for s in range(len(g["thetas"]))),
+                 atol=1e-10, what="averaged posterior mean at the optimum")
+    assert "mc_mean" in bq.optimal_solutions
+    # GP version: full-dimensional points, task coordinate kept fixed
+    np.random.seed(4)
+    res3 = gp.optimize_posterior_mean(n_restarts=12, n_best_restarts=4, var_noise=th[0], mean=th[1],
+                                      parameters_kernel=th[2:])
+    s3 = res3["solution"]
+    assert s3.shape == (g["points"].shape[1],)
+    want3 = ogp.compute_posterior_parameters(s3.reshape(1, -1), th[0], th[1], th[2:],
+                                             only_mean=True)["mean"]
+    assert_close(res3["optimal_value"], np.asarray(want3).reshape(-1), rtol=cond_rtol(g, 0),
+                 atol=1e-10, what="GP posterior mean at the optimum")
+    if int(g["kind"]) == 2:
+        assert float(s3[-1]) == float(int(s3[-1]))  # still a task id
+
+
+def test_mle_parameters_and_serialisation_roundtrip(golden):
+    """a16 + the JSON wire format: L-BFGS-B on the GPU log-likelihood reaches the optimum that
+    the same optimiser finds on the oracle; serialize() -> json -> deserialize() reproduces the
+    model."""
+    import json
+    from scipy.optimize import fmin_l_bfgs_b
+    from bayesian_quadrature_optimization_b200.models.gp_fitting_gaussian import GPFittingGaussian
+    g = golden("scaled_gamma")
+    gp, _ = _models(g)
+    spec, ogp, _ = oracle_from_golden(g)
+    start = g["thetas"][1].copy()
+    res = gp.mle_parameters(start=start)
+    assert set(["solution", "optimal_value", "gradient", "warnflag", "task"]) <= set(res)
+    assert res["optimal_value"] >= gp.log_likelihood(start[0], start[1], start[2:]) - 1e-9
+
+    def f(x):
+        try:
+            return -ogp.log_likelihood(x[0], x[1], x[2:])
+        except Exception:
+            return np.inf
+
+    ref = fmin_l_bfgs_b(f, start, fprime=lambda x: -np.clip(
+        ogp.grad_log_likelihood(x[0], x[1], x[2:]), -1e300, 1e300), bounds=gp.get_bounds_parameters)
+    assert_close(res["optimal_value"], -ref[1], rtol=1e-6, atol=1e-6, what="mle optimum")
+    gp.fit_gp_regression(start=start)
+    assert_close(gp.get_value_parameters_model, res["solution"], rtol=0, atol=0)
+    # serialisation
+    gp.samples_parameters = [t.copy() for t in g["thetas"]]
+    wire = json.loads(json.dumps(gp.serialize()))
+    assert set(wire) >= {"type_kernel", "training_data", "dimensions", "kernel_values", "mean_value",
+                         "var_noise_value", "thinning", "n_burning", "max_steps_out", "data",
+                         "bounds_domain", "type_bounds", "name_model", "training_name",
+                         "problem_name", "same_correlation", "start_point_sampler",
+                         "samples_parameters"}
+    gp2 = GPFittingGaussian.deserialize(wire, noise=True, define_samplers=False)
+    th = g["thetas"][0]
+    assert gp2.log_likelihood(th[0], th[1], th[2:]) == gp.log_likelihood(th[0], th[1], th[2:])
+    assert_close(np.array(gp2.samples_parameters), g["thetas"], rtol=0, atol=0)
+    assert_close(gp2.get_value_parameters_model, gp.get_value_parameters_model, rtol=0, atol=0)
+
+
+def test_add_points_extends_cached_factors(golden):
+    """add_points_evaluations keeps the cached hyper-sample batches alive by appending to their
+    factors; results equal those of the invalidate-and-refactorise path of the reference."""
+    from bayesian_quadrature_optimization_b200.models.gp_fitting_gaussian import GPFittingGaussian
+    g = golden("scaled_gamma")
+    gp_inc, _ = _models(g)
+    gp_ref, _ = _models(g)
+    gp_ref.incremental_updates = False
+    thetas = g["thetas"]
+    for gp in (gp_inc, gp_ref):
+        gp.log_likelihood_batch(thetas)  # factors of all hyper-samples become resident
+    rng = np.random.RandomState(9)
+    for it in range(3):
+        p = np.concatenate([rng.uniform(0, 1, int(g["dx"])),
+                            rng.gamma(2.0, 1.0, g["points"].shape[1] - int(g["dx"]))]).reshape(1, -1)
+        v = np.array([np.sin(p.sum())])
+        gp_inc.add_points_evaluations(p, v)
+        gp_ref.add_points_evaluations(p, v)
+        assert len(gp_inc._hb_cache) >= 1 and len(gp_ref._hb_cache) == 0
+        for hb in gp_inc._hb_cache.values():
+            assert hb.L is not None and hb.eng.n == len(gp_inc.data['evaluations'])
+        a = gp_inc.log_likelihood_batch(thetas)
+        b = gp_ref.log_likelihood_batch(thetas)
+        assert_close(a, b, rtol=1e-11, what="llh after %d appended points" % (it + 1))
+        q = g["query"][0:2]
+        th = thetas[0]
+        pa = gp_inc.compute_posterior_parameters(q, th[0], th[1], th[2:])
+        pb = gp_ref.compute_posterior_parameters(q, th[0], th[1], th[2:])
+        assert_close(pa["mean"], pb["mean"], rtol=1e-9, atol=1e-12)
+        assert_close(pa["cov"], pb["cov"], rtol=1e-7, atol=1e-11)

@@ -371,3 +371,35 @@ def test_adam_step_matches_reference_sgd():
             _cabi.ptr(lo), _cabi.ptr(up), R, dim, t, 0.1, 0.9, 0.999, 1e-8,
             torch.cuda.current_stream().cuda_stream), "adam")
     assert_close(pt.cpu().numpy(), want, rtol=1e-12, atol=1e-14, what="adam")
+
+
+@pytest.mark.parametrize("n", [1, 5, 63, 64, 65, 200, 300])
+def test_factor_append_matches_refactorisation(n):
+    """extending S factors by one point in O(n^2) gives the factor, alpha and
+    log-likelihood of a fresh O(n^3) factorisation of the n + 1 points."""
+    from bayesian_quadrature_optimization_b200 import engine as E, _cabi
+    rng = np.random.RandomState(100 + n)
+    pts = np.concatenate([rng.uniform(0, 1, (n + 1, 2)), rng.randint(0, 3, (n + 1, 1)).astype(float)], 1)
+    y = np.sin(3 * pts[:, 0]) + pts[:, 2] + 0.1 * rng.normal(0, 1, n + 1)
+    vno = 0.01 + 0.01 * rng.uniform(0, 1, n + 1)
+    thetas = np.array([[0.05, 0.1, 0.4, 0.6, 0.3, -0.2],
+                       [0.02, -0.1, 0.5, 0.3, 0.1, -0.4]])
+    for noise_obs in (None, vno):
+        eng = E.GPEngine(_cabi.KIND_PRODUCT_TASKS, 3, 3, True)
+        eng.set_data(pts[:n], y[:n], None if noise_obs is None else noise_obs[:n])
+        hb = eng.hypers(thetas).factorize()
+        eng2 = E.GPEngine(_cabi.KIND_PRODUCT_TASKS, 3, 3, True)
+        eng2.set_data(pts, y, noise_obs)
+        got = hb.appended(eng2)
+        want = eng2.hypers(thetas).factorize()
+        assert np.all(got.info == 0)
+        assert_close(got.L.cpu().numpy(), want.L.cpu().numpy(), rtol=1e-10, atol=1e-13,
+                     what="appended factor n=%d" % n)
+        assert_close(got.alpha.cpu().numpy(), want.alpha.cpu().numpy(), rtol=1e-8, atol=1e-10,
+                     what="alpha after append")
+        assert_close(got.log_likelihood().cpu().numpy(), want.log_likelihood().cpu().numpy(),
+                     rtol=1e-11, what="llh after append")
+        spec = orc.KernelSpec(orc.PRODUCT_TASKS, 3, n_tasks=3, same_correlation=True)
+        ogp = orc.OracleGP(spec, pts, y, noise_obs)
+        ref = [ogp.log_likelihood(t[0], t[1], t[2:]) for t in thetas]
+        assert_close(got.log_likelihood().cpu().numpy(), ref, rtol=1e-10, what="llh vs oracle")
