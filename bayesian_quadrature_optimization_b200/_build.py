@@ -88,16 +88,22 @@ def build_variant(tag: str, defines: dict) -> Path:
     nvcc = _nvcc()
     out = LIB_DIR / ("libbqo_sm100_%s.so" % tag)
     objs = []
+    # macros that only bqo_stage_c.cu reads recompile that file alone; anything else, everything
+    stage_c_only = all(k in ("IM_WARPS", "EVAL_NV", "BQO_EXP_BITS", "BQO_POLY_UR", "BQO_HALF_INT")
+                       for k in defines)
+    flags = ["-D%s=%s" % kv for kv in defines.items()]
+    procs = []
     for src in SOURCES:
         obj = LIB_DIR / (src[:-3] + ".o")
-        if src == "bqo_stage_c.cu":
-            obj = LIB_DIR / ("bqo_stage_c_%s.o" % tag)
-            flags = ["-D%s=%s" % kv for kv in defines.items()]
+        if src == "bqo_stage_c.cu" or not stage_c_only:
+            obj = LIB_DIR / ("%s_%s.o" % (src[:-3], tag))
             cmd = [nvcc, *NVCC_FLAGS, *flags, "-c", str(CSRC / src), "-o", str(obj)]
-            r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
-            if r.returncode != 0:
-                raise RuntimeError(r.stdout.decode())
+            procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
         objs.append(str(obj))
+    for pr in procs:
+        out_, _ = pr.communicate()
+        if pr.returncode != 0:
+            raise RuntimeError(out_.decode())
     link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(out), *objs]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     if r.returncode != 0:

@@ -15,82 +15,180 @@
 #define LDT (NB + 1)
 
 // ---------------------------------------------------------------------------------------------
+// 1/sqrt(d) to full precision: MUFU.RSQ64H seed (2^-22) and two Newton steps.
+__device__ __forceinline__ double bqo_rsqrt_full(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double hd = 0.5 * d;
+    double e = fma(-hd * y, y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-hd * y, y, 0.5);
+    y = fma(y, e, y);
+    return y;
+}
+
 // Factor the NB x NB block held in shared memory `Ls` (stride LDT), lower triangle, in place.
-// Left-looking by column; threads 0..NB-1 own one row each.  Returns (to all threads) 0 or the
-// 1-based index of the first non-positive pivot.  `nv` = valid rows/cols (<= NB).
-__device__ int potrf_block_smem(double* Ls, int nv, int* flag_sm) {
-    const int t = threadIdx.x;
+// 128 threads.  Returns (to all threads) 0 or the 1-based index of the first non-positive pivot.
+// Rows / columns >= nv must hold the identity (the loaders do that), so the loops need no tails.
+//
+// Blocked right-looking, 8 block steps of width 8 (a column-by-column version needs 64 x 2
+// barriers and a latency-bound dot product per column: 56 us per block on B200):
+//   (1) the 8x8 diagonal block: lanes 0..7 of warp 0 hold one row each in registers; per pivot
+//       1/sqrt by MUFU.RSQ64H + Newton, the pivot column goes through shared memory;
+//   (2) the panel below it: one thread per row, 8 right-looking steps in registers;
+//   (3) the trailing update A[i][j] -= sum_p L[i][c0+p] L[j][c0+p], j <= i: row i's eight panel
+//       values in registers, the (row, column-group) pairs spread over all 128 threads.
+// `rdiag` (NB doubles of shared memory) receives 1 / l_kk.
+#define PBS 8
+__device__ int potrf_block_smem(double* Ls, int* flag_sm, double* rdiag) {
+    __shared__ double colbuf[PBS];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     if (t == 0) *flag_sm = 0;
     __syncthreads();
-    for (int k = 0; k < nv; ++k) {
-        if (t >= k && t < nv) {
-            double a0 = 0.0, a1 = 0.0;
-            int j = 0;
-            for (; j + 1 < k; j += 2) {
-                a0 = fma(Ls[t * LDT + j], Ls[k * LDT + j], a0);
-                a1 = fma(Ls[t * LDT + j + 1], Ls[k * LDT + j + 1], a1);
+    for (int c0 = 0; c0 < NB; c0 += PBS) {
+        // ---- (1) diagonal 8x8 block ----------------------------------------------------------
+        if (warp == 0) {
+            double a[PBS];
+            const int row = c0 + (lane & (PBS - 1));
+#pragma unroll
+            for (int q = 0; q < PBS; ++q) a[q] = Ls[row * LDT + c0 + q];
+            int bad = 0;
+#pragma unroll
+            for (int p = 0; p < PBS; ++p) {
+                const double d = __shfl_sync(0xffffffffu, a[p], p);
+                if (!(d > 0.0) && bad == 0) bad = c0 + p + 1;  // also catches NaN
+                const double r = bqo_rsqrt_full(d > 0.0 ? d : 1.0);
+                if (lane == p) {
+                    double g = d * r;                     // sqrt(d), one correction step
+                    a[p] = fma(fma(-g, g, d), 0.5 * r, g);
+                    rdiag[c0 + p] = r;
+                } else if (lane > p) {
+                    a[p] *= r;
+                }
+                if (lane < PBS) colbuf[lane] = a[p];
+                __syncwarp();
+#pragma unroll
+                for (int q = p + 1; q < PBS; ++q)
+                    if (lane >= q) a[q] = fma(-a[p], colbuf[q], a[q]);
+                __syncwarp();
             }
-            if (j < k) a0 = fma(Ls[t * LDT + j], Ls[k * LDT + j], a0);
-            Ls[t * LDT + k] -= (a0 + a1);
+            if (lane < PBS) {
+#pragma unroll
+                for (int q = 0; q < PBS; ++q)
+                    if (q <= lane) Ls[row * LDT + c0 + q] = a[q];
+            }
+            if (bad && lane == 0) *flag_sm = bad;
         }
         __syncthreads();
-        double d = Ls[k * LDT + k];
-        if (!(d > 0.0)) {  // also catches NaN
-            if (t == 0 && *flag_sm == 0) *flag_sm = k + 1;
-            __syncthreads();
-            return *flag_sm;
+        if (*flag_sm) return *flag_sm;
+        const int m = NB - c0 - PBS;  // rows below the diagonal block
+        if (m <= 0) break;
+        // ---- (2) panel: rows c0+8 .. 63, x L_d^T = a -------------------------------------------
+        if (t < m) {
+            double x[PBS];
+            double* ar = Ls + (c0 + PBS + t) * LDT + c0;
+#pragma unroll
+            for (int q = 0; q < PBS; ++q) x[q] = ar[q];
+#pragma unroll
+            for (int p = 0; p < PBS; ++p) {
+                x[p] *= rdiag[c0 + p];
+#pragma unroll
+                for (int q = p + 1; q < PBS; ++q)
+                    x[q] = fma(-x[p], Ls[(c0 + q) * LDT + c0 + p], x[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < PBS; ++q) ar[q] = x[q];
         }
-        double sd = sqrt(d);
         __syncthreads();
-        if (t == k) Ls[k * LDT + k] = sd;
-        if (t > k && t < nv) Ls[t * LDT + k] /= sd;
+        // ---- (3) trailing update ----------------------------------------------------------------
+        {
+            const int groups = 128 / m;          // column groups per row (>= 2)
+            const int ri = t % m, g = t / m;
+            if (g < groups) {
+                const int i = c0 + PBS + ri;
+                double li[PBS];
+#pragma unroll
+                for (int q = 0; q < PBS; ++q) li[q] = Ls[i * LDT + c0 + q];
+                for (int j = c0 + PBS + g; j <= i; j += groups) {
+                    const double* lj = Ls + j * LDT + c0;
+                    double acc = 0.0;
+#pragma unroll
+                    for (int q = 0; q < PBS; ++q) acc = fma(li[q], lj[q], acc);
+                    Ls[i * LDT + j] -= acc;
+                }
+            }
+        }
         __syncthreads();
     }
     return 0;
 }
 
-// Panel kernel for block column k0.  grid = (row tiles from the diagonal tile down, S).
-// Every CTA factors the 64x64 diagonal block in its own shared memory (redundant, ~5 us, but it
-// removes the launch and the global synchronisation a separate diagonal kernel would need) and
-// then solves its 64 rows of the panel, X L11^T = A21, one thread per row with L11 broadcast
-// from shared memory.  The diagonal tile's CTA stores the factor in `diag_scratch` instead of in
-// place: the other CTAs of this launch still read the unfactored block from A.
-// (Two right-looking rewrites were measured and dropped: rows in registers, fully unrolled --
-// 16 000 straight-line instructions, instruction-fetch bound at 95 us; tiles in shared memory
-// with rolled loops -- shared-memory latency and bank conflicts, 113 us; this version: 72-90 us.)
+// Panel kernel for block column k0: factor the 64x64 diagonal block, then solve the rows below
+// it, X L11^T = A21, one thread per row with L11 broadcast from shared memory.
+//   MODE 0 (fused): grid = (row tiles from the diagonal tile down, S).  Every CTA factors the
+//     diagonal block itself -- redundant, but it removes a launch and a global synchronisation;
+//     this is the latency-optimal form (45 us per block column) and is used while the grid fits
+//     the machine in about one wave.
+//   MODE 1 + MODE 2 (split): one CTA per matrix factors the block and stores it in
+//     `diag_scratch`; a second launch solves the row tiles against the stored factor.  Used when
+//     the fused grid would be several waves of redundant factorisations (20 matrices of
+//     n = 2048: 620 CTAs, 102 us fused).
+// The diagonal tile's factor goes to `diag_scratch` instead of in place in MODE 0 because the
+// other CTAs of that launch still read the unfactored block from A; potrf_finish_kernel copies
+// it back.
+// (Two right-looking rewrites of the row solve were measured and dropped: rows in registers with
+// the factor fully unrolled too -- 16 000 straight-line instructions, instruction-fetch bound;
+// tiles in shared memory with rolled loops -- shared-memory latency and bank conflicts.)
+template <int MODE>
 __global__ void __launch_bounds__(128) potrf_panel_kernel(double* __restrict__ A, int n, int k0,
                                                           int* __restrict__ info,
                                                           double* __restrict__ diag_scratch) {
     extern __shared__ double dyn_smem[];
     double* Ls = dyn_smem;
     __shared__ int flag;
+    __shared__ double rdiag[NB];
     const int s = blockIdx.y;
     if (info[s] != 0) return;  // this matrix already failed
     double* As = A + (int64_t)s * n * n;
     const int nv = (n - k0 < NB) ? n - k0 : NB;
     const int nb = (n + NB - 1) / NB;
     const int t = threadIdx.x;
-    for (int e = t; e < NB * NB; e += blockDim.x) {
-        int r = e / NB, c = e % NB;
-        double v = 0.0;
-        if (r < nv && c <= r) v = As[(int64_t)(k0 + r) * n + (k0 + c)];
-        Ls[r * LDT + c] = v;
-    }
-    __syncthreads();
-    int bad = potrf_block_smem(Ls, nv, &flag);
-    if (bad) {
-        if (blockIdx.x == 0 && t == 0) info[s] = k0 + bad;
-        return;
-    }
-    if (blockIdx.x == 0) {
-        double* dst = diag_scratch + ((int64_t)s * nb + k0 / NB) * NB * NB;
+    const int tile = (MODE == 2) ? blockIdx.x + 1 : blockIdx.x;  // 0 = the diagonal tile
+    double* scratch = diag_scratch + ((int64_t)s * nb + k0 / NB) * NB * NB;
+    if (MODE == 2) {
+        // the factor was stored by the MODE 1 launch
         for (int e = t; e < NB * NB; e += blockDim.x) {
             int r = e / NB, c = e % NB;
-            dst[e] = (r < nv && c <= r) ? Ls[r * LDT + c] : 0.0;
+            double v = scratch[e];
+            if (r == c) {
+                if (r >= nv) v = 1.0;
+                rdiag[r] = 1.0 / v;
+            }
+            Ls[r * LDT + c] = v;
         }
-        return;
+        __syncthreads();
+    } else {
+        for (int e = t; e < NB * NB; e += blockDim.x) {
+            int r = e / NB, c = e % NB;
+            double v = (r == c) ? 1.0 : 0.0;  // rows beyond the matrix: identity
+            if (r < nv && c <= r) v = As[(int64_t)(k0 + r) * n + (k0 + c)];
+            Ls[r * LDT + c] = v;
+        }
+        __syncthreads();
+        int bad = potrf_block_smem(Ls, &flag, rdiag);
+        if (bad) {
+            if (tile == 0 && t == 0) info[s] = k0 + bad;
+            return;
+        }
+        if (tile == 0) {
+            for (int e = t; e < NB * NB; e += blockDim.x) {
+                int r = e / NB, c = e % NB;
+                scratch[e] = (r < nv && c <= r) ? Ls[r * LDT + c] : 0.0;
+            }
+            return;
+        }
     }
-    const int row = k0 + blockIdx.x * NB + t;
+    const int row = k0 + tile * NB + t;
     if (t < NB && row < n) {
         double x[NB];
         double* ap = As + (int64_t)row * n + k0;
@@ -101,7 +199,7 @@ __global__ void __launch_bounds__(128) potrf_panel_kernel(double* __restrict__ A
             double acc = x[j];
 #pragma unroll
             for (int k = 0; k < j; ++k) acc = fma(-x[k], Ls[j * LDT + k], acc);
-            x[j] = acc / Ls[j * LDT + j];
+            x[j] = acc * rdiag[j];
         }
 #pragma unroll
         for (int j = 0; j < NB; ++j) ap[j] = x[j];
@@ -162,8 +260,14 @@ static int potrf_launch(double* A, int n, int S, int* info, cudaStream_t cs) {
     cudaMemsetAsync(info, 0, sizeof(int) * S, cs);
     for (int k0 = 0; k0 < n; k0 += NB) {
         int tiles = (n - k0 + NB - 1) / NB;  // diagonal tile + row tiles below it
-        dim3 pg(tiles, S);
-        potrf_panel_kernel<<<pg, 128, SMEM_LS, cs>>>(A, n, k0, info, diag_scratch);
+        if ((int64_t)tiles * S <= 3 * 148 || tiles == 1) {
+            dim3 pg(tiles, S);
+            potrf_panel_kernel<0><<<pg, 128, SMEM_LS, cs>>>(A, n, k0, info, diag_scratch);
+        } else {
+            dim3 fg(1, S), sg(tiles - 1, S);
+            potrf_panel_kernel<1><<<fg, 128, SMEM_LS, cs>>>(A, n, k0, info, diag_scratch);
+            potrf_panel_kernel<2><<<sg, 128, SMEM_LS, cs>>>(A, n, k0, info, diag_scratch);
+        }
         int tr = tiles - 1;
         if (tr > 0) {
             dim3 sg(tr, tr, S);

@@ -275,9 +275,11 @@ class GPFittingGaussian(object):
                     self._hb_cache[key] = hb.appended(eng2)
 
     incremental_updates = True  # class-level switch (tests compare both paths)
+    batched_slice_probes = True  # slice sampler sends independent probes in one batched call
 
     def clean_cache(self):
         self._hb_cache = OrderedDict()
+        self._log_prob_memo = OrderedDict()
         self.best_solution = {}
 
     # -- kernel matrices ---------------------------------------------------------------------------
@@ -452,25 +454,71 @@ class GPFittingGaussian(object):
             self._kernel_priors.append((slice(dm, len(kv)), prior))
         self.length_scale_indexes = list(range(2, 2 + dm))
 
-    def log_prob_parameters(self, parameters):
-        """:1543-1567: sum of log-priors + GPU log-likelihood."""
-        parameters = np.asarray(parameters, dtype=float)
+    def _log_prior_parameters(self, parameters):
         lp = self.var_noise.log_prior(parameters[0:1]) + self.mean.log_prior(parameters[1:2])
         kp = parameters[2:]
         for sl, prior in self._kernel_priors:
             lp += prior.logprob(kp[sl])
+        return lp
+
+    def log_prob_parameters(self, parameters):
+        """:1543-1567: sum of log-priors + GPU log-likelihood.  The last few results are memoised
+        by value: the slice sampler re-evaluates its current point at the start of every
+        direction (slice_sampling.py:262-264), which is the point it has just accepted."""
+        parameters = np.ascontiguousarray(np.asarray(parameters, dtype=float))
+        key = (len(self.data['evaluations']), parameters.tobytes())
+        memo = self.__dict__.setdefault('_log_prob_memo', OrderedDict())
+        if key in memo:
+            return memo[key]
+        lp = self._log_prior_parameters(parameters)
         if not np.isinf(lp):
             try:
-                lp += self.log_likelihood(parameters[0], parameters[1], kp)
+                lp += self.log_likelihood(parameters[0], parameters[1], parameters[2:])
             except linalg.LinAlgError:
-                return -np.inf
+                lp = -np.inf
+        memo[key] = lp
+        while len(memo) > 64:
+            memo.popitem(last=False)
         return lp
+
+    def log_prob_parameters_batch(self, vectors):
+        """Batched log_prob_parameters: priors on the host, ONE batched factorisation for all
+        vectors with a finite prior.  Values are bit-identical to the
+        one-at-a-time path (every matrix is reduced by its own CTAs in a fixed order)."""
+        vectors = [np.ascontiguousarray(np.asarray(v, dtype=float)) for v in vectors]
+        memo = self.__dict__.setdefault('_log_prob_memo', OrderedDict())
+        n = len(self.data['evaluations'])
+        out = [None] * len(vectors)
+        todo = []
+        for i, v in enumerate(vectors):
+            key = (n, v.tobytes())
+            if key in memo:
+                out[i] = memo[key]
+                continue
+            lp = self._log_prior_parameters(v)
+            if np.isinf(lp):
+                out[i] = lp
+                memo[key] = lp
+            else:
+                out[i] = lp
+                todo.append(i)
+        if todo:
+            llh = self.log_likelihood_batch(np.array([vectors[i] for i in todo]))
+            for i, l in zip(todo, llh):
+                out[i] = out[i] + l if np.isfinite(l) else -np.inf
+                memo[(n, vectors[i].tobytes())] = out[i]
+        while len(memo) > 64:
+            memo.popitem(last=False)
+        return out
 
     def set_samplers(self):
         """:214-269: a random-direction slice sampler on the non-length-scale parameters and a
         component-wise one on the length scales; optional burn-in."""
         from ..samplers.hyper_slice_sampler import SliceSampling
         log_prob = lambda vector, model: model.log_prob_parameters(vector)
+        log_prob_batch = None
+        if self.batched_slice_probes:
+            log_prob_batch = lambda vectors, model: model.log_prob_parameters_batch(vectors)
         self.slice_samplers = []
         indexes = [i for i in range(self.dimension_parameters) if i not in self.length_scale_indexes]
         ignore_index = None
@@ -479,10 +527,11 @@ class GPFittingGaussian(object):
         if ignore_index is None or len(indexes) != len(ignore_index):
             self.slice_samplers.append(SliceSampling(
                 log_prob, indexes, ignore_index=ignore_index,
-                max_steps_out=self.max_steps_out, component_wise=False))
+                max_steps_out=self.max_steps_out, component_wise=False,
+                log_prob_batch=log_prob_batch))
         self.slice_samplers.append(SliceSampling(
             log_prob, self.length_scale_indexes, max_steps_out=self.max_steps_out,
-            component_wise=True))
+            component_wise=True, log_prob_batch=log_prob_batch))
         self._two_blocks = len(self.slice_samplers) == 2
         if self.start_point_sampler is not None and len(self.start_point_sampler) > 0:
             if len(self.samples_parameters) == 0:

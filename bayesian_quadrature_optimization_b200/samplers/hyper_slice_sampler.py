@@ -4,6 +4,14 @@ component-wise or random-direction moves) kept on the host -- it is a sequential
 while every `log_prob` probe is a GPU log-marginal-likelihood.  The numpy.random call order
 (interval offset, slice height, doubling coin flips, shrinkage proposals) follows the reference so
 that a seed reproduces a chain up to the 1e-11 agreement of the two likelihoods.
+
+Batched probes.  One probe costs a Cholesky factorisation whose time on the
+GPU hardly depends on how many matrices are factorised together, so when the model offers a batched
+log-probability (`log_prob_batch`) the probes whose positions are known in advance go out together:
+the two interval ends, the two ends of every halving in the acceptance test, and the next
+`speculate` shrinkage proposals -- the k-th proposal only depends on the positions (not the values) of
+the rejected ones before it.  The random-number stream is rewound after a speculative draw and
+replayed proposal by proposal, so the chain is exactly the sequential one.
 """
 import numpy as np
 import numpy.random as npr
@@ -41,6 +49,8 @@ class SliceSampling(object):
         self.max_steps_out = params.get('max_steps_out', 1000)
         self.component_wise = params.get('component_wise', True)
         self.doubling_step = params.get('doubling_step', True)
+        self.log_prob_batch = params.get('log_prob_batch')  # optional: (vectors, *args) -> values
+        self.speculate = int(params.get('speculate', 4))
 
     def slice_sample(self, point, fixed_parameters, *args_log_prob):
         point = np.asarray(point, dtype=float)
@@ -70,6 +80,19 @@ class SliceSampling(object):
             new_point = combine_vectors(new_point, fixed_parameters, self.indexes)
         return self.log_prob(new_point, *args_log_prob)
 
+    def directional_log_probs(self, xs, direction, point, fixed_parameters=None, *args_log_prob):
+        """log_prob at several positions along the direction: one batched call when available."""
+        if self.log_prob_batch is None or len(xs) == 1:
+            return [self.directional_log_prob(x, direction, point, fixed_parameters, *args_log_prob)
+                    for x in xs]
+        pts = []
+        for x in xs:
+            new_point = point + x * direction
+            if fixed_parameters is not None:
+                new_point = combine_vectors(new_point, fixed_parameters, self.indexes)
+            pts.append(new_point)
+        return list(self.log_prob_batch(pts, *args_log_prob))
+
     def acceptable(self, z, llh, L, U, direction, point, fixed_parameters, *args):
         if not self.doubling_step:
             return True
@@ -83,8 +106,7 @@ class SliceSampling(object):
             if U == old_U and L == old_L:
                 return False
             D = (middle > 0 and z >= middle) or (middle <= 0 and z < middle)
-            lp0 = self.directional_log_prob(U, direction, point, fixed_parameters, *args)
-            lp1 = self.directional_log_prob(L, direction, point, fixed_parameters, *args)
+            lp0, lp1 = self.directional_log_probs([U, L], direction, point, fixed_parameters, *args)
             if D and llh >= lp0 and llh >= lp1:
                 return False
         return True
@@ -92,8 +114,8 @@ class SliceSampling(object):
     def find_x_interval(self, llh, lower, upper, direction, point, fixed_parameters, *args):
         l_out = u_out = 0
         if self.doubling_step:
-            lp0 = self.directional_log_prob(lower, direction, point, fixed_parameters, *args)
-            lp1 = self.directional_log_prob(upper, direction, point, fixed_parameters, *args)
+            lp0, lp1 = self.directional_log_probs([lower, upper], direction, point,
+                                                  fixed_parameters, *args)
             while (lp0 > llh or lp1 > llh) and (l_out + u_out < self.max_steps_out):
                 if npr.rand() < 0.5:
                     l_out += 1
@@ -118,9 +140,30 @@ class SliceSampling(object):
 
     def find_sample(self, lower, upper, llh, direction, point, fixed_parameters, *args):
         start_upper, start_lower = upper, lower
+        ahead = []  # log-probabilities of the coming proposals, evaluated speculatively
         while True:
+            if not ahead and self.log_prob_batch is not None and self.speculate > 1:
+                # the next proposals if every one before them is rejected: their positions only
+                # depend on the positions of the rejected ones.  Draw, evaluate together, rewind.
+                state = npr.get_state()
+                zs, lo, up = [], lower, upper
+                for _ in range(self.speculate):
+                    z = (up - lo) * npr.rand() + lo
+                    zs.append(z)
+                    if z < 0:
+                        lo = z
+                    elif z > 0:
+                        up = z
+                    else:
+                        break
+                npr.set_state(state)
+                ahead = self.directional_log_probs(zs, direction, point, fixed_parameters, *args)
             new_z = (upper - lower) * npr.rand() + lower
-            new_llh = self.directional_log_prob(new_z, direction, point, fixed_parameters, *args)
+            if ahead:
+                new_llh = ahead.pop(0)
+            else:
+                new_llh = self.directional_log_prob(new_z, direction, point, fixed_parameters,
+                                                    *args)
             if np.isnan(new_llh):
                 new_llh = -np.inf
             if new_llh > llh and self.acceptable(new_z, llh, start_lower, start_upper, direction,

@@ -385,3 +385,50 @@ def test_add_points_extends_cached_factors(golden):
         pb = gp_ref.compute_posterior_parameters(q, th[0], th[1], th[2:])
         assert_close(pa["mean"], pb["mean"], rtol=1e-9, atol=1e-12)
         assert_close(pa["cov"], pb["cov"], rtol=1e-7, atol=1e-11)
+
+
+def test_batched_slice_probes_give_the_sequential_chain():
+    """speculative / paired probes evaluated in one batched factorisation
+    leave the Markov chain (and the numpy random stream) exactly as the one-probe-at-a-time
+    algorithm of the reference."""
+    from bayesian_quadrature_optimization_b200.models.gp_fitting_gaussian import GPFittingGaussian
+    from bayesian_quadrature_optimization_b200.lib import constant as K
+    rng = np.random.RandomState(5)
+    n = 40
+    pts = rng.uniform(0, 1, (n, 3))
+    y = np.sin(3 * pts.sum(1)) + 0.1 * rng.normal(0, 1, n)
+    td = {"points": pts.tolist(), "evaluations": list(y), "var_noise": []}
+
+    def make(batched):
+        GPFittingGaussian.batched_slice_probes = batched
+        try:
+            return GPFittingGaussian([K.SCALED_KERNEL, K.MATERN52_NAME], td, [3],
+                                     bounds_domain=[[0, 1]] * 3, thinning=1, n_burning=2,
+                                     max_steps_out=10, random_seed=3, noise=True)
+        finally:
+            GPFittingGaussian.batched_slice_probes = True
+
+    calls = {"batch": 0, "single": 0}
+    gp_b, gp_s = make(True), make(False)
+    assert gp_b.slice_samplers[0].log_prob_batch is not None
+    assert gp_s.slice_samplers[0].log_prob_batch is None
+    orig_batch = gp_b.log_likelihood_batch
+    orig_single = gp_s.log_likelihood
+
+    def count_batch(th):
+        calls["batch"] += 1
+        return orig_batch(th)
+
+    def count_single(*a):
+        calls["single"] += 1
+        return orig_single(*a)
+
+    gp_b.log_likelihood_batch = count_batch
+    gp_s.log_likelihood = count_single
+    sb = gp_b.sample_parameters(4, random_seed=11)
+    after_b = np.random.rand()
+    ss = gp_s.sample_parameters(4, random_seed=11)
+    after_s = np.random.rand()
+    assert_close(np.array(sb), np.array(ss), rtol=0, atol=0, what="batched vs sequential chain")
+    assert after_b == after_s  # the random stream is in the same state
+    assert calls["batch"] > 0 and calls["single"] > 0
