@@ -138,6 +138,13 @@ def _cpu_unit_worker(args):
     samples so that the per-unit fixed cost and the per-Z cost can be separated."""
     os.environ["OMP_NUM_THREADS"] = "1"
     cand_idx, hyper_idx, z_lo, z_hi = args
+    try:
+        # one BLAS/OpenMP thread per worker (the pool already uses every core); the environment
+        # variable alone does not reach libraries the parent process loaded before the fork
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=1)
+    except Exception:
+        pass
     from oracle import bqo_oracle as orc
     wl = _WL
     spec = orc.KernelSpec(orc.SCALED_MATERN52, DX + DW)
