@@ -54,6 +54,8 @@ class EI(object):
                                                    self.noisy_evaluations)
             ei, _ = hb.ei(point, np.array([best]), grad=False)
             return ei.cpu().numpy()[0]
+        # the quadrature model lives on the x coordinates; extra (task) columns are ignored
+        point = point.reshape(-1, point.shape[-1])[:, :len(self.gp.x_domain)]
         post = self.gp.compute_posterior_parameters(point, var_noise, mean, parameters_kernel)
         mu = post['mean']
         cov = np.clip(post['cov'], 0, None)
@@ -65,11 +67,43 @@ class EI(object):
                 np.sqrt(cov) * norm.pdf(normalized_factor)
         return np.atleast_1d(evaluation)
 
+    def _bq_ei_batched(self, thetas, xpts, gradient):
+        """EI of the posterior of G at xpts for every hyper-sample in `thetas` -> (ei [S][P],
+        grad [S][P][d_x] or None), device tensors.  best_s = max posterior mean of G over the x of
+        the training points (BayesianQuadrature.get_historical_best_solution, :1542-1577)."""
+        from .. import _cabi
+        quad = self.gp
+        bq = quad.engine_for(np.asarray(thetas, dtype=float))
+        eng = bq.eng
+        dx = len(quad.x_domain)
+        xpts = eng.to_device(xpts).reshape(-1, dx)
+        if gradient:
+            mean, var, gm, gv = bq.quadrature_posterior_grad(xpts)
+        else:
+            mean, var = bq.quadrature_posterior(xpts)
+            gm = gv = None
+        var = torch.clamp(var, min=0.0).contiguous()  # np.clip(cov, 0, None), ei.py:99
+        train_x = quad.gp.data['points'][:, quad.x_domain]
+        best = bq.quadrature_posterior(train_x, var=False)[0].max(dim=1).values.contiguous()
+        S, P = int(mean.shape[0]), int(mean.shape[1])
+        ei = eng.empty(S, P)
+        gei = eng.empty(S, P, dx) if gradient else None
+        _cabi.check(eng.lib.bqo_ei_batched(
+            _cabi.ptr(mean.contiguous()), _cabi.ptr(var), _cabi.ptr(gm), _cabi.ptr(gv),
+            _cabi.ptr(best), S, P, dx if gradient else 0, _cabi.ptr(ei), _cabi.ptr(gei),
+            torch.cuda.current_stream().cuda_stream), "bqo_ei_batched")
+        return ei, gei
+
     def evaluate_gradient(self, point, var_noise=None, mean=None, parameters_kernel=None):
         """:135-176 -> np.array(n)."""
         point = np.asarray(point, dtype=float).reshape(1, -1)
         if self._is_bq():
-            raise NotImplementedError("EI gradient on the quadrature model is not accelerated")
+            theta = self.gp._theta(var_noise, mean, parameters_kernel)
+            dx = len(self.gp.x_domain)
+            _, gei = self._bq_ei_batched(theta.reshape(1, -1), point[:, :dx], True)
+            g = gei.cpu().numpy()[0, 0]
+            pad = point.shape[1] - dx
+            return np.concatenate([g, np.zeros(pad)]) if pad > 0 else g
         gp = self.gp
         var_noise, mean, parameters_kernel = gp._defaults(var_noise, mean, parameters_kernel)
         hb = gp._hb1(var_noise, mean, parameters_kernel)
@@ -88,10 +122,13 @@ class EI(object):
         The reference loops BayesianEvaluations.evaluate over theta with a cold Cholesky cache."""
         gp = self._gp_model()
         if self._is_bq():
-            vals = [np.mean([self.evaluate(p.reshape(1, -1), t[0], t[1], t[2:])[0]
-                             for t in gp.samples_parameters[-n_samples_parameters:]])
-                    for p in np.asarray(points, dtype=float)]
-            return np.array(vals), None
+            thetas = np.array(gp.samples_parameters[-n_samples_parameters:])
+            dx = len(self.gp.x_domain)
+            pts_in = points if isinstance(points, torch.Tensor) else np.asarray(points, dtype=float)
+            pts_in = pts_in.reshape(-1, pts_in.shape[-1])[:, :dx]
+            ei, gei = self._bq_ei_batched(thetas, pts_in, gradient)
+            val = ei.mean(dim=0).cpu().numpy()
+            return val, (gei.mean(dim=0).cpu().numpy() if gradient else None)
         thetas = np.array(gp.samples_parameters[-n_samples_parameters:])
         hb = gp.hyper_batch(thetas)
         hb.factorize(max_tries=7)
@@ -115,12 +152,10 @@ class EI(object):
         With n_samples_parameters == 0: L-BFGS-B per start on the GPU objective.  Otherwise the
         Bayesian-averaged EI (all hyper-samples in one launch per step) is climbed from every
         start at once with the reference's Adam rule (sbo/lib/stochastic_gradient_descent.py)."""
-        if self._is_bq():
-            raise NotImplementedError("EI.optimize on the quadrature model is not accelerated")
         if random_seed is not None:
             np.random.seed(random_seed)
         gp = self.gp
-        bounds = gp.bounds
+        bounds = gp.bounds  # the quadrature model exposes the x bounds here (model_only_x)
         if start is None:
             start = np.array(DomainService.get_points_domain(
                 n_restarts, bounds, type_bounds=gp.type_bounds, simplex_domain=self.simplex_domain))
@@ -145,7 +180,7 @@ class EI(object):
         else:
             import ctypes as C
             from .. import _cabi
-            eng = gp._engine()
+            eng = self._gp_model()._engine()
             pts = eng.to_device(start.copy())
             R, dim = int(pts.shape[0]), int(pts.shape[1])
             m0, v0 = torch.zeros_like(pts), torch.zeros_like(pts)

@@ -19,7 +19,8 @@ class MultiTasks(object):
     def __init__(self, bayesian_quadrature, n_tasks):
         self.bq = bayesian_quadrature
         self.n_tasks = n_tasks
-        self.ei_tasks = EI(self.bq.gp)
+        self.ei = EI(self.bq)           # EI on G(x) = E_W F(x, W)   (multi_task.py:53)
+        self.ei_tasks = EI(self.bq.gp)  # EI on F(x, t)              (multi_task.py:54)
 
     def _thetas(self, n_samples_parameters):
         gp = self.bq.gp
@@ -49,32 +50,12 @@ class MultiTasks(object):
 
     def optimize_first(self, start=None, random_seed=None, parallel=True, n_restarts=100,
                        n_samples_parameters=0, n_best_restarts=0, maxepoch=11):
-        """:60-80 -> np.array(d_x).  The reference climbs EI(G) with SGD from the best random
-        starts; here the Bayesian-averaged EI(G) of all random starts is evaluated in one batch and
-        the best start is polished by a few rounds of batched local perturbations (derivative
-        free: EI(G) needs a triangular solve per point, its gradient is not on the hot path)."""
-        if random_seed is not None:
-            np.random.seed(random_seed)
-        bounds_x = self.bq.bounds_x()
-        if start is None:
-            start = np.array(DomainService.get_points_domain(
-                n_restarts, bounds_x, type_bounds=len(bounds_x) * [0]))
-        start = np.asarray(start, dtype=float).reshape(-1, len(bounds_x))
-        lo = np.array([b[0] for b in bounds_x], dtype=float)
-        up = np.array([b[-1] for b in bounds_x], dtype=float)
-        values = self.ei_quadrature(start, n_samples_parameters)
-        best = start[int(np.argmax(values))].copy()
-        best_v = float(np.max(values))
-        radius = 0.1 * (up - lo)
-        for _ in range(max(1, maxepoch // 2)):
-            cand = np.clip(best[None, :] + radius[None, :] * np.random.uniform(
-                -1, 1, (32, len(bounds_x))), lo, up)
-            v = self.ei_quadrature(cand, n_samples_parameters)
-            if np.max(v) > best_v:
-                best_v = float(np.max(v))
-                best = cand[int(np.argmax(v))].copy()
-            radius *= 0.5
-        return best
+        """:60-80 -> np.array(d_x): maximise EI on the posterior of G exactly as the reference
+        does, through EI(bq).optimize (all restarts advance together on the device)."""
+        solution = self.ei.optimize(start, random_seed, parallel, n_restarts,
+                                    n_best_restarts=n_best_restarts,
+                                    n_samples_parameters=n_samples_parameters, maxepoch=maxepoch)
+        return np.asarray(solution['solution'], dtype=float)[:len(self.bq.x_domain)]
 
     def choose_best_task_given_x(self, x, n_samples_parameters=0):
         """:82-95 -> (task index, Bayesian EI value): argmax over tasks of the EI of F at (x, t)

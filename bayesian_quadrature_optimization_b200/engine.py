@@ -324,6 +324,42 @@ class BQEngine(object):
         KP = hb.cross_cov(pts.contiguous())                          # [S][P*M][n]
         return KP.reshape(hb.S, P, M, eng.n).mean(dim=2)
 
+    def quadrature_rows_grad(self, xpts, w_set=0):
+        """(B, grad_x B): [S][P][n] and [S][P][d_x][n]
+        (evaluate_grad_quadrature_cross_cov, bayesian_quadrature.py:336-362)."""
+        eng, hb, d = self.eng, self.hb, self.eng.desc
+        xpts = eng.to_device(xpts).reshape(-1, self.dx)
+        P = int(xpts.shape[0])
+        if self.is_product:
+            pts = torch.cat([xpts, torch.zeros(P, 1, dtype=F64, device=eng.device)], dim=1)
+            KP, dKP = hb.cross_cov(pts, grad=True)                   # both carry C[0][task_j]
+            T = d.n_tasks
+            C = hb.hyp[:, _cabi_taskc_offset():_cabi_taskc_offset() + T * T].reshape(hb.S, T, T)
+            tid = hb.tid.long()
+            f = (self.qt[:, tid] / C[:, 0, :][:, tid])               # [S][n]
+            return KP * f.unsqueeze(1), dKP[:, :, :self.dx, :] * f.unsqueeze(1).unsqueeze(2)
+        ws = self.wsets[w_set]
+        M = int(ws.shape[0])
+        pts = torch.cat([xpts.unsqueeze(1).expand(P, M, self.dx),
+                         ws.unsqueeze(0).expand(P, M, self.dw)], dim=2).reshape(P * M, d.dim)
+        KP, dKP = hb.cross_cov(pts.contiguous(), grad=True)
+        B = KP.reshape(hb.S, P, M, eng.n).mean(dim=2)
+        dB = dKP.reshape(hb.S, P, M, d.dim_m, eng.n)[:, :, :, :self.dx, :].mean(dim=2)
+        return B, dB
+
+    def quadrature_posterior_grad(self, xpts, w_set=0):
+        """mean [S][P], var [S][P], grad mean [S][P][d_x], grad var [S][P][d_x] of the posterior
+        of G (gradient_posterior_parameters, bayesian_quadrature.py:581-643: the prior term
+        E_W E_W' k is constant in x for these radial kernels)."""
+        hb = self.hb
+        B, dB = self.quadrature_rows_grad(xpts, w_set)
+        mean = hb.theta[:, 1:2] + (B * hb.alpha.unsqueeze(1)).sum(dim=2)
+        sol = hb.solve(B.clone().contiguous())
+        var = self.quadrature_prior_var(xpts, w_set) - (B * sol).sum(dim=2)
+        gmean = (dB * hb.alpha.unsqueeze(1).unsqueeze(2)).sum(dim=3)
+        gvar = -2.0 * (dB * sol.unsqueeze(2)).sum(dim=3)
+        return mean, var, gmean.contiguous(), gvar.contiguous()
+
     def quadrature_prior_var(self, xpts, w_set=0):
         """E_W E_W' k((x,W),(x,W')) for every hyper-sample: [S][P]
         (evaluate_quadrate_cov, bayesian_quadrature.py:282-306; exact double sum for finite W,

@@ -235,6 +235,15 @@ class BayesianQuadrature(object):
                            np.full(1, w_set, dtype=np.int32) if self.w_sets is not None else None)
         return out[0, 2:2 + dx].cpu().numpy()
 
+    def gradient_posterior_parameters(self, point, var_noise=None, mean=None,
+                                      parameters_kernel=None, cache=True, parallel=True, w_set=0):
+        """:581-643 -> {'mean': np.array(d_x), 'cov': np.array(d_x)}."""
+        theta = self._theta(var_noise, mean, parameters_kernel)
+        bq = self.engine_for(theta)
+        point = np.asarray(point, dtype=float).reshape(1, len(self.x_domain))
+        _, _, gm, gv = bq.quadrature_posterior_grad(point, w_set)
+        return {'mean': gm[0, 0].cpu().numpy(), 'cov': gv[0, 0].cpu().numpy()}
+
     def objective_posterior_mean(self, point, var_noise=None, mean=None, parameters_kernel=None):
         point = np.asarray(point, dtype=float).reshape((1, -1))
         return self.compute_posterior_parameters(point, var_noise=var_noise, mean=mean,

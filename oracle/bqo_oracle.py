@@ -510,6 +510,18 @@ class OracleBQ(object):
         _, solve = self.gp.chol_solve(var_noise, mean, params)
         return np.dot(gradient, solve)
 
+    def gradient_posterior_parameters(self, point, var_noise, mean, params, w=None):
+        """{'mean': grad mu_G, 'cov': grad var_G}: bayesian_quadrature.py:581-643 (the prior term
+        E E k is taken as constant in x, as the reference does)."""
+        point = np.asarray(point, dtype=float).reshape(1, -1)
+        gradient = self.evaluate_grad_quadrature_cross_cov(point, self.gp.points, params, w=w)
+        chol, solve = self.gp.chol_solve(var_noise, mean, params)
+        vec_covs = self.evaluate_quadrature_cross_cov(point, self.gp.points, params, w=w)
+        grad_mu = np.dot(gradient, solve)
+        solve_3 = cho_solve(chol, gradient.transpose())
+        grad_cov = -2.0 * np.dot(vec_covs.reshape(1, -1), solve_3)
+        return {"mean": grad_mu, "cov": grad_cov.reshape(-1)}
+
     def get_parameters_for_samples(self, candidate_point, var_noise, mean, params):
         """:1074-1145."""
         chol, solve = self.gp.chol_solve(var_noise, mean, params)

