@@ -34,6 +34,26 @@ def _c3(n=2048, S=2, seed=0):
     return pts, y, thetas
 
 
+def _check_maximiser_properties(bq, ub, zs, starts, lo, up, n_units):
+    """Size-independent properties of the inner maximiser: its value is reproduced by a + Z b at
+    the returned argument, the argument is in the box, and no start point or box vertex beats it."""
+    dx = len(lo)
+    out_max, out_arg, _ = bq.inner_maximize(ub, zs, starts, count_evals=True)
+    out_max, out_arg = out_max.cpu().numpy(), out_arg.cpu().numpy()
+    assert np.all(out_arg >= lo - 1e-15) and np.all(out_arg <= up + 1e-15)
+    verts = np.array([[up[l] if (v >> (dx - 1 - l)) & 1 else lo[l] for l in range(dx)]
+                      for v in range(1 << dx)], float)
+    probe = np.concatenate([starts, verts], 0)
+    for u in range(n_units):
+        ab = bq.sample_ab(ub, probe, np.full(len(probe), u, dtype=np.int32)).cpu().numpy()
+        at = bq.sample_ab(ub, out_arg[u], np.full(len(zs), u, dtype=np.int32)).cpu().numpy()
+        for i, z in enumerate(zs):
+            assert_close(at[i, 0] + z * at[i, 1], out_max[u, i], rtol=1e-11, atol=1e-12,
+                         what="value at argmax")
+            assert out_max[u, i] >= np.max(ab[:, 0] + z * ab[:, 1]) - 1e-12
+    return out_max, out_arg
+
+
 def test_c3_stage_b_c_against_oracle_at_n2048():
     """North-star shape: Scaled(Matern52), d = 4 + 2, n = 2048, gamma W with 10 samples."""
     from bayesian_quadrature_optimization_b200 import engine as E, _cabi
@@ -183,6 +203,9 @@ def test_c4_shape_product_100_tasks_n4096():
                                         for t in range(T)]) for th in thetas])
     assert_close(ei, want_ei, rtol=1e-7, atol=1e-14, what="EI over tasks")
     assert int(np.argmax(ei.mean(0))) == int(np.argmax(want_ei.mean(0)))
+    # inner maximiser at n = 4096 (operands staged in 212 KB of shared memory)
+    _check_maximiser_properties(bq, ub, np.array([-0.7, 1.1]), rng.uniform(0, 10, (2, dx)), lo, up,
+                                2 * S)
 
 
 def test_c5_shape_cholesky_loglik_gradient_n8192():
@@ -205,7 +228,24 @@ def test_c5_shape_cholesky_loglik_gradient_n8192():
     assert_close(hb.log_likelihood().cpu().numpy()[0], ogp.log_likelihood(th[0], th[1], th[2:]),
                  rtol=1e-9, what="llh n=8192")
     grad = hb.grad_log_likelihood().cpu().numpy()[0]
-    del hb, Sigma, rec
+    # stage C at n = 8192: the training set no longer fits shared memory, the maximiser streams
+    # its operands from L2 (un-staged instantiation of the same kernel)
+    dx = 4
+    lo, up = np.zeros(dx), np.ones(dx)
+    wset = np.random.RandomState(4).gamma(2.0, 1.0, (10, 2))
+    bq = E.BQEngine(hb, dx, wsets=wset, lower=lo, upper=up)
+    r5 = np.random.RandomState(5)
+    cand = np.concatenate([r5.uniform(0, 1, (1, 4)), r5.gamma(2.0, 1.0, (1, 2))], 1)
+    ub = bq.setup(cand)
+    _, out_arg = _check_maximiser_properties(bq, ub, np.array([-1.0, 0.8]),
+                                             np.random.RandomState(6).uniform(0, 1, (2, dx)),
+                                             lo, up, 1)
+    obq = orc.OracleBQ(ogp, list(range(dx)), orc.GAMMA)
+    v = obq.compute_parameters_for_sample(out_arg[0, 1], cand, th[0], th[1], th[2:], w=wset)
+    got = bq.sample_ab(ub, out_arg[0, 1:2], np.zeros(1, dtype=np.int32)).cpu().numpy()[0]
+    assert_close(got[0:2], [v["a"][0], np.asarray(v["b"]).reshape(-1)[0]], rtol=1e-6, atol=1e-8,
+                 what="a, b at n=8192 against the oracle")
+    del hb, Sigma, rec, bq, ub
     # central differences in three coordinates: noise, one length scale, sigma2
     for j, h in [(0, 1e-7), (3, 1e-5), (8, 1e-5)]:
         tp, tm = th.copy(), th.copy()
