@@ -67,3 +67,30 @@ def allgather_ordered_sum(partial: torch.Tensor):
     for r in range(1, ws):
         total += bufs[r]
     return total
+
+
+def evaluate_candidates_hyper_sharded(make_bq, thetas, cands, z, starts, max_mean=None, **kwargs):
+    """Hyper-samples across ranks (the partition that bounds memory, one n x n factor
+    per hyper-sample): rank r factorises and scores only its slice of `thetas`; the per-candidate
+    sums over hyper-samples are combined with ONE all_gather and a rank-ordered sum, so every rank
+    holds bit-identical totals and the argmax over candidates agrees everywhere.
+
+    :param make_bq: callable(thetas_slice) -> BQEngine for those hyper-samples on this rank's GPU
+    :return: {'evaluations': tensor[C], 'gradient': tensor[C][dim_m] or None, 'argmax': int}
+    """
+    rank, ws = world()
+    thetas = np.asarray(thetas, dtype=float)
+    S = thetas.shape[0]
+    lo, hi = shard_range(S, rank, ws)
+    if hi > lo:
+        bq = make_bq(thetas[lo:hi])
+        mm = None if max_mean is None else np.asarray(max_mean, dtype=float)[lo:hi]
+        res = bq.evaluate_candidates(cands, z, starts, max_mean=mm, **kwargs)
+        part_v = res['evaluations'] * float(hi - lo)
+        part_g = None if res.get('gradient') is None else res['gradient'] * float(hi - lo)
+        dev = part_v.device
+    else:  # more ranks than hyper-samples: this rank contributes zeros
+        raise ValueError("hyper-sample sharding needs at least one hyper-sample per rank")
+    tot_v = allgather_ordered_sum(part_v) / float(S)
+    tot_g = None if part_g is None else allgather_ordered_sum(part_g) / float(S)
+    return {'evaluations': tot_v, 'gradient': tot_g, 'argmax': int(torch.argmax(tot_v).item())}
