@@ -206,8 +206,11 @@ __global__ void __launch_bounds__(128) potrf_panel_kernel(double* __restrict__ A
     }
 }
 
-// Trailing update: A[i][j] -= sum_k L[i][k0+k] L[j][k0+k] for i, j >= k0 + NB, lower tiles only.
-__global__ void __launch_bounds__(128) potrf_syrk_kernel(double* __restrict__ A, int n, int k0,
+// Trailing update A[i][j] -= sum_{k < K} L[i][kc+k] L[j][kc+k] on the lower tiles of the square
+// that starts at row/column `base`; only the first `ncolblk` block columns of it are touched
+// (1 = the strip that the second panel of a 128-wide step needs, all = the full update).
+__global__ void __launch_bounds__(128) potrf_syrk_kernel(double* __restrict__ A, int n, int kc, int K,
+                                                         int base, int ncolblk,
                                                          const int* __restrict__ info) {
     extern __shared__ double dyn_smem[];
     double* Asm = dyn_smem;
@@ -215,16 +218,15 @@ __global__ void __launch_bounds__(128) potrf_syrk_kernel(double* __restrict__ A,
     const int s = blockIdx.z;
     if (info[s] != 0) return;
     const int bi = blockIdx.y, bj = blockIdx.x;
-    if (bj > bi) return;
+    if (bj > bi || bj >= ncolblk) return;
     double* As = A + (int64_t)s * n * n;
-    const int base = k0 + NB;
     const int i0 = base + bi * NB, j0 = base + bj * NB;
     const int ri = (n - i0 < NB) ? n - i0 : NB;
     const int rj = (n - j0 < NB) ? n - j0 : NB;
     BqoAcc acc;
     acc.zero();
-    bqo_gemm_tile<true, true>(acc, As + (int64_t)i0 * n + k0, n, ri, As + (int64_t)j0 * n + k0, n,
-                              rj, NB, Asm, Bsm);
+    bqo_gemm_tile<true, true>(acc, As + (int64_t)i0 * n + kc, n, ri, As + (int64_t)j0 * n + kc, n,
+                              rj, K, Asm, Bsm);
     bqo_acc_foreach(acc, [&](int r, int c, double& v) {
         if (r < ri && c < rj) As[(int64_t)(i0 + r) * n + (j0 + c)] -= v;
     });
@@ -252,14 +254,17 @@ __global__ void potrf_finish_kernel(double* __restrict__ A, int n, const int* __
 #define SMEM_SYRK ((size_t)(2 * BQO_OPER_TILE_DOUBLES) * sizeof(double))
 #define SMEM_TRSM ((size_t)(2 * BQO_OPER_TILE_DOUBLES + 2 * NB * LDT) * sizeof(double))
 
+#ifndef POTRF_W
+#define POTRF_W 4
+#endif
 static int potrf_launch(double* A, int n, int S, int* info, cudaStream_t cs) {
     const int nb = (n + NB - 1) / NB;
     double* diag_scratch = nullptr;
     cudaError_t e = cudaMallocAsync((void**)&diag_scratch, sizeof(double) * (size_t)S * nb * NB * NB, cs);
     if (e != cudaSuccess) return (int)e;
     cudaMemsetAsync(info, 0, sizeof(int) * S, cs);
-    for (int k0 = 0; k0 < n; k0 += NB) {
-        int tiles = (n - k0 + NB - 1) / NB;  // diagonal tile + row tiles below it
+    auto panel = [&](int k0) {
+        const int tiles = (n - k0 + NB - 1) / NB;  // diagonal tile + row tiles below it
         if ((int64_t)tiles * S <= 3 * 148 || tiles == 1) {
             dim3 pg(tiles, S);
             potrf_panel_kernel<0><<<pg, 128, SMEM_LS, cs>>>(A, n, k0, info, diag_scratch);
@@ -268,11 +273,26 @@ static int potrf_launch(double* A, int n, int S, int* info, cudaStream_t cs) {
             potrf_panel_kernel<1><<<fg, 128, SMEM_LS, cs>>>(A, n, k0, info, diag_scratch);
             potrf_panel_kernel<2><<<sg, 128, SMEM_LS, cs>>>(A, n, k0, info, diag_scratch);
         }
-        int tr = tiles - 1;
-        if (tr > 0) {
-            dim3 sg(tr, tr, S);
-            potrf_syrk_kernel<<<sg, 128, SMEM_SYRK, cs>>>(A, n, k0, info);
+    };
+    auto syrk = [&](int kc, int K, int base, int ncolblk) {
+        const int tr = (n - base + NB - 1) / NB;
+        if (tr <= 0) return;
+        dim3 sg(ncolblk < tr ? ncolblk : tr, tr, S);
+        potrf_syrk_kernel<<<sg, 128, SMEM_SYRK, cs>>>(A, n, kc, K, base, ncolblk, info);
+    };
+    // POTRF_W 64-wide panels per step.  Panel p of a step first receives, as a one-block-column
+    // strip, the update of the p panels before it (K = 64 p); the full trailing update then runs
+    // once per step with K = 64 POTRF_W: 1/POTRF_W of the passes over the trailing matrix and
+    // POTRF_W times the work per operand tile (K = 64 updates ran at 12 TFLOP/s).
+    for (int k0 = 0; k0 < n; k0 += POTRF_W * NB) {
+        for (int p = 0; p < POTRF_W; ++p) {
+            const int kp = k0 + p * NB;
+            if (kp >= n) break;
+            if (p > 0) syrk(k0, p * NB, kp, 1);
+            panel(kp);
         }
+        const int kend = k0 + POTRF_W * NB;
+        if (kend < n) syrk(k0, POTRF_W * NB, kend, 1 << 30);
     }
     dim3 zg((n + 255) / 256, n, S);
     potrf_finish_kernel<<<zg, 256, 0, cs>>>(A, n, info, diag_scratch);
@@ -640,8 +660,8 @@ __global__ void __launch_bounds__(128) tri_inv_level_kernel(const double* __rest
 
 // Inv = W^T W with W = L^-1 row-major lower triangular:
 // Inv[a][b] = sum_{i >= max(a,b)} W[i][a] W[i][b].  Lower tiles only, K range starts at the
-// tile's first row (W vanishes above it; the diagonal blocks carry explicit zeros); each tile
-// is also stored transposed so that Inv comes out full and symmetric.
+// tile's first row (W vanishes above it; the diagonal blocks carry explicit zeros).  The strict
+// upper tiles of Inv are NOT written.
 __global__ void __launch_bounds__(128) inv_syrk_kernel(const double* __restrict__ W, int n,
                                                        double* __restrict__ Inv) {
     extern __shared__ double dyn_smem[];
@@ -659,11 +679,10 @@ __global__ void __launch_bounds__(128) inv_syrk_kernel(const double* __restrict_
     acc.zero();
     bqo_gemm_tile<false, false>(acc, Wm + (int64_t)a0 * n + a0, n, ra, Wm + (int64_t)a0 * n + b0, n,
                                 rb, n - a0, Asm, Bsm);
+    // only the lower tiles are stored (the diagonal tiles are complete squares): the one consumer,
+    // the gradient contraction, visits exactly those
     bqo_acc_foreach(acc, [&](int r, int c, double& v) {
-        if (r < ra && c < rb) {
-            Iv[(int64_t)(a0 + r) * n + (b0 + c)] = v;
-            Iv[(int64_t)(b0 + c) * n + (a0 + r)] = v;
-        }
+        if (r < ra && c < rb) Iv[(int64_t)(a0 + r) * n + (b0 + c)] = v;
     });
 }
 

@@ -42,6 +42,8 @@ __global__ void __launch_bounds__(256)
     const bool general_tasks = (d.kind == BQO_KIND_PRODUCT_TASKS) && !d.same_corr;
     // M and every dK_j are symmetric: only tiles on or below the diagonal are visited, the
     // strictly lower ones with weight 2 (the task-pair sums are used symmetrised downstream).
+    // Inv is only defined on those tiles (bqo_internal_inverse_from_chol stores 64x64 lower
+    // tiles; a 32x32 tile on or below the diagonal always lies inside one of them).
     const double wsym = (blockIdx.x < blockIdx.y) ? 2.0 : 1.0;
     if (j < n && blockIdx.x <= blockIdx.y) {
         double xj[BQO_MAX_DIM];
