@@ -415,7 +415,8 @@ __global__ void __launch_bounds__(128) trsm_kernel(const double* __restrict__ L,
 
 template <bool FORWARD>
 __global__ void __launch_bounds__(TRSV_THREADS) trsv_kernel(const double* __restrict__ L, int n,
-                                                            double* __restrict__ Bt, int m) {
+                                                            double* __restrict__ Bt, int m, int r0,
+                                                            int r1) {
     extern __shared__ double dyn_smem[];
     double* xs = dyn_smem;                         // [nb * NB] the vector (zero padded)
     const int nb = (n + NB - 1) / NB;
@@ -425,12 +426,17 @@ __global__ void __launch_bounds__(TRSV_THREADS) trsv_kernel(const double* __rest
     const double* Lm = L + (int64_t)s * n * n;
     double* b = Bt + ((int64_t)s * m + blockIdx.x) * n;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    for (int i = t; i < nb * NB; i += TRSV_THREADS) xs[i] = (i < n) ? b[i] : 0.0;
+    // rows [r0, r1) of the system (r0 a multiple of 64): everything outside was already
+    // eliminated by the caller (trsv_gemv_*), see potrs_launch
+    const int kb0 = r0 / NB, kb1 = (r1 + NB - 1) / NB;
+    for (int i = r0 + t; i < kb1 * NB; i += TRSV_THREADS) xs[i] = (i < r1) ? b[i] : 0.0;
     __syncthreads();
-    for (int kb = FORWARD ? 0 : nb - 1; FORWARD ? (kb < nb) : (kb >= 0); kb += FORWARD ? 1 : -1) {
+    for (int kb = FORWARD ? kb0 : kb1 - 1; FORWARD ? (kb < kb1) : (kb >= kb0);
+         kb += FORWARD ? 1 : -1) {
         const int k0 = kb * NB;
         const int kv = (n - k0 < NB) ? n - k0 : NB;
         // diagonal block (and the reciprocals of its diagonal) into shared memory
+#pragma unroll
         for (int e = t; e < NB * NB; e += TRSV_THREADS) {
             int r = e / NB, c = e % NB;
             double v = 0.0;
@@ -438,7 +444,7 @@ __global__ void __launch_bounds__(TRSV_THREADS) trsv_kernel(const double* __rest
             Ls[r * LDT + c] = v;
             if (r == c) rd[r] = (r < kv) ? 1.0 / v : 1.0;
         }
-        if (FORWARD && k0 > 0) {
+        if (FORWARD && k0 > r0) {
             // rows k0 + warp*TRSV_ROWS + q: acc_q = sum_{c < k0} L[row][c] y[c]
             double acc[TRSV_ROWS];
 #pragma unroll
@@ -453,7 +459,7 @@ __global__ void __launch_bounds__(TRSV_THREADS) trsv_kernel(const double* __rest
                 lrow[q] = Lm + (int64_t)row * n;
             }
 #pragma unroll 4
-            for (int c = lane; c < k0; c += 64) {
+            for (int c = r0 + lane; c < k0; c += 64) {
                 const double x0 = xs[c], x1 = xs[c + 32];
 #pragma unroll
                 for (int q = 0; q < TRSV_ROWS; ++q) {
@@ -498,9 +504,9 @@ __global__ void __launch_bounds__(TRSV_THREADS) trsv_kernel(const double* __rest
             xs[k0 + lane + 32] = v1;
         }
         __syncthreads();
-        if (!FORWARD && k0 > 0) {
-            // y[c] -= sum_j L[k0 + j][c] x[k0 + j] for every column c < k0
-            for (int c = t; c < k0; c += TRSV_THREADS) {
+        if (!FORWARD && k0 > r0) {
+            // y[c] -= sum_j L[k0 + j][c] x[k0 + j] for every column r0 <= c < k0
+            for (int c = r0 + t; c < k0; c += TRSV_THREADS) {
                 double a0 = 0.0, a1 = 0.0;
                 const double* lc = Lm + (int64_t)k0 * n + c;
                 int j = 0;
@@ -515,7 +521,77 @@ __global__ void __launch_bounds__(TRSV_THREADS) trsv_kernel(const double* __rest
             __syncthreads();
         }
     }
-    for (int i = t; i < n; i += TRSV_THREADS) b[i] = xs[i];
+    for (int i = r0 + t; i < r1; i += TRSV_THREADS) b[i] = xs[i];
+}
+
+// Elimination of a solved block from the rest of the vector, spread over many CTAs (a single CTA
+// per vector streams L at the bandwidth of one SM):
+//   forward : b[r] -= sum_{c in [c0, c1)} L[r][c] y[c]   for r >= c1   (warp per 8 rows)
+//   backward: y[c] -= sum_{j in [r0, r1)} L[j][c] x[j]   for c <  r0   (thread per column)
+#define TRSV_BLK 256
+__global__ void __launch_bounds__(256) trsv_gemv_fwd_kernel(const double* __restrict__ L, int n,
+                                                            double* __restrict__ Bt, int m, int c0,
+                                                            int c1) {
+    __shared__ double xb[TRSV_BLK];
+    const int s = blockIdx.z, v = blockIdx.y;
+    const double* Lm = L + (int64_t)s * n * n;
+    double* b = Bt + ((int64_t)s * m + v) * n;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int i = t; i < TRSV_BLK; i += 256) xb[i] = (c0 + i < c1) ? b[c0 + i] : 0.0;
+    __syncthreads();
+    const int rbase = c1 + blockIdx.x * 64 + warp * 8;
+    double acc[8];
+    const double* lrow[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        acc[q] = 0.0;
+        const int row = (rbase + q < n) ? rbase + q : n - 1;
+        lrow[q] = Lm + (int64_t)row * n + c0;
+    }
+    const int w = c1 - c0;  // multiple of 64 (c1 < n here)
+    for (int c = lane; c < w; c += 32) {
+        const double x = xb[c];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = fma(lrow[q][c], x, acc[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const double a = bqo_warp_sum(acc[q]);
+        if (lane == 0 && rbase + q < n) b[rbase + q] -= a;
+    }
+}
+
+__global__ void __launch_bounds__(256) trsv_gemv_bwd_kernel(const double* __restrict__ L, int n,
+                                                            double* __restrict__ Bt, int m, int r0,
+                                                            int r1) {
+    // CTA = 64 columns x 4 row groups (64 rows of the block each); partial sums meet in shared memory
+    __shared__ double xb[TRSV_BLK];
+    __shared__ double part[4][64];
+    const int s = blockIdx.z, v = blockIdx.y;
+    const double* Lm = L + (int64_t)s * n * n;
+    double* b = Bt + ((int64_t)s * m + v) * n;
+    const int t = threadIdx.x, tx = t & 63, ty = t >> 6;
+    for (int i = t; i < TRSV_BLK; i += 256) xb[i] = (r0 + i < r1) ? b[r0 + i] : 0.0;
+    __syncthreads();
+    const int c = blockIdx.x * 64 + tx;
+    const int h = r1 - r0;
+    const int j0 = ty * 64, j1 = (j0 + 64 < h) ? j0 + 64 : h;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    if (c < r0) {
+        const double* lc = Lm + (int64_t)r0 * n + c;
+        int j = j0;
+#pragma unroll 4
+        for (; j + 3 < j1; j += 4) {
+            a0 = fma(lc[(int64_t)j * n], xb[j], a0);
+            a1 = fma(lc[(int64_t)(j + 1) * n], xb[j + 1], a1);
+            a2 = fma(lc[(int64_t)(j + 2) * n], xb[j + 2], a2);
+            a3 = fma(lc[(int64_t)(j + 3) * n], xb[j + 3], a3);
+        }
+        for (; j < j1; ++j) a0 = fma(lc[(int64_t)j * n], xb[j], a0);
+    }
+    part[ty][tx] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (ty == 0 && c < r0) b[c] -= (part[0][tx] + part[1][tx]) + (part[2][tx] + part[3][tx]);
 }
 
 // The vector path reads L once per right-hand side (n^2 x 8 bytes per direction), the tile path
@@ -534,8 +610,26 @@ static int potrs_launch(const double* L, int n, int S, double* Bt, int m, int id
         cudaFuncSetAttribute(trsv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
         cudaFuncSetAttribute(trsv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
         dim3 grid(m, S);
-        trsv_kernel<true><<<grid, TRSV_THREADS, sb, cs>>>(L, n, Bt, m);
-        if (!forward_only) trsv_kernel<false><<<grid, TRSV_THREADS, sb, cs>>>(L, n, Bt, m);
+        // blocks of TRSV_BLK rows: one CTA per vector solves the block, then the block is
+        // eliminated from the remaining rows by (rows / 64) x m x S CTAs
+        for (int r0 = 0; r0 < n; r0 += TRSV_BLK) {
+            const int r1 = (r0 + TRSV_BLK < n) ? r0 + TRSV_BLK : n;
+            trsv_kernel<true><<<grid, TRSV_THREADS, sb, cs>>>(L, n, Bt, m, r0, r1);
+            if (r1 < n) {
+                dim3 gg((n - r1 + 63) / 64, m, S);
+                trsv_gemv_fwd_kernel<<<gg, 256, 0, cs>>>(L, n, Bt, m, r0, r1);
+            }
+        }
+        if (forward_only) return (int)cudaGetLastError();
+        const int last = ((n - 1) / TRSV_BLK) * TRSV_BLK;
+        for (int r0 = last; r0 >= 0; r0 -= TRSV_BLK) {
+            const int r1 = (r0 + TRSV_BLK < n) ? r0 + TRSV_BLK : n;
+            trsv_kernel<false><<<grid, TRSV_THREADS, sb, cs>>>(L, n, Bt, m, r0, r1);
+            if (r0 > 0) {
+                dim3 gg((r0 + 63) / 64, m, S);
+                trsv_gemv_bwd_kernel<<<gg, 256, 0, cs>>>(L, n, Bt, m, r0, r1);
+            }
+        }
         return (int)cudaGetLastError();
     }
     static bool attr_done = false;
