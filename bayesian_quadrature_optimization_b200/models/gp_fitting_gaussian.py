@@ -8,6 +8,7 @@ slice-sampled hyper-samples in one launch) the acquisition functions use.
 """
 from __future__ import annotations
 
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -119,6 +120,7 @@ class GPFittingGaussian(object):
         self._eng = None
         self._hb_cache = OrderedDict()
         self._hb_cache_size = 64
+        self._hb_cache_bytes = int(float(os.environ.get("BQO_FACTOR_CACHE_GB", "24")) * 2 ** 30)
         self.best_solution = {}
 
         # model values (reference: set_parameters_kernel, :355-422).  When the data carries
@@ -224,7 +226,16 @@ class GPFittingGaussian(object):
         if hb is None:
             hb = self._engine().hypers(thetas)
             self._hb_cache[key] = hb
-            while len(self._hb_cache) > self._hb_cache_size:
+            # least-recently-used eviction by entry count and by device bytes: a factorised batch
+            # holds S n^2 doubles (plus scaled points), 10 GB for 20 hyper-samples at n = 8192
+            n = self._engine().n
+
+            def nbytes(h):
+                return 8 * h.S * n * (n if h.L is not None else 0) + 8 * h.S * n * (self._dim + 2)
+
+            while len(self._hb_cache) > 1 and (
+                    len(self._hb_cache) > self._hb_cache_size or
+                    sum(nbytes(h) for h in self._hb_cache.values()) > self._hb_cache_bytes):
                 self._hb_cache.popitem(last=False)
         else:
             self._hb_cache.move_to_end(key)
