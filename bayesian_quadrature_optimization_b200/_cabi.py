@@ -55,6 +55,7 @@ class StageC(C.Structure):
         ("wsets", C.c_void_p),
         ("lower", C.c_void_p),
         ("upper", C.c_void_p),
+        ("wdist", C.c_void_p),
     ]
 
 
@@ -114,6 +115,7 @@ SIGNATURES = {
         [_KD, _P, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     ),
     "bqo_weight_alpha": (C.c_int, [_KD, _P, _P, _P, _I, _I, _P, _P]),
+    "bqo_wdist_precompute": (C.c_int, [_KD, _P, _I, _P, _I, _I, _I, _P, _I, _I, _P, _P]),
     "bqo_sample_ab_batched": (C.c_int, [_SC, _P, _P, _P, _I, _P, _P]),
     "bqo_inner_maximize_batched": (C.c_int, [_SC, _IO, _P, _P, _P, _P, _P, _P]),
     "bqo_grad_vector_b_batched": (C.c_int, [_SC, _P, _I, _P, _P, _P, _P]),

@@ -240,10 +240,15 @@ __device__ __forceinline__ EvalPtrs eval_ptrs_from(const UnitCtx<DX, DW>& u) {
 // w_j = wa_j - (Z/den) wb_j (`zd` = Z/den): half the accumulators, half the per-point FMAs and
 // ten registers less in the line-search evaluations of the inner maximiser.  F is returned in
 // o.a and grad F in o.ga (o.b = o.gb = 0).
-template <int DX, int DW, bool PRE, int MT = 0, bool CMB = false>
+// WD = true takes the W part of every squared distance, sum_l (K w_ml/ls_l - K X_jl/ls_l)^2, from
+// the table `wd` built once per (hyper-sample, W set) by bqo_wdist_precompute: it does not depend
+// on x, so the 60 evaluations per (unit, Z) need not recompute it.  `wd` points at this lane's
+// column of the unit's table, laid out [j / 32][m][32] (coalesced, W-sample offsets immediate).
+template <int DX, int DW, bool PRE, int MT = 0, bool CMB = false, bool WD = false>
 __device__ __forceinline__ void eval_ab_warp(const EvalPtrs& p, const UnitCtx<DX, DW>& u,
                                              const double* x, const double* __restrict__ ws,
-                                             AbOut<DX>& o, double zd = 0.0) {
+                                             AbOut<DX>& o, double zd = 0.0,
+                                             const double* __restrict__ wd = nullptr) {
     const int lane = threadIdx.x & 31;
     double xsc[DX];
 #pragma unroll
@@ -263,7 +268,39 @@ __device__ __forceinline__ void eval_ab_warp(const EvalPtrs& p, const UnitCtx<DX
             Dx = fma(dxl[l], dxl[l], Dx);
         }
         double E0 = 0.0, E1 = 0.0, H = 0.0;  // sum e, sum u e, sum u2 e over the W samples
-        if (DW > 0) {
+        if (DW > 0 && WD) {
+            const double* wj = wd + (size_t)(j >> 5) * (M * 32);
+            auto step_nv = [&](int m) {
+                double q2v[EVAL_NV], ev[EVAL_NV], t1v[EVAL_NV];
+#pragma unroll
+                for (int q = 0; q < EVAL_NV; ++q) q2v[q] = Dx + __ldg(wj + (m + q) * 32);
+                bqo_matern52_q_v<EVAL_NV>(q2v, SmemExpTab(), ev, t1v);
+#pragma unroll
+                for (int q = 0; q < EVAL_NV; ++q) {
+                    E0 += ev[q];
+                    E1 = fma(t1v[q], ev[q], E1);
+                    H = fma(q2v[q], ev[q], H);
+                }
+            };
+            auto step_1 = [&](int m) {
+                double q2v[1], ev[1], t1v[1];
+                q2v[0] = Dx + __ldg(wj + m * 32);
+                bqo_matern52_q_v<1>(q2v, SmemExpTab(), ev, t1v);
+                E0 += ev[0];
+                E1 = fma(t1v[0], ev[0], E1);
+                H = fma(q2v[0], ev[0], H);
+            };
+            if (MT > 0) {
+#pragma unroll
+                for (int m = 0; m + EVAL_NV <= MT; m += EVAL_NV) step_nv(m);
+#pragma unroll
+                for (int m = MT - (MT % EVAL_NV); m < MT; ++m) step_1(m);
+            } else {
+                int m = 0;
+                for (; m + EVAL_NV <= M; m += EVAL_NV) step_nv(m);
+                for (; m < M; ++m) step_1(m);
+            }
+        } else if (DW > 0) {
             double xw[DW > 0 ? DW : 1];
 #pragma unroll
             for (int l = 0; l < DW; ++l) {
@@ -526,16 +563,70 @@ extern "C" int bqo_sample_ab_batched(const bqo_stage_c* pb, const double* pts,
 }
 
 // ---------------------------------------------------------------------------------------------
+// W-distance table: out[s][ws][j / 32][m][j % 32] = sum_l (K w_ml / ls_l - K X_jl / ls_l)^2 over the
+// w coordinates, in the units of the fast evaluation (K = BQO_PRESCALE), with exactly the
+// operand expressions of the on-the-fly path.  It depends on the hyper-sample and the W set
+// only, so it is built once per BQ engine and read by every evaluation of the inner maximiser.
+__global__ void wdist_kernel(const double* __restrict__ hyp, int64_t stride,
+                             const double* __restrict__ Xs, int n, int dim_m, int dx, int dw,
+                             const double* __restrict__ wsets, int n_wsets, int M,
+                             double* __restrict__ out) {
+    const int nblk = (n + 31) / 32;
+    const int64_t per = (int64_t)nblk * M * 32;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.y, wsi = blockIdx.z;
+    if (idx >= per) return;
+    const int lane = (int)(idx & 31);
+    const int m = (int)((idx >> 5) % M);
+    const int jb = (int)((idx >> 5) / M);
+    const int j = jb * 32 + lane;
+    double acc = 0.0;
+    if (j < n) {
+        const double* h = hyp + (int64_t)s * stride;
+        for (int l = 0; l < dw; ++l) {
+            const double wv = (wsets[((int64_t)wsi * M + m) * dw + l] / h[BQO_H_LS + dx + l]) *
+                              BQO_PRESCALE;
+            const double xw = Xs[((int64_t)s * dim_m + dx + l) * n + j] * BQO_PRESCALE;
+            const double d = wv - xw;
+            acc = fma(d, d, acc);
+        }
+    }
+    out[((int64_t)s * n_wsets + wsi) * per + idx] = acc;
+}
+
+extern "C" int bqo_wdist_precompute(const bqo_kernel_desc* desc, const double* hyp, int32_t S,
+                                    const double* Xs, int32_t n, int32_t dx, int32_t dw,
+                                    const double* wsets, int32_t n_wsets, int32_t M, double* out,
+                                    void* stream) {
+    BQO_CHECK_ARG(desc != nullptr, 1);
+    BQO_CHECK_ARG(hyp != nullptr, 2);
+    BQO_CHECK_ARG(S > 0 && S <= 65535, 3);
+    BQO_CHECK_ARG(Xs != nullptr, 4);
+    BQO_CHECK_ARG(n > 0, 5);
+    BQO_CHECK_ARG(dx > 0 && dw > 0 && dx + dw == desc->dim_m, 6);
+    BQO_CHECK_ARG(wsets != nullptr, 8);
+    BQO_CHECK_ARG(n_wsets > 0 && n_wsets <= 65535, 9);
+    BQO_CHECK_ARG(M > 0, 10);
+    BQO_CHECK_ARG(out != nullptr, 11);
+    const int64_t per = (int64_t)((n + 31) / 32) * M * 32;
+    dim3 grid((unsigned)((per + 255) / 256), S, n_wsets);
+    wdist_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(hyp, bqo_hyper_stride_impl(*desc), Xs, n,
+                                                         desc->dim_m, dx, dw, wsets, n_wsets, M, out);
+    BQO_RETURN_LAST_ERROR();
+}
+
+// ---------------------------------------------------------------------------------------------
 // Inner maximisation.  CTA = (unit, chunk of Z samples); warp = one run (Z sample, start).
 // The optimiser is a projected BFGS with Armijo backtracking on phi = -(a + Z b); its iteration
 // cap, relative-decrease test (factr) and projected-gradient test (pgtol) are those of the
 // L-BFGS-B call the reference makes (scipy fmin_l_bfgs_b via Optimization.optimize,
 // sbo/lib/optimization.py:87-155, with maxiter=10, factr=1e12 from sbo/services/bgo.py:43-44).
 // oracle/inner_opt.py restates the same iteration in numpy.
-// 24 warps x 80 registers: measured best on B200 (sweep of {12,16,20,24,28} warps x {1,2,5}
-// interleaved W samples, profiles/r01_inner_maximize_v1.md)
+// 28 warps x 72 registers: measured best on B200 once the W-distance table freed the registers
+// that held the W samples (sweeps of {12..32} warps x {1,2,5} interleaved W samples,
+// profiles/r01_inner_maximize_v1.md and r01_tuning_sweeps.md; 24 x 80 before the table)
 #ifndef IM_WARPS
-#define IM_WARPS 24
+#define IM_WARPS 28
 #endif
 #define IM_MAX_VERT 64  // 2^DX for DX <= 6
 
@@ -546,7 +637,7 @@ struct RunState {  // per-warp optimiser state in shared memory (warp-uniform va
     double phi;
 };
 
-template <int DX, int DW, bool STAGE, int MT>
+template <int DX, int DW, bool STAGE, int MT, bool WD = false>
 __global__ void __launch_bounds__(IM_WARPS * 32, 1)
     inner_maximize_kernel(bqo_stage_c pb, bqo_inner_opt opt, const double* __restrict__ z,
                           const double* __restrict__ starts, double* __restrict__ out_max,
@@ -566,8 +657,9 @@ __global__ void __launch_bounds__(IM_WARPS * 32, 1)
     // ---- shared memory carve-up -------------------------------------------------------------
     double* s_tab = dyn_smem;                // [BQO_EXP_TABLE] exp table
     double* sm = dyn_smem + BQO_EXP_TABLE;
-    double* s_xs = sm;                       // STAGE: [D][n]
-    double* s_wa = s_xs + (STAGE ? (size_t)D * n : 0);
+    constexpr int XROWS = WD ? DX : D;       // with the W-distance table the w rows stay in HBM
+    double* s_xs = sm;                       // STAGE: [XROWS][n]
+    double* s_wa = s_xs + (STAGE ? (size_t)XROWS * n : 0);
     double* s_wb = s_wa + (STAGE ? n : 0);
     double* s_ws = s_wb + (STAGE ? n : 0);   // [M][DW] the unit's W set, scaled
     double* s_pre = s_ws + (size_t)M * (DW > 0 ? DW : 0);  // [n_pre][2+2DX]
@@ -591,7 +683,7 @@ __global__ void __launch_bounds__(IM_WARPS * 32, 1)
         const double* gxs = s_u.xs;
         const double* gwa = s_u.wa;
         const double* gwb = s_u.wb;
-        for (int e = threadIdx.x; e < D * n; e += blockDim.x) s_xs[e] = gxs[e] * BQO_PRESCALE;
+        for (int e = threadIdx.x; e < XROWS * n; e += blockDim.x) s_xs[e] = gxs[e] * BQO_PRESCALE;
         for (int e = threadIdx.x; e < n; e += blockDim.x) {
             s_wa[e] = gwa[e];
             s_wb[e] = gwb[e];
@@ -620,6 +712,13 @@ __global__ void __launch_bounds__(IM_WARPS * 32, 1)
         for (int e = threadIdx.x; e < M * DW; e += blockDim.x)
             s_ws[e] = (wsrc[e] / u.ls[DX + (e % (DW > 0 ? DW : 1))]) * BQO_PRESCALE;
     }
+    // this lane's column of the unit's W-distance table (hyper-sample k, W set c % n_wsets)
+    const double* wd = nullptr;
+    if (WD) {
+        const size_t nblk = (size_t)(n + 31) / 32;
+        wd = pb.wdist + (((size_t)pb.unit_k[unit] * pb.n_wsets + (pb.unit_c[unit] % pb.n_wsets)) *
+                         nblk) * ((size_t)M * 32) + lane;
+    }
     if (threadIdx.x == 0) *s_counter = 0;
     const double* st = starts + (opt.starts_per_hyper ? (int64_t)pb.unit_k[unit] * n_starts * DX : 0);
     __syncthreads();
@@ -642,7 +741,7 @@ __global__ void __launch_bounds__(IM_WARPS * 32, 1)
             for (int l = 0; l < DX; ++l) x[l] = ((v >> (DX - 1 - l)) & 1) ? pb.upper[l] : pb.lower[l];
         }
         AbOut<DX> o;
-        eval_ab_warp<DX, DW, STAGE, MT>(ep, u, x, s_ws, o);
+        eval_ab_warp<DX, DW, STAGE, MT, false, WD>(ep, u, x, s_ws, o, 0.0, wd);
         ++evals;
         if (lane == 0) {
             double* op = s_pre + (size_t)p * (2 + 2 * DX);
@@ -743,7 +842,7 @@ __global__ void __launch_bounds__(IM_WARPS * 32, 1)
                     decr = fma(S.g[l], t - S.x[l], decr);
                 }
                 AbOut<DX> o;
-                eval_ab_warp<DX, DW, STAGE, MT, true>(ep, u, xn, s_ws, o, Z * u.inv_den);
+                eval_ab_warp<DX, DW, STAGE, MT, true, WD>(ep, u, xn, s_ws, o, Z * u.inv_den, wd);
                 ++evals;
                 phin = -(o.a + Z * o.b);
                 if (phin <= S.phi + c1 * decr) {
@@ -882,8 +981,8 @@ __global__ void __launch_bounds__(IM_WARPS * 32, 1)
 }
 
 static size_t inner_smem_bytes(const bqo_stage_c* pb, const bqo_inner_opt* opt, bool stage,
-                               size_t state_bytes) {
-    const int D = pb->dx + pb->dw;
+                               size_t state_bytes, bool wd = false) {
+    const int D = wd ? pb->dx : pb->dx + pb->dw;  // staged coordinate rows
     const int M = pb->dw > 0 ? pb->M : 1;
     const int NV = 1 << pb->dx;
     const int n_pre = opt->n_starts + (opt->use_vertices ? NV : 0);
@@ -916,24 +1015,27 @@ extern "C" int bqo_inner_maximize_batched(const bqo_stage_c* pb, const bqo_inner
     BQO_CHECK_ARG(grid64 < 2147483647LL, 1);
     const int grid = (int)grid64;
     if (n_evals) cudaMemsetAsync(n_evals, 0, sizeof(unsigned long long) * pb->n_units, cs);
-#define LAUNCH_IM_K(DXV, DWV, STG, MTV, SB)                                                      \
+#define LAUNCH_IM_K(DXV, DWV, STG, MTV, WDV, SB)                                                 \
     do {                                                                                         \
-        cudaFuncSetAttribute(inner_maximize_kernel<DXV, DWV, STG, MTV>,                          \
+        cudaFuncSetAttribute(inner_maximize_kernel<DXV, DWV, STG, MTV, WDV>,                     \
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SB));            \
-        inner_maximize_kernel<DXV, DWV, STG, MTV><<<grid, IM_WARPS * 32, (SB), cs>>>(            \
+        inner_maximize_kernel<DXV, DWV, STG, MTV, WDV><<<grid, IM_WARPS * 32, (SB), cs>>>(       \
             *pb, *opt, z, starts, out_max, out_arg, n_evals);                                    \
     } while (0)
 #define LAUNCH_IM(DXV, DWV)                                                                      \
     do {                                                                                         \
-        size_t sb = inner_smem_bytes(pb, opt, true, sizeof(RunState<DXV>));                      \
+        const bool use_wd = (DWV > 0) && pb->wdist != nullptr && pb->M == 10;                    \
+        size_t sb = inner_smem_bytes(pb, opt, true, sizeof(RunState<DXV>), use_wd);              \
         if (sb <= 227 * 1024) {                                                                  \
             /* M = 10 (N_SAMPLES of sbo/lib/expectations.py:7) gets the fully unrolled build */  \
-            if (DWV > 0 && pb->M == 10) LAUNCH_IM_K(DXV, DWV, true, (DWV > 0 ? 10 : 0), sb);     \
-            else LAUNCH_IM_K(DXV, DWV, true, 0, sb);                                             \
+            if (use_wd) LAUNCH_IM_K(DXV, DWV, true, (DWV > 0 ? 10 : 0), (DWV > 0), sb);          \
+            else if (DWV > 0 && pb->M == 10)                                                     \
+                LAUNCH_IM_K(DXV, DWV, true, (DWV > 0 ? 10 : 0), false, sb);                      \
+            else LAUNCH_IM_K(DXV, DWV, true, 0, false, sb);                                      \
         } else {                                                                                 \
             sb = inner_smem_bytes(pb, opt, false, sizeof(RunState<DXV>));                        \
             if (sb > 227 * 1024) return -2;                                                      \
-            LAUNCH_IM_K(DXV, DWV, false, 0, sb);                                                 \
+            LAUNCH_IM_K(DXV, DWV, false, 0, false, sb);                                          \
         }                                                                                        \
     } while (0)
     SC_DISPATCH(pb, LAUNCH_IM);

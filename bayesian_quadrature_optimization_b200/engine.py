@@ -289,8 +289,16 @@ class BQEngine(object):
                 raise ValueError("wsets must be [n_wsets][M][d_w]")
             self.wsets = ws.contiguous()
             self.n_wsets, self.M = int(ws.shape[0]), int(ws.shape[1])
+            # the W part of every squared distance is independent of x: one table per
+            # (hyper-sample, W set), read by every evaluation of the inner maximiser
+            nblk = (eng.n + 31) // 32
+            self.wdist = eng.empty(hb.S, self.n_wsets, nblk, self.M, 32)
+            check(eng.lib.bqo_wdist_precompute(
+                C.byref(d), ptr(hb.hyp), hb.S, ptr(hb.Xs), eng.n, self.dx, self.dw, ptr(self.wsets),
+                self.n_wsets, self.M, ptr(self.wdist), _stream()), "bqo_wdist_precompute")
         else:
             self.wsets, self.n_wsets, self.M = None, 0, 1
+            self.wdist = None
         self.lower = None if lower is None else eng.to_device(lower).reshape(-1)
         self.upper = None if upper is None else eng.to_device(upper).reshape(-1)
         # noise term of the denominator: mean observed noise if any, else var_noise_s
@@ -448,7 +456,10 @@ class BQEngine(object):
         pb.R, pb.den, pb.beta4, pb.cand = ptr(ub.R), ptr(ub.den), ptr(ub.beta4), ptr(ub.cand)
         pb.unit_k, pb.unit_c = ptr(ub.unit_k), ptr(ub.unit_c)
         pb.wsets, pb.lower, pb.upper = ptr(self.wsets), ptr(self.lower), ptr(self.upper)
+        pb.wdist = ptr(self.wdist) if self.use_wdist else None
         return pb
+
+    use_wdist = True  # class-level switch (tests compare against the on-the-fly distances)
 
     # -- stage C ---------------------------------------------------------------------------------------
     def sample_ab(self, ub, pts, pt_unit, pt_wset=None):

@@ -213,7 +213,19 @@ typedef struct bqo_stage_c {
     const double* wsets;    /* [n_wsets][M][dw] raw W samples (gamma.rvs of expectations.py:105) */
     const double* lower;    /* [dx] box bounds of x */
     const double* upper;    /* [dx] */
+    const double* wdist;    /* [S][n_wsets][ceil(n/32)][M][32] from bqo_wdist_precompute, or NULL
+                               (the W part of the squared distances is then recomputed in every
+                               evaluation) */
 } bqo_stage_c;
+
+/* W part of the squared scaled distances between the W samples of every set and every training
+ * point, per hyper-sample (it does not depend on the query point x): the term that gamma_expect
+ * (sbo/lib/expectations.py:76-118) re-evaluates inside every kernel call through
+ * Distances.dist_square_length_scale (sbo/lib/distances.py:10-29).
+ * out: S * n_wsets * ceil(n/32) * M * 32 doubles. */
+int bqo_wdist_precompute(const bqo_kernel_desc* desc, const double* hyp, int32_t S, const double* Xs,
+                         int32_t n, int32_t dx, int32_t dw, const double* wsets, int32_t n_wsets,
+                         int32_t M, double* out, void* stream);
 
 /* a, b, grad a, grad b at P points: point q belongs to unit pt_unit[q], uses W set pt_wset[q]
  * (compute_parameters_for_sample / compute_gradient_parameters_for_sample,

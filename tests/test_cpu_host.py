@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     from bayesian_quadrature_optimization_b200 import _cabi
     assert ctypes.sizeof(_cabi.KernelDesc) == 24
-    assert ctypes.sizeof(_cabi.StageC) == 24 + 8 * 4 + 14 * 8
+    assert ctypes.sizeof(_cabi.StageC) == 24 + 8 * 4 + 15 * 8
     assert ctypes.sizeof(_cabi.InnerOpt) == 48
     d = _cabi.KernelDesc(2, 3, 2, 4, 1, 4)
     assert _cabi.load().bqo_hyper_stride(ctypes.byref(d)) == 4 + 2 * 16 + 2 * 16
