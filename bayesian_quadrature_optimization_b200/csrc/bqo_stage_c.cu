@@ -1163,6 +1163,123 @@ __global__ void __launch_bounds__(AB_WARPS * 32)
     }
 }
 
+// Staged variant for the Monte-Carlo-W models: CTA = unit, warps loop over the unit's points.
+// The x rows (in units of K), s2 and the exp table are staged once per unit as in the inner
+// maximiser, the W part of the distances comes from the bqo_wdist_precompute table (default W
+// set of the unit), the D rows Sigma^-1 grad_l gamma are streamed from L2.
+template <int DX, int DW>
+__global__ void __launch_bounds__(IM_WARPS * 32, 1)
+    grad_vector_b_staged_kernel(bqo_stage_c pb, const double* __restrict__ pts, int npts,
+                                double* __restrict__ out, int32_t* __restrict__ is_nan) {
+    constexpr int D = DX + DW;
+    constexpr int MT = 10;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int unit = blockIdx.x;
+    const int n = pb.n;
+    double* s_tab = dyn_smem;
+    double* s_xs = dyn_smem + BQO_EXP_TABLE;  // [DX][n]
+    double* s_wb = s_xs + (size_t)DX * n;     // [n]
+    double* s_ws = s_wb + n;                  // [MT][DW]
+    __shared__ UnitCtx<DX, DW> s_u;
+    if (threadIdx.x == 0) unit_ctx_init<DX, DW>(s_u, pb, unit);
+    bqo_exp_table_init(s_tab);
+    __syncthreads();
+    const UnitCtx<DX, DW>& u = s_u;
+    const int k = pb.unit_k[unit], c = pb.unit_c[unit];
+    const double den = pb.den[(int64_t)k * pb.C + c];
+    if (den * den == 0.0) {  // beta_1[0] == 0 -> np.nan (bayesian_quadrature.py:1483-1484)
+        if (threadIdx.x == 0) is_nan[unit] = 1;
+        for (int e = threadIdx.x; e < npts * D; e += blockDim.x)
+            out[(int64_t)unit * npts * D + e] = nan("");
+        return;
+    }
+    if (threadIdx.x == 0) is_nan[unit] = 0;
+    {
+        const double* gxs = u.xs;
+        const double* gwb = u.wb;
+        for (int e = threadIdx.x; e < DX * n; e += blockDim.x) s_xs[e] = gxs[e] * BQO_PRESCALE;
+        for (int e = threadIdx.x; e < n; e += blockDim.x) s_wb[e] = gwb[e];
+        const double* wsrc = pb.wsets + (size_t)(c % pb.n_wsets) * MT * DW;
+        for (int e = threadIdx.x; e < MT * DW; e += blockDim.x)
+            s_ws[e] = (wsrc[e] / u.ls[DX + (e % (DW > 0 ? DW : 1))]) * BQO_PRESCALE;
+    }
+    __syncthreads();
+    const size_t nblk = (size_t)(n + 31) / 32;
+    const double* wd = pb.wdist + (((size_t)k * pb.n_wsets + (c % pb.n_wsets)) * nblk) *
+                                      ((size_t)MT * 32) + lane;
+    const double* V = u.wb + n;  // rows 1..D of the unit: Sigma^-1 grad_l gamma (q-weighted)
+    const double beta1 = 1.0 / den;
+    for (int p = warp; p < npts; p += IM_WARPS) {
+        const int64_t gp = (int64_t)unit * npts + p;
+        double xsc[DX];
+#pragma unroll
+        for (int l = 0; l < DX; ++l) xsc[l] = (pts[gp * DX + l] / u.ls[l]) * BQO_PRESCALE;
+        double Sb = 0.0, SV[D];
+#pragma unroll
+        for (int l = 0; l < D; ++l) SV[l] = 0.0;
+        for (int j = lane; j < n; j += 32) {
+            double Dx = 1e-300;
+#pragma unroll
+            for (int l = 0; l < DX; ++l) {
+                const double df = xsc[l] - s_xs[l * n + j];
+                Dx = fma(df, df, Dx);
+            }
+            const double* wj = wd + (size_t)(j >> 5) * (MT * 32);
+            double E0 = 0.0, E1 = 0.0, H = 0.0;
+#pragma unroll
+            for (int m = 0; m < MT; m += 2) {
+                double q2v[2], ev[2], t1v[2];
+                q2v[0] = Dx + __ldg(wj + m * 32);
+                q2v[1] = Dx + __ldg(wj + (m + 1) * 32);
+                bqo_matern52_q_v<2>(q2v, SmemExpTab(), ev, t1v);
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    E0 += ev[q];
+                    E1 = fma(t1v[q], ev[q], E1);
+                    H = fma(q2v[q], ev[q], H);
+                }
+            }
+            const double ksum = fma(H, BQO_H_TO_K, fma(E1, BQO_LN2_N, E0));
+            Sb = fma(ksum, s_wb[j], Sb);
+#pragma unroll
+            for (int l = 0; l < D; ++l) SV[l] = fma(ksum, __ldg(V + (int64_t)l * n + j), SV[l]);
+        }
+        // candidate terms: k((p, w_m), c) and its gradient with respect to c
+        double Kc = 0.0, GC[D];
+#pragma unroll
+        for (int l = 0; l < D; ++l) GC[l] = 0.0;
+        for (int m = lane; m < MT; m += 32) {
+            double df[D];
+            double q2v[1], ev[1], t1v[1];
+            q2v[0] = 1e-300;
+#pragma unroll
+            for (int l = 0; l < DX; ++l) df[l] = u.cs[l] * BQO_PRESCALE - xsc[l];
+#pragma unroll
+            for (int l = 0; l < DW; ++l) df[DX + l] = u.cs[DX + l] * BQO_PRESCALE - s_ws[m * DW + l];
+#pragma unroll
+            for (int l = 0; l < D; ++l) q2v[0] = fma(df[l], df[l], q2v[0]);
+            bqo_matern52_q_v<1>(q2v, SmemExpTab(), ev, t1v);
+            const double gm = fma(t1v[0], BQO_LN2_N, 1.0) * ev[0];
+            Kc += fma(q2v[0] * ev[0], BQO_H_TO_K, gm);
+            const double g = BQO_GRAD_FAC * gm;
+#pragma unroll
+            for (int l = 0; l < D; ++l) GC[l] = fma(g, df[l], GC[l]);
+        }
+        Sb = bqo_warp_sum(Sb);
+        Kc = bqo_warp_sum(Kc);
+        const double beta2 = u.scale * (u.wc * Kc - Sb);
+#pragma unroll
+        for (int l = 0; l < D; ++l) {
+            const double sv = bqo_warp_sum(SV[l]);
+            const double gc = bqo_warp_sum(GC[l]);
+            const double beta3 = u.scale * (u.wc * gc * u.inv_ls[l] - sv);
+            const double beta4 = pb.beta4[((int64_t)k * pb.C + c) * D + l];
+            const double g = beta1 * beta3 + 0.5 * (beta1 * beta1 * beta1) * beta2 * beta4;
+            if (lane == 0) out[gp * D + l] = g;
+        }
+    }
+}
+
 extern "C" int bqo_grad_vector_b_batched(const bqo_stage_c* pb, const double* pts, int32_t npts,
                                          const int32_t* pt_wset, double* out, int32_t* is_nan,
                                          void* stream) {
@@ -1173,6 +1290,27 @@ extern "C" int bqo_grad_vector_b_batched(const bqo_stage_c* pb, const double* pt
     BQO_CHECK_ARG(out != nullptr, 5);
     BQO_CHECK_ARG(is_nan != nullptr, 6);
     cudaStream_t cs = (cudaStream_t)stream;
+    // staged kernel: Monte-Carlo W with the distance table, the default W set, enough points per
+    // unit to pay for the staging, and the unit's operands fit shared memory
+    {
+        const size_t sb = sizeof(double) * ((size_t)BQO_EXP_TABLE + (size_t)(pb->dx + 1) * pb->n +
+                                            (size_t)10 * pb->dw) + 16;
+        if (pb->dw > 0 && pb->wdist != nullptr && pb->M == 10 && pt_wset == nullptr &&
+            npts >= IM_WARPS && sb <= 227 * 1024) {
+#define LAUNCH_GVBS(DXV, DWV)                                                                    \
+    do {                                                                                         \
+        if (DWV > 0) {                                                                           \
+            cudaFuncSetAttribute(grad_vector_b_staged_kernel<DXV, (DWV > 0 ? DWV : 1)>,          \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);          \
+            grad_vector_b_staged_kernel<DXV, (DWV > 0 ? DWV : 1)>                                \
+                <<<pb->n_units, IM_WARPS * 32, sb, cs>>>(*pb, pts, npts, out, is_nan);           \
+        }                                                                                        \
+    } while (0)
+            SC_DISPATCH(pb, LAUNCH_GVBS);
+#undef LAUNCH_GVBS
+            BQO_RETURN_LAST_ERROR();
+        }
+    }
     int64_t total = (int64_t)pb->n_units * npts;
     int grid = (int)((total + AB_WARPS - 1) / AB_WARPS);
     size_t smem = sizeof(double) * (BQO_EXP_TABLE + AB_WARPS * (size_t)(pb->M > 0 ? pb->M : 1) * (pb->dw > 0 ? pb->dw : 1));

@@ -132,6 +132,20 @@ def test_c3_stage_b_c_against_oracle_at_n2048():
     v = obq.compute_parameters_for_sample(out_arg[0, 1], cands[0:1], th[0], th[1], th[2:], w=wset)
     assert_close(v["a"][0] + zs[1] * np.asarray(v["b"]).reshape(-1)[0], out_max[0, 1],
                  rtol=100 * rtols[0], atol=1e-9, what="oracle value at device argmax")
+    # the W-distance table against the on-the-fly distances, and the staged gradient_vector_b
+    # kernel (>= 28 points per unit) against the per-point kernel (explicit W sets)
+    E.BQEngine.use_wdist = False
+    try:
+        om2, oa2, _ = bq.inner_maximize(ub, zs, starts, count_evals=True)
+    finally:
+        E.BQEngine.use_wdist = True
+    assert_close(om2.cpu().numpy(), out_max, rtol=1e-10, atol=1e-12, what="table vs on-the-fly")
+    many = np.random.RandomState(8).uniform(0, 1, (2 * S, 40, dx))
+    g_staged, nan1 = bq.grad_vector_b(ub, many)
+    g_plain, nan2 = bq.grad_vector_b(ub, many, pt_wset=np.zeros((2 * S, 40), dtype=np.int32))
+    assert not nan1.cpu().numpy().any() and not nan2.cpu().numpy().any()
+    assert_close(g_staged.cpu().numpy(), g_plain.cpu().numpy(), rtol=1e-9, atol=1e-11,
+                 what="staged gradient_vector_b")
     # gradient_vector_b at the maximisers
     gvb, is_nan = bq.grad_vector_b(ub, out_arg)
     assert not is_nan.cpu().numpy().any()
