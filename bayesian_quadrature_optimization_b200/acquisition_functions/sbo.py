@@ -114,6 +114,58 @@ class SBO(object):
             use_vertices=len(bounds_x) < 7)
         return {'max': float(mx.cpu().numpy()[0, 0]), 'optimum': arg.cpu().numpy()[0, 0]}
 
+    # -- one-sample stochastic gradient (a35) ------------------------------------------------------------
+    def evaluate_gradient_given_sample_given_parameters(
+            self, candidate_point, sample, parameters=None, n_restarts=10, n_best_restarts=0,
+            n_threads=0, parallel=True, method_opt=None, **opt_params_mc):
+        """:964-1045 -> np.array(1 x d) or the object np.nan: Z * grad_c b(x*; c) at the maximiser
+        x* of a + Z b for this Z and these hyper-parameters (device maximiser from the cached
+        starting points, then gradient_vector_b at x*)."""
+        gp = self.bq.gp
+        if parameters is None:
+            var_noise, mean = gp.var_noise.value[0], gp.mean.value[0]
+            parameters_kernel = gp.kernel.hypers_values_as_array
+        else:
+            var_noise, mean, parameters_kernel = parameters[0], parameters[1], parameters[2:]
+        if self.starting_points_sbo is None:
+            self.generate_starting_points_evaluate_mc(n_restarts)
+        theta = self.bq._theta(var_noise, mean, parameters_kernel)
+        bq = self.bq.engine_for(theta)
+        candidate_point = np.asarray(candidate_point, dtype=float).reshape(1, -1)
+        ub = bq.setup(candidate_point)
+        _, arg, _ = bq.inner_maximize(
+            ub, np.array([sample], dtype=float), np.asarray(self.starting_points_sbo, dtype=float),
+            maxiter=opt_params_mc.get('maxiter', 15000), factr=opt_params_mc.get('factr', 1e7),
+            pgtol=self.inner_pgtol, max_ls=self.inner_max_ls,
+            use_vertices=len(self._bounds_x()) < 7)
+        maximum = arg.cpu().numpy()[0, 0].reshape(1, -1)
+        gradient_b = self.bq.gradient_vector_b(candidate_point, maximum, var_noise=var_noise,
+                                               mean=mean, parameters_kernel=parameters_kernel)
+        if gradient_b is np.nan:
+            return np.nan
+        return gradient_b * sample
+
+    def grad_voi_sgd(self, point, monte_carlo, bayesian, n_restarts=10, n_best_restarts=0,
+                     n_threads=0, parallel=True, method_opt=None, random_seed=None,
+                     **opt_params_mc):
+        """:1103-1142 -> np.array(d) or the object np.nan: one slice sample of the
+        hyper-parameters (if bayesian), one Z ~ N(0, 1) (if monte_carlo), then the gradient above.
+        SBO.optimize averages many of these per epoch on the device instead."""
+        if random_seed is not None:
+            np.random.seed(random_seed)
+        point = np.asarray(point, dtype=float).reshape((1, -1))
+        params = self.bq.gp.sample_parameters(1)[0] if bayesian else None
+        sample = np.random.normal(0, 1, 1)[0] if monte_carlo else None
+        if sample is None:
+            raise NotImplementedError("the discretised (non Monte-Carlo) SGD gradient is "
+                                      "SBO.evaluate_gradient")
+        grad = self.evaluate_gradient_given_sample_given_parameters(
+            point, sample, params, n_restarts, n_best_restarts, n_threads, parallel,
+            method_opt=method_opt, **opt_params_mc)
+        if grad is np.nan:
+            return grad
+        return grad[0, :]
+
     # -- Monte-Carlo Bayesian estimate over many candidates -----------------------------------------------
     def _max_posterior_mean(self, bq, parameters, n_restarts=100):
         """max_x E[G(x)] per hyper-sample (optimize_posterior_mean, bayesian_quadrature.py:693-910,

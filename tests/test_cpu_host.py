@@ -147,3 +147,55 @@ def test_world_size_two_gloo_selection():
         assert gi == 3 and v == values[3]          # np.argmax tie rule: first index
         lo0, hi0 = 0, 6
         assert tot == values[:6].sum() + values[6:].sum()
+
+
+def test_host_sgd_matches_oracle_and_handles_unavailable_gradients():
+    """lib/stochastic_gradient_descent.SGD (a36): Adam path equals the oracle's restatement bit for
+    bit; the object np.nan triggers the random perturbation; momentum SGD converges too."""
+    from bayesian_quadrature_optimization_b200.lib.stochastic_gradient_descent import SGD
+    from oracle import bqo_oracle as orc
+    target = np.array([0.3, 0.8, 0.55])
+    grad = lambda x: 2.0 * (x - target)
+    bounds = [(0.0, 1.0)] * 3
+    start = np.array([0.9, 0.1, 0.2])
+    got = SGD(start, grad, 2, bounds=bounds, maxepoch=40)
+    want = orc.sgd_adam(start, grad, 2, bounds=bounds, maxepoch=40)
+    assert np.array_equal(got, want)
+    assert np.array_equal(start, np.array([0.9, 0.1, 0.2]))  # inputs are never mutated
+    calls = {"n": 0}
+
+    def sometimes_unavailable(x, scale):
+        calls["n"] += 1
+        if calls["n"] in (1, 2, 7):
+            return np.nan
+        return scale * 2.0 * (x - target)
+
+    np.random.seed(0)
+    out = SGD(start, sometimes_unavailable, 1, args=(1.0,), bounds=bounds, maxepoch=200)
+    assert np.all(out >= 0.0) and np.all(out <= 1.0) and np.linalg.norm(out - target) < 0.15
+    out2 = SGD(start, grad, 1, bounds=bounds, adam=False, learning_rate=0.05, momentum=0.5,
+               maxepoch=300)
+    assert np.linalg.norm(out2 - target) < 0.05
+    # projection: an optimum outside the box ends on the boundary
+    out3 = SGD(start, lambda x: 2.0 * (x - np.array([2.0, -1.0, 0.5])), 1, bounds=bounds,
+               maxepoch=250)
+    assert out3[0] == 1.0 and out3[1] == 0.0
+
+
+def test_bayesian_evaluations_mean_and_std():
+    from bayesian_quadrature_optimization_b200.bayesian.bayesian_evaluations import \
+        BayesianEvaluations
+
+    class Model(object):
+        samples_parameters = [np.array([0.1, 1.0, 2.0, 3.0]), np.array([0.2, 2.0, 4.0, 5.0]),
+                              np.array([0.3, 3.0, 6.0, 7.0])]
+
+    def f(point, extra, var_noise, mean, params):
+        return float(point[0] * extra + var_noise + mean + params.sum())
+
+    vals = [2.0 * 10 + 0.2 + 2.0 + 9.0, 2.0 * 10 + 0.3 + 3.0 + 13.0]
+    m, s = BayesianEvaluations.evaluate(f, np.array([2.0]), Model(), 2, None, 10)
+    assert m == np.mean(vals) and s == np.std(vals)
+    g = lambda point, var_noise, mean, params: point * mean
+    m2, s2 = BayesianEvaluations.evaluate(g, np.array([1.0, 2.0]), Model(), 3)
+    assert np.allclose(m2, np.array([2.0, 4.0])) and m2.shape == (2,) and s2.shape == (2,)

@@ -488,3 +488,36 @@ def test_quadrature_posterior_gradients_and_ei_on_g(golden, name):
         assert all(bq2.bounds[l][0] <= sol[l] <= bq2.bounds[l][-1] for l in range(dx))
         # the Adam climb does not end below the best of its own starting values
         assert np.isfinite(res["optimal_value"])
+
+
+def test_one_sample_stochastic_gradient(golden):
+    """a35: grad_voi_sgd / evaluate_gradient_given_sample_given_parameters return Z * grad_c b at the
+    device's maximiser; checked against the oracle's gradient_vector_b at that maximiser."""
+    from bayesian_quadrature_optimization_b200.acquisition_functions.sbo import SBO
+    g = golden("scaled_gamma")
+    gp, bq = _models(g)
+    spec, ogp, obq = oracle_from_golden(g)
+    sbo = SBO(bq)
+    th = g["thetas"][0]
+    cand = g["cands"][0:1]
+    np.random.seed(5)
+    grad = sbo.evaluate_gradient_given_sample_given_parameters(cand, 0.7, th, n_restarts=3,
+                                                               factr=1e12, maxiter=10)
+    assert grad.shape == (1, g["points"].shape[1])
+    xstar = _argmax_of(sbo, bq, cand, 0.7, th)
+    want = obq.gradient_vector_b(cand, xstar, th[0], th[1], th[2:], w=g["wset"]) * 0.7
+    assert_close(grad, want, rtol=1e-6, atol=1e-9, what="one-sample gradient")
+    gp.samples_parameters = [t.copy() for t in g["thetas"]]
+    np.random.seed(6)
+    gv = sbo.grad_voi_sgd(cand[0], True, False, n_restarts=3, factr=1e12, maxiter=10)
+    assert gv.shape == (g["points"].shape[1],) and np.all(np.isfinite(gv))
+
+
+def _argmax_of(sbo, bq, cand, z, th):
+    """The maximiser the device finds for (cand, z, theta) from sbo.starting_points_sbo."""
+    eng = bq.engine_for(bq._theta(th[0], th[1], th[2:]))
+    ub = eng.setup(np.asarray(cand, dtype=float).reshape(1, -1))
+    _, arg, _ = eng.inner_maximize(ub, np.array([z]), np.asarray(sbo.starting_points_sbo),
+                                   maxiter=10, factr=1e12, pgtol=sbo.inner_pgtol,
+                                   max_ls=sbo.inner_max_ls, use_vertices=True)
+    return arg.cpu().numpy()[0, 0].reshape(1, -1)
