@@ -114,6 +114,9 @@ __device__ __forceinline__ double bqo_matern52_dr(double r, double r2) {
 #define BQO_LN2_N (BQO_LN2 / (double)BQO_EXP_TABLE)                 // c = ln2 / N
 #define BQO_H_TO_K (BQO_LN2_N * BQO_LN2_N / 3.0)                    // sum k = G + this * H
 #define BQO_GRAD_FAC (-BQO_FIVE_THIRDS / BQO_PRESCALE)              // d/dx = this * G * dx' / ls
+// Bound of each of the two parts (x part, W part) of a squared distance on the unclamped path:
+// their sum stays below 2^(2 (BITS + 9)), i.e. u < 2^(BITS + 9) (k < 1e-150 beyond that anyway).
+#define BQO_U2_PART_HI ((1023 + 2 * (BQO_EXP_BITS + 9) - 1) << 20)   // high word of 2^(2(BITS+9)-1)
 
 // The one constant that is not an FP64 immediate lives in constant memory so that DFMA/DMUL read
 // it as a c[bank][off] operand; as literals ptxas re-materialised each 64-bit constant with two
@@ -153,7 +156,9 @@ __device__ __forceinline__ void bqo_exp_table_init(double* tab) {
 // `tab(m)` reads table entry m mod N (a functor so that the caller decides how the shared-memory
 // address is formed).
 // FP64 instructions per evaluation (N = 2048): sqrt 5, reduction 3, polynomial 3, table multiply 1.
-template <int NV, class Tab>
+// CLAMP = false: the caller guarantees u2 <= 2^(2 (BITS + 9)) (bqo_wdist_precompute bounds its table
+// and the x part is clamped once per training point), so the per-evaluation clamp is dropped.
+template <int NV, class Tab, bool CLAMP = true>
 __device__ __forceinline__ void bqo_matern52_q_v(const double (&u2)[NV], Tab tab, double (&e)[NV],
                                                  double (&t1)[NV]) {
     double g[NV], h[NV], w[NV], kf[NV], fr[NV], p[NV];
@@ -184,8 +189,11 @@ __device__ __forceinline__ void bqo_matern52_q_v(const double (&u2)[NV], Tab tab
         // u below 2^(BITS+9) + 1: exp(-u c) stops at 2^-512, k <= 1e-150, instead of decaying
         // further, the low word of magic + u can never wrap, and the exponent arithmetic below
         // stays inside the normal range whatever the inputs (tiny length scales included).
-        unsigned uh = min((unsigned)__double2hiint(g[q]), (unsigned)((1023 + BQO_EXP_BITS + 9) << 20));
-        g[q] = __hiloint2double((int)uh, __double2loint(g[q]));
+        if (CLAMP) {
+            unsigned uh = min((unsigned)__double2hiint(g[q]),
+                              (unsigned)((1023 + BQO_EXP_BITS + 9) << 20));
+            g[q] = __hiloint2double((int)uh, __double2loint(g[q]));
+        }
         // (F2I.F64 / I2F.F64 instead of the two DADDs measured 2.3% slower: profiles/r01_tuning_sweeps.md)
         double tk = magic + g[q];
         n[q] = (unsigned)__double2loint(tk);

@@ -259,7 +259,9 @@ __device__ __forceinline__ void eval_ab_warp(const EvalPtrs& p, const UnitCtx<DX
     const int M = (MT > 0) ? MT : p.M;
     for (int j = lane; j < p.n; j += 32) {
         double dxl[DX];
-        double Dx = 1e-300;  // keeps q2 a normal positive number for the fast sqrt (k(0) = 1)
+        // keeps q2 a normal positive number for the fast sqrt (k(0) = 1); with the W-distance
+        // table the floor is part of the table entries
+        double Dx = (DW > 0 && WD) ? 0.0 : 1e-300;
 #pragma unroll
         for (int l = 0; l < DX; ++l) {
             double xj = p.xs[l * p.ldx + j];
@@ -270,11 +272,15 @@ __device__ __forceinline__ void eval_ab_warp(const EvalPtrs& p, const UnitCtx<DX
         double E0 = 0.0, E1 = 0.0, H = 0.0;  // sum e, sum u e, sum u2 e over the W samples
         if (DW > 0 && WD) {
             const double* wj = wd + (size_t)(j >> 5) * (M * 32);
+            // one clamp of the x part per training point (the table is bounded when it is built)
+            // replaces the clamp inside every kernel evaluation
+            Dx = __hiloint2double((int)min((unsigned)__double2hiint(Dx), (unsigned)BQO_U2_PART_HI),
+                                  __double2loint(Dx));
             auto step_nv = [&](int m) {
                 double q2v[EVAL_NV], ev[EVAL_NV], t1v[EVAL_NV];
 #pragma unroll
                 for (int q = 0; q < EVAL_NV; ++q) q2v[q] = Dx + __ldg(wj + (m + q) * 32);
-                bqo_matern52_q_v<EVAL_NV>(q2v, SmemExpTab(), ev, t1v);
+                bqo_matern52_q_v<EVAL_NV, SmemExpTab, false>(q2v, SmemExpTab(), ev, t1v);
 #pragma unroll
                 for (int q = 0; q < EVAL_NV; ++q) {
                     E0 += ev[q];
@@ -285,7 +291,7 @@ __device__ __forceinline__ void eval_ab_warp(const EvalPtrs& p, const UnitCtx<DX
             auto step_1 = [&](int m) {
                 double q2v[1], ev[1], t1v[1];
                 q2v[0] = Dx + __ldg(wj + m * 32);
-                bqo_matern52_q_v<1>(q2v, SmemExpTab(), ev, t1v);
+                bqo_matern52_q_v<1, SmemExpTab, false>(q2v, SmemExpTab(), ev, t1v);
                 E0 += ev[0];
                 E1 = fma(t1v[0], ev[0], E1);
                 H = fma(q2v[0], ev[0], H);
@@ -590,6 +596,9 @@ __global__ void wdist_kernel(const double* __restrict__ hyp, int64_t stride,
             const double d = wv - xw;
             acc = fma(d, d, acc);
         }
+        // bounded (the evaluation then needs no clamp of its own) and strictly positive (the
+        // fast square root needs a normal positive argument; + 1e-300 only changes acc == 0)
+        acc = fmin(acc, __hiloint2double(BQO_U2_PART_HI, 0)) + 1e-300;
     }
     out[((int64_t)s * n_wsets + wsi) * per + idx] = acc;
 }
@@ -1218,12 +1227,14 @@ __global__ void __launch_bounds__(IM_WARPS * 32, 1)
 #pragma unroll
         for (int l = 0; l < D; ++l) SV[l] = 0.0;
         for (int j = lane; j < n; j += 32) {
-            double Dx = 1e-300;
+            double Dx = 0.0;
 #pragma unroll
             for (int l = 0; l < DX; ++l) {
                 const double df = xsc[l] - s_xs[l * n + j];
                 Dx = fma(df, df, Dx);
             }
+            Dx = __hiloint2double((int)min((unsigned)__double2hiint(Dx), (unsigned)BQO_U2_PART_HI),
+                                  __double2loint(Dx));
             const double* wj = wd + (size_t)(j >> 5) * (MT * 32);
             double E0 = 0.0, E1 = 0.0, H = 0.0;
 #pragma unroll
@@ -1231,7 +1242,7 @@ __global__ void __launch_bounds__(IM_WARPS * 32, 1)
                 double q2v[2], ev[2], t1v[2];
                 q2v[0] = Dx + __ldg(wj + m * 32);
                 q2v[1] = Dx + __ldg(wj + (m + 1) * 32);
-                bqo_matern52_q_v<2>(q2v, SmemExpTab(), ev, t1v);
+                bqo_matern52_q_v<2, SmemExpTab, false>(q2v, SmemExpTab(), ev, t1v);
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     E0 += ev[q];
