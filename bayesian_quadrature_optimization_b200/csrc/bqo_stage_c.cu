@@ -257,6 +257,8 @@ __device__ __forceinline__ void eval_ab_warp(const EvalPtrs& p, const UnitCtx<DX
 #pragma unroll
     for (int l = 0; l < DX; ++l) GA[l] = GB[l] = 0.0;
     const int M = (MT > 0) ? MT : p.M;
+    constexpr bool REC = PRE && WD && (DW > 0);
+    constexpr int RECLD = (DX + 2) | 1;
     for (int j = lane; j < p.n; j += 32) {
         double dxl[DX];
         // keeps q2 a normal positive number for the fast sqrt (k(0) = 1); with the W-distance
@@ -264,7 +266,9 @@ __device__ __forceinline__ void eval_ab_warp(const EvalPtrs& p, const UnitCtx<DX
         double Dx = (DW > 0 && WD) ? 0.0 : 1e-300;
 #pragma unroll
         for (int l = 0; l < DX; ++l) {
-            double xj = p.xs[l * p.ldx + j];
+            // staged + W-distance table: one record [x_1..x_DX, wa, wb, pad] per training point
+            // (odd stride in doubles: conflict-free 64-bit loads at immediate offsets)
+            double xj = REC ? p.xs[(size_t)j * RECLD + l] : p.xs[l * p.ldx + j];
             if (!PRE) xj *= BQO_PRESCALE;
             dxl[l] = xsc[l] - xj;
             Dx = fma(dxl[l], dxl[l], Dx);
@@ -374,7 +378,8 @@ __device__ __forceinline__ void eval_ab_warp(const EvalPtrs& p, const UnitCtx<DX
         }
         const double G = fma(E1, BQO_LN2_N, E0);  // sum_m (1 + sqrt5 r_m) e_m
         const double ksum = fma(H, BQO_H_TO_K, G);
-        const double wa = p.wa[j], wb = p.wb[j];
+        const double wa = REC ? p.xs[(size_t)j * RECLD + DX] : p.wa[j];
+        const double wb = REC ? p.xs[(size_t)j * RECLD + DX + 1] : p.wb[j];
         if (CMB) {
             const double w = fma(-zd, wb, wa);
             Sa = fma(ksum, w, Sa);
@@ -667,10 +672,11 @@ __global__ void __launch_bounds__(IM_WARPS * 32, 1)
     double* s_tab = dyn_smem;                // [BQO_EXP_TABLE] exp table
     double* sm = dyn_smem + BQO_EXP_TABLE;
     constexpr int XROWS = WD ? DX : D;       // with the W-distance table the w rows stay in HBM
-    double* s_xs = sm;                       // STAGE: [XROWS][n]
-    double* s_wa = s_xs + (STAGE ? (size_t)XROWS * n : 0);
-    double* s_wb = s_wa + (STAGE ? n : 0);
-    double* s_ws = s_wb + (STAGE ? n : 0);   // [M][DW] the unit's W set, scaled
+    constexpr int RECLD = (DX + 2) | 1;      // WD: records [x_1..x_DX, wa, wb, pad] per point
+    double* s_xs = sm;                       // STAGE: [XROWS][n], or [n][RECLD] with WD
+    double* s_wa = s_xs + (STAGE ? (WD ? (size_t)RECLD * n : (size_t)XROWS * n) : 0);
+    double* s_wb = s_wa + ((STAGE && !WD) ? n : 0);
+    double* s_ws = s_wb + ((STAGE && !WD) ? n : 0);   // [M][DW] the unit's W set, scaled
     double* s_pre = s_ws + (size_t)M * (DW > 0 ? DW : 0);  // [n_pre][2+2DX]
     double* s_prex = s_pre + (size_t)n_pre * (2 + 2 * DX);              // [n_pre][DX]
     double* s_run = s_prex + (size_t)n_pre * DX;  // [nz][n_starts][1+DX] run results
@@ -692,10 +698,22 @@ __global__ void __launch_bounds__(IM_WARPS * 32, 1)
         const double* gxs = s_u.xs;
         const double* gwa = s_u.wa;
         const double* gwb = s_u.wb;
-        for (int e = threadIdx.x; e < XROWS * n; e += blockDim.x) s_xs[e] = gxs[e] * BQO_PRESCALE;
-        for (int e = threadIdx.x; e < n; e += blockDim.x) {
-            s_wa[e] = gwa[e];
-            s_wb[e] = gwb[e];
+        if (WD) {
+            for (int e = threadIdx.x; e < DX * n; e += blockDim.x) {
+                const int l = e / n, j = e - l * n;  // coalesced global reads
+                s_xs[(size_t)j * RECLD + l] = gxs[e] * BQO_PRESCALE;
+            }
+            for (int j = threadIdx.x; j < n; j += blockDim.x) {
+                s_xs[(size_t)j * RECLD + DX] = gwa[j];
+                s_xs[(size_t)j * RECLD + DX + 1] = gwb[j];
+            }
+        } else {
+            for (int e = threadIdx.x; e < XROWS * n; e += blockDim.x)
+                s_xs[e] = gxs[e] * BQO_PRESCALE;
+            for (int e = threadIdx.x; e < n; e += blockDim.x) {
+                s_wa[e] = gwa[e];
+                s_wb[e] = gwb[e];
+            }
         }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -991,7 +1009,8 @@ __global__ void __launch_bounds__(IM_WARPS * 32, 1)
 
 static size_t inner_smem_bytes(const bqo_stage_c* pb, const bqo_inner_opt* opt, bool stage,
                                size_t state_bytes, bool wd = false) {
-    const int D = wd ? pb->dx : pb->dx + pb->dw;  // staged coordinate rows
+    // staged doubles per training point: D + 2 rows, or one record of odd length with the table
+    const int D = wd ? (((pb->dx + 2) | 1) - 2) : pb->dx + pb->dw;
     const int M = pb->dw > 0 ? pb->M : 1;
     const int NV = 1 << pb->dx;
     const int n_pre = opt->n_starts + (opt->use_vertices ? NV : 0);

@@ -38,11 +38,11 @@ if ROOT not in sys.path:
 N_TRAIN, DX, DW = 2048, 4, 2
 N_HYPER, N_Z, M_W, N_WSETS = 20, 100, 10, 8
 N_CAND_TOTAL = 10000
-# 111 x 20 = 2220 units = 15 per SM; with 50 Z samples per CTA the inner maximiser runs 4440 CTAs =
-# 30 per SM (sweeps of {37,74,111,148} x {20,25,34,50,100} in profiles/r01_tuning_sweeps.md)
+# 111 x 20 = 2220 units = 15 per SM; one CTA per unit (all 100 Z samples): 2220 CTAs = 15 per SM
+# (sweeps of {37,74,111,148} x {20,25,34,50,100} in profiles/r01_tuning_sweeps.md)
 CAND_PER_STEP = int(os.environ.get("BQO_CAND_PER_STEP", "111"))
 N_RESTARTS_MC, MAXITER_MC, FACTR_MC = 5, 10, 1e12  # bgo() defaults, sbo/services/bgo.py:43-44
-Z_PER_CTA = int(os.environ.get("BQO_Z_PER_CTA", "50"))
+Z_PER_CTA = int(os.environ.get("BQO_Z_PER_CTA", "100"))
 
 
 def make_workload(seed_shift=0):
