@@ -1061,9 +1061,12 @@ extern "C" int bqo_inner_maximize_batched(const bqo_stage_c* pb, const bqo_inner
                 LAUNCH_IM_K(DXV, DWV, true, (DWV > 0 ? 10 : 0), false, sb);                      \
             else LAUNCH_IM_K(DXV, DWV, true, 0, false, sb);                                      \
         } else {                                                                                 \
+            /* training set too large for shared memory: operands stream from L2; the      */  \
+            /* unrolled W loop and the distance table still apply                            */  \
             sb = inner_smem_bytes(pb, opt, false, sizeof(RunState<DXV>));                        \
             if (sb > 227 * 1024) return -2;                                                      \
-            LAUNCH_IM_K(DXV, DWV, false, 0, false, sb);                                          \
+            if (use_wd) LAUNCH_IM_K(DXV, DWV, false, (DWV > 0 ? 10 : 0), (DWV > 0), sb);         \
+            else LAUNCH_IM_K(DXV, DWV, false, 0, false, sb);                                     \
         }                                                                                        \
     } while (0)
     SC_DISPATCH(pb, LAUNCH_IM);
