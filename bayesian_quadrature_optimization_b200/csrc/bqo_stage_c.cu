@@ -149,7 +149,7 @@ struct UnitCtx {
     const double* xs;   // [(DX+DW)][ldx] scaled training coordinates (global or shared)
     const double* wa;   // [n] weights of a (alpha, q-weighted for PRODUCT)
     const double* wb;   // [n] weights of b (s2, q-weighted for PRODUCT)
-    const double* tab;  // shared-memory table 2^(j/32) of the fast exp
+    const double* tab;  // shared-memory exp table of the fast evaluation (bqo_common.cuh)
     int ldx;            // stride between coordinate rows of xs
     int n;
     int M;
