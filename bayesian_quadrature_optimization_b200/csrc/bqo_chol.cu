@@ -206,6 +206,10 @@ __global__ void __launch_bounds__(128) potrf_panel_kernel(double* __restrict__ A
     }
 }
 
+#ifndef POTRF_SYRK_STAGES
+#define POTRF_SYRK_STAGES 2  // K <= 256 here: a short pipeline and one more resident CTA per SM
+#endif
+#define SMEM_POTRF_SYRK ((size_t)(2 * BQO_OPER_BUF_DOUBLES(POTRF_SYRK_STAGES)) * sizeof(double))
 // Trailing update A[i][j] -= sum_{k < K} L[i][kc+k] L[j][kc+k] on the lower tiles of the square
 // that starts at row/column `base`; only the first `ncolblk` block columns of it are touched
 // (1 = the strip that the second panel of a 128-wide step needs, all = the full update).
@@ -214,7 +218,7 @@ __global__ void __launch_bounds__(128) potrf_syrk_kernel(double* __restrict__ A,
                                                          const int* __restrict__ info) {
     extern __shared__ double dyn_smem[];
     double* Asm = dyn_smem;
-    double* Bsm = Asm + BQO_OPER_TILE_DOUBLES;
+    double* Bsm = Asm + BQO_OPER_BUF_DOUBLES(POTRF_SYRK_STAGES);
     const int s = blockIdx.z;
     if (info[s] != 0) return;
     const int bi = blockIdx.y, bj = blockIdx.x;
@@ -225,8 +229,8 @@ __global__ void __launch_bounds__(128) potrf_syrk_kernel(double* __restrict__ A,
     const int rj = (n - j0 < NB) ? n - j0 : NB;
     BqoAcc acc;
     acc.zero();
-    bqo_gemm_tile<true, true>(acc, As + (int64_t)i0 * n + kc, n, ri, As + (int64_t)j0 * n + kc, n,
-                              rj, K, Asm, Bsm);
+    bqo_gemm_tile<true, true, POTRF_SYRK_STAGES>(acc, As + (int64_t)i0 * n + kc, n, ri,
+                                                 As + (int64_t)j0 * n + kc, n, rj, K, Asm, Bsm);
     bqo_acc_foreach(acc, [&](int r, int c, double& v) {
         if (r < ri && c < rj) As[(int64_t)(i0 + r) * n + (j0 + c)] -= v;
     });
@@ -251,14 +255,18 @@ __global__ void potrf_finish_kernel(double* __restrict__ A, int n, const int* __
 }
 
 #define SMEM_LS ((size_t)NB * LDT * sizeof(double))
-#define SMEM_SYRK ((size_t)(2 * BQO_OPER_TILE_DOUBLES) * sizeof(double))
-#define SMEM_TRSM ((size_t)(2 * BQO_OPER_TILE_DOUBLES + 2 * NB * LDT) * sizeof(double))
+#define SMEM_SYRK ((size_t)(2 * BQO_OPER_BUF_DOUBLES(BQO_GEMM_STAGES)) * sizeof(double))
+// the solves keep two CTAs per SM: two pipeline stages next to their two 64x64 work tiles
+#define TRSM_STAGES 2
+#define SMEM_TRSM ((size_t)(2 * BQO_OPER_BUF_DOUBLES(TRSM_STAGES) + 2 * NB * LDT) * sizeof(double))
 
 #ifndef POTRF_W
 #define POTRF_W 4
 #endif
 static int potrf_launch(double* A, int n, int S, int* info, cudaStream_t cs) {
     const int nb = (n + NB - 1) / NB;
+    cudaFuncSetAttribute(potrf_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)SMEM_POTRF_SYRK);
     double* diag_scratch = nullptr;
     cudaError_t e = cudaMallocAsync((void**)&diag_scratch, sizeof(double) * (size_t)S * nb * NB * NB, cs);
     if (e != cudaSuccess) return (int)e;
@@ -278,7 +286,7 @@ static int potrf_launch(double* A, int n, int S, int* info, cudaStream_t cs) {
         const int tr = (n - base + NB - 1) / NB;
         if (tr <= 0) return;
         dim3 sg(ncolblk < tr ? ncolblk : tr, tr, S);
-        potrf_syrk_kernel<<<sg, 128, SMEM_SYRK, cs>>>(A, n, kc, K, base, ncolblk, info);
+        potrf_syrk_kernel<<<sg, 128, SMEM_POTRF_SYRK, cs>>>(A, n, kc, K, base, ncolblk, info);
     };
     // POTRF_W 64-wide panels per step.  Panel p of a step first receives, as a one-block-column
     // strip, the update of the p panels before it (K = 64 p); the full trailing update then runs
@@ -320,8 +328,8 @@ __global__ void __launch_bounds__(128) trsm_kernel(const double* __restrict__ L,
                                                    int identity_rhs) {
     extern __shared__ double dyn_smem[];
     double* Asm = dyn_smem;
-    double* Bsm = Asm + BQO_OPER_TILE_DOUBLES;
-    double* Ts = Bsm + BQO_OPER_TILE_DOUBLES;
+    double* Bsm = Asm + BQO_OPER_BUF_DOUBLES(TRSM_STAGES);
+    double* Ts = Bsm + BQO_OPER_BUF_DOUBLES(TRSM_STAGES);
     double* Ls = Ts + NB * LDT;
     const int s = blockIdx.y;
     const double* Lm = L + (int64_t)s * n * n;
@@ -341,14 +349,16 @@ __global__ void __launch_bounds__(128) trsm_kernel(const double* __restrict__ L,
             int kstart = identity_rhs ? kb_begin * NB : 0;
             // acc[r][c] = sum_{k<k0} Y[r][k] L[k0+c][k]
             if (k0 > kstart)
-                bqo_gemm_tile<true, true>(acc, Bs_ + kstart, n, rv, Lm + (int64_t)k0 * n + kstart,
-                                          n, kv, k0 - kstart, Asm, Bsm);
+                bqo_gemm_tile<true, true, TRSM_STAGES>(acc, Bs_ + kstart, n, rv,
+                                                       Lm + (int64_t)k0 * n + kstart, n, kv,
+                                                       k0 - kstart, Asm, Bsm);
         } else {
             // acc[r][c] = sum_{k>=k0+NB} X[r][k] L[k][k0+c]
             int kk = k0 + NB;
             if (kk < n)
-                bqo_gemm_tile<true, false>(acc, Bs_ + kk, n, rv, Lm + (int64_t)kk * n + k0, n, kv,
-                                           n - kk, Asm, Bsm);
+                bqo_gemm_tile<true, false, TRSM_STAGES>(acc, Bs_ + kk, n, rv,
+                                                        Lm + (int64_t)kk * n + k0, n, kv, n - kk,
+                                                        Asm, Bsm);
         }
         __syncthreads();
         bqo_acc_foreach(acc, [&](int r, int c, double& v) {
@@ -720,7 +730,7 @@ __global__ void __launch_bounds__(128) tri_inv_level_kernel(const double* __rest
                                                             int pairs) {
     extern __shared__ double dyn_smem[];
     double* Asm = dyn_smem;
-    double* Bsm = Asm + BQO_OPER_TILE_DOUBLES;
+    double* Bsm = Asm + BQO_OPER_BUF_DOUBLES(BQO_GEMM_STAGES);
     const int s = blockIdx.z / pairs;
     const int pair = blockIdx.z % pairs;
     const int o = pair * 2 * b;
@@ -760,7 +770,7 @@ __global__ void __launch_bounds__(128) inv_syrk_kernel(const double* __restrict_
                                                        double* __restrict__ Inv) {
     extern __shared__ double dyn_smem[];
     double* Asm = dyn_smem;
-    double* Bsm = Asm + BQO_OPER_TILE_DOUBLES;
+    double* Bsm = Asm + BQO_OPER_BUF_DOUBLES(BQO_GEMM_STAGES);
     const int s = blockIdx.z;
     const int ba = blockIdx.y, bb = blockIdx.x;
     if (bb > ba) return;
@@ -790,6 +800,12 @@ int bqo_internal_inverse_from_chol(const double* L, int n, int S, double* Inv, d
                              (int)smem_diag);
         attr_done = true;
     }
+    cudaFuncSetAttribute(tri_inv_level_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)SMEM_SYRK);
+    cudaFuncSetAttribute(tri_inv_level_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)SMEM_SYRK);
+    cudaFuncSetAttribute(inv_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)SMEM_SYRK);
     dim3 dg(nb, S);
     tri_inv_diag_kernel<<<dg, NB, smem_diag, cs>>>(L, n, Wbuf);
     for (int b = NB; b < n; b *= 2) {

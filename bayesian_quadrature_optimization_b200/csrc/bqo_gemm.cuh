@@ -127,35 +127,84 @@ __device__ __forceinline__ void bqo_commit_oper(double* __restrict__ sm, const d
     }
 }
 
+// ---- cp.async staging ----------------------------------------------------------------------
+// One 64 x 16 operand tile per stage; every thread copies its 8 elements with 8-byte cp.async
+// (zero fill outside the valid rows / k), the same element-to-thread map as bqo_fetch_oper.
+__device__ __forceinline__ void bqo_cp_async8(double* smem_dst, const double* gsrc, bool valid) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int bytes = valid ? 8 : 0;  // src-size 0: the 8 destination bytes are zero filled
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(dst), "l"(gsrc), "r"(bytes));
+}
+
+template <bool KCONTIG>
+__device__ __forceinline__ void bqo_stage_oper(double* __restrict__ sm,
+                                               const double* __restrict__ base, int64_t ld,
+                                               int rows_valid, int k_valid) {
+    const int t = threadIdx.x;
+    if (KCONTIG) {
+        const int row = t >> 1, kh = (t & 1) * 8;
+        const bool rv = row < rows_valid;
+        const double* src = base + (int64_t)(rv ? row : 0) * ld;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+            const int k = kh + kk;
+            const bool ok = rv && k < k_valid;
+            bqo_cp_async8(sm + row * BQO_LDK + k, src + (ok ? k : 0), ok);
+        }
+    } else {
+        const int k = t >> 3, r0 = (t & 7) * 8;
+        const bool kv = k < k_valid;
+        const double* src = base + (int64_t)(kv ? k : 0) * ld;
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+            const int row = r0 + rr;
+            const bool ok = kv && row < rows_valid;
+            bqo_cp_async8(sm + k * BQO_LDR + row, src + (ok ? row : 0), ok);
+        }
+    }
+}
+
+#define BQO_GEMM_STAGES 3
+#define BQO_OPER_BUF_DOUBLES(ST) ((ST) * BQO_OPER_TILE_DOUBLES)
+
 // Full K loop: acc += sum_k A(row,k) B(col,k).  As/Bs: shared operand buffers of
-// BQO_OPER_TILE_DOUBLES doubles each.  A(row,k) at A[row*lda + k] (A_KCONTIG) or A[k*lda + row];
-// likewise for B with its own leading dimension.  Software pipelined: slab k+1 is fetched into
-// registers before the DMMAs of slab k are issued.
-template <bool A_KCONTIG, bool B_KCONTIG>
+// BQO_OPER_BUF_DOUBLES(STAGES) doubles each.  A(row,k) at A[row*lda + k] (A_KCONTIG) or
+// A[k*lda + row]; likewise for B with its own leading dimension.
+// STAGES-deep cp.async pipeline, one barrier per slab: the copies of slab i + STAGES - 1 are in
+// flight while the DMMAs of slab i execute (the first version prefetched ONE slab into registers
+// and ran the DMMA sub-pipe at 56 % with 0.18 eligible warps per cycle, long-scoreboard bound).
+// All copies have landed and been consumed when the function returns; callers that reuse the
+// buffers must still separate two calls with a __syncthreads().
+template <bool A_KCONTIG, bool B_KCONTIG, int STAGES = BQO_GEMM_STAGES>
 __device__ __forceinline__ void bqo_gemm_tile(BqoAcc& acc, const double* __restrict__ A,
                                               int64_t lda, int a_rows, const double* __restrict__ B,
                                               int64_t ldb, int b_rows, int K, double* As,
                                               double* Bs) {
     if (K <= 0) return;
-    double ra[8], rb[8];
-    {
-        int kv = K < BQO_BK ? K : BQO_BK;
-        bqo_fetch_oper<A_KCONTIG>(ra, A, lda, a_rows, kv);
-        bqo_fetch_oper<B_KCONTIG>(rb, B, ldb, b_rows, kv);
-    }
-    for (int k0 = 0; k0 < K; k0 += BQO_BK) {
-        __syncthreads();  // previous slab's fragments have been read
-        bqo_commit_oper<A_KCONTIG>(As, ra);
-        bqo_commit_oper<B_KCONTIG>(Bs, rb);
-        __syncthreads();
-        const int kn = k0 + BQO_BK;
-        if (kn < K) {
-            int kv = K - kn < BQO_BK ? K - kn : BQO_BK;
-            bqo_fetch_oper<A_KCONTIG>(ra, A_KCONTIG ? A + kn : A + (int64_t)kn * lda, lda, a_rows, kv);
-            bqo_fetch_oper<B_KCONTIG>(rb, B_KCONTIG ? B + kn : B + (int64_t)kn * ldb, ldb, b_rows, kv);
+    const int nslab = (K + BQO_BK - 1) / BQO_BK;
+    auto issue = [&](int slab) {
+        if (slab < nslab) {
+            const int k0 = slab * BQO_BK;
+            const int kv = K - k0 < BQO_BK ? K - k0 : BQO_BK;
+            const int st = slab % STAGES;
+            bqo_stage_oper<A_KCONTIG>(As + st * BQO_OPER_TILE_DOUBLES,
+                                      A_KCONTIG ? A + k0 : A + (int64_t)k0 * lda, lda, a_rows, kv);
+            bqo_stage_oper<B_KCONTIG>(Bs + st * BQO_OPER_TILE_DOUBLES,
+                                      B_KCONTIG ? B + k0 : B + (int64_t)k0 * ldb, ldb, b_rows, kv);
         }
-        bqo_mma_slab<A_KCONTIG, B_KCONTIG>(acc, As, Bs);
+        asm volatile("cp.async.commit_group;\n" ::);  // (possibly empty: keeps the group count)
+    };
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) issue(s);
+    for (int slab = 0; slab < nslab; ++slab) {
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(STAGES - 2));  // slab `slab` has landed
+        __syncthreads();  // ... for every thread, and slab - 1's buffer is free again
+        issue(slab + STAGES - 1);
+        const int st = slab % STAGES;
+        bqo_mma_slab<A_KCONTIG, B_KCONTIG>(acc, As + st * BQO_OPER_TILE_DOUBLES,
+                                           Bs + st * BQO_OPER_TILE_DOUBLES);
     }
+    asm volatile("cp.async.wait_group 0;\n" ::);
 }
 
 // Visit the accumulator entries of this thread: f(row, col, value_ref) with tile-local row/col.
