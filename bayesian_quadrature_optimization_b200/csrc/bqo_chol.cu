@@ -143,7 +143,7 @@ template <int MODE>
 __global__ void __launch_bounds__(128) potrf_panel_kernel(double* __restrict__ A, int n, int k0,
                                                           int* __restrict__ info,
                                                           double* __restrict__ diag_scratch) {
-    extern __shared__ double dyn_smem[];
+    extern __shared__ __align__(16) double dyn_smem[];
     double* Ls = dyn_smem;
     __shared__ int flag;
     __shared__ double rdiag[NB];
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(128) potrf_panel_kernel(double* __restrict__ A
 __global__ void __launch_bounds__(128) potrf_syrk_kernel(double* __restrict__ A, int n, int kc, int K,
                                                          int base, int ncolblk,
                                                          const int* __restrict__ info) {
-    extern __shared__ double dyn_smem[];
+    extern __shared__ __align__(16) double dyn_smem[];
     double* Asm = dyn_smem;
     double* Bsm = Asm + BQO_OPER_BUF_DOUBLES(POTRF_SYRK_STAGES);
     const int s = blockIdx.z;
@@ -326,7 +326,7 @@ template <bool FORWARD>
 __global__ void __launch_bounds__(128) trsm_kernel(const double* __restrict__ L, int n,
                                                    double* __restrict__ Bt, int m,
                                                    int identity_rhs) {
-    extern __shared__ double dyn_smem[];
+    extern __shared__ __align__(16) double dyn_smem[];
     double* Asm = dyn_smem;
     double* Bsm = Asm + BQO_OPER_BUF_DOUBLES(TRSM_STAGES);
     double* Ts = Bsm + BQO_OPER_BUF_DOUBLES(TRSM_STAGES);
@@ -427,7 +427,7 @@ template <bool FORWARD>
 __global__ void __launch_bounds__(TRSV_THREADS) trsv_kernel(const double* __restrict__ L, int n,
                                                             double* __restrict__ Bt, int m, int r0,
                                                             int r1) {
-    extern __shared__ double dyn_smem[];
+    extern __shared__ __align__(16) double dyn_smem[];
     double* xs = dyn_smem;                         // [nb * NB] the vector (zero padded)
     const int nb = (n + NB - 1) / NB;
     double* Ls = xs + (size_t)nb * NB;             // [NB][LDT] diagonal block
@@ -684,7 +684,7 @@ int bqo_internal_inverse_from_chol(const double* L, int n, int S, double* Inv, d
 
 __global__ void __launch_bounds__(NB) tri_inv_diag_kernel(const double* __restrict__ L, int n,
                                                           double* __restrict__ W) {
-    extern __shared__ double dyn_smem[];
+    extern __shared__ __align__(16) double dyn_smem[];
     double* Ls = dyn_smem;
     double* Ws = Ls + NB * LDT;
     const int s = blockIdx.y;
@@ -728,7 +728,7 @@ __global__ void __launch_bounds__(128) tri_inv_level_kernel(const double* __rest
                                                             double* __restrict__ W,
                                                             double* __restrict__ T, int n, int b,
                                                             int pairs) {
-    extern __shared__ double dyn_smem[];
+    extern __shared__ __align__(16) double dyn_smem[];
     double* Asm = dyn_smem;
     double* Bsm = Asm + BQO_OPER_BUF_DOUBLES(BQO_GEMM_STAGES);
     const int s = blockIdx.z / pairs;
@@ -768,7 +768,7 @@ __global__ void __launch_bounds__(128) tri_inv_level_kernel(const double* __rest
 // upper tiles of Inv are NOT written.
 __global__ void __launch_bounds__(128) inv_syrk_kernel(const double* __restrict__ W, int n,
                                                        double* __restrict__ Inv) {
-    extern __shared__ double dyn_smem[];
+    extern __shared__ __align__(16) double dyn_smem[];
     double* Asm = dyn_smem;
     double* Bsm = Asm + BQO_OPER_BUF_DOUBLES(BQO_GEMM_STAGES);
     const int s = blockIdx.z;
