@@ -114,31 +114,6 @@ extern "C" int bqo_scale_points(const bqo_kernel_desc* desc, const double* hyp, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Exp table of the fast Matern evaluation (bqo_common.cuh) in global memory for the kernels whose
-// CTAs are too small to build their own copy in shared memory: 16 KB, L1/L2 resident.  Filled once
-// per device by the first assembly call.
-__device__ double bqo_g_exp_tab[BQO_EXP_TABLE];
-
-__global__ void exp_table_global_init_kernel() {
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < BQO_EXP_TABLE; j += gridDim.x * blockDim.x)
-        bqo_g_exp_tab[j] = exp2(-(double)j / (double)BQO_EXP_TABLE) * BQO_TAB_FOLD;
-}
-
-struct GlobalExpTab {
-    __device__ __forceinline__ double operator()(unsigned m) const {
-        return __ldg(&bqo_g_exp_tab[m & (unsigned)(BQO_EXP_TABLE - 1)]);
-    }
-};
-
-static void ensure_global_exp_table(cudaStream_t cs) {
-    static bool done[64] = {false};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || done[dev]) return;
-    exp_table_global_init_kernel<<<8, 256, 0, cs>>>();
-    done[dev] = true;
-}
-
 // K[s][i][j].  32x32 tiles, 4 rows per thread; column reads of the SoA Xs are coalesced, row
 // reads broadcast.  The Matern factor goes through the fast evaluation (HBM-write bound at
 // n = 2048: 671 MB per 20 hyper-samples; with libm exp/sqrt the kernel was instruction bound at
@@ -207,7 +182,7 @@ extern "C" int bqo_kernel_assemble_batched(const bqo_kernel_desc* desc, const do
     dim3 grid((n + 31) / 32, (n + 31) / 32, S);
     int64_t st = bqo_hyper_stride_impl(*desc);
     cudaStream_t cs = (cudaStream_t)stream;
-    ensure_global_exp_table(cs);
+    bqo_ensure_global_exp_table(cs);
 #define LAUNCH_ASM(DMV)                                                                          \
     assemble_kernel<DMV><<<grid, block, 0, cs>>>(*desc, hyp, st, Xs, tid, n, noise_obs,          \
                                                  add_noise, extra_diag, K)

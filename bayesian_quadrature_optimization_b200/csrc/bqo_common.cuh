@@ -257,6 +257,31 @@ __device__ __forceinline__ void bqo_matern52_q_v(const double (&u2)[NV], Tab tab
     }
 }
 
+// Exp table of the fast evaluation in global memory, for kernels whose CTAs are too small to
+// build their own copy in shared memory: 16 KB, L1/L2 resident.  One copy per translation unit
+// that uses it, filled once per device by the first launch that needs it.
+static __device__ double bqo_g_exp_tab[BQO_EXP_TABLE];
+
+static __global__ void bqo_exp_table_global_init_kernel() {
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < BQO_EXP_TABLE; j += gridDim.x * blockDim.x)
+        bqo_g_exp_tab[j] = exp2(-(double)j / (double)BQO_EXP_TABLE) * BQO_TAB_FOLD;
+}
+
+struct GlobalExpTab {
+    __device__ __forceinline__ double operator()(unsigned m) const {
+        return __ldg(&bqo_g_exp_tab[m & (unsigned)(BQO_EXP_TABLE - 1)]);
+    }
+};
+
+static inline void bqo_ensure_global_exp_table(cudaStream_t cs) {
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || done[dev]) return;
+    bqo_exp_table_global_init_kernel<<<8, 256, 0, cs>>>();
+    done[dev] = true;
+}
+
 __device__ __forceinline__ double bqo_warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -29,8 +29,8 @@ __global__ void __launch_bounds__(256)
                                double* __restrict__ Wtask) {
     __shared__ double red[32];
     const int s = blockIdx.z;
-    const int j = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int i0 = blockIdx.y * 32 + (threadIdx.x >> 5) * 4;
+    const int by = (int)gridDim.y - 1 - (int)blockIdx.y;  // longest rows of tiles first
+    const int i0 = by * 32 + (threadIdx.x >> 5) * 4;
     const double* h = hyp + (int64_t)s * stride;
     const double* xs = Xs + (int64_t)s * d.dim_m * n;
     const double* inv = Inv + (int64_t)s * n * n;
@@ -44,8 +44,12 @@ __global__ void __launch_bounds__(256)
     // strictly lower ones with weight 2 (the task-pair sums are used symmetrised downstream).
     // Inv is only defined on those tiles (bqo_internal_inverse_from_chol stores 64x64 lower
     // tiles; a 32x32 tile on or below the diagonal always lies inside one of them).
-    const double wsym = (blockIdx.x < blockIdx.y) ? 2.0 : 1.0;
-    if (j < n && blockIdx.x <= blockIdx.y) {
+    // A CTA walks one row of tiles, so the eleven block reductions below are paid once per
+    // row of tiles and not once per tile (they dominated the kernel).
+    for (int bx = 0; bx <= by; ++bx) {
+    const int j = bx * 32 + (threadIdx.x & 31);
+    const double wsym = (bx < by) ? 2.0 : 1.0;
+    if (j < n) {
         double xj[BQO_MAX_DIM];
         for (int l = 0; l < dm; ++l) xj[l] = xs[(int64_t)l * n + j];
         const double aj = al[j];
@@ -60,8 +64,16 @@ __global__ void __launch_bounds__(256)
                 df[l] = xs[(int64_t)l * n + i] - xj[l];
                 r2 = fma(df[l], df[l], r2);
             }
-            double km, g;
-            bqo_matern52_kg(r2, km, g);
+            // fast evaluation (bqo_common.cuh): e = exp(-sqrt5 r), u = K r
+            double km = 1.0, g = -BQO_FIVE_THIRDS;
+            if (i != j) {
+                double u2v[1], ev[1], uv[1];
+                u2v[0] = fma(r2, BQO_PRESCALE * BQO_PRESCALE, 1e-300);
+                bqo_matern52_q_v<1>(u2v, GlobalExpTab(), ev, uv);
+                const double lin = fma(uv[0], BQO_LN2_N, 1.0) * ev[0];  // (1 + sqrt5 r) e
+                km = fma(u2v[0] * ev[0], BQO_H_TO_K, lin);
+                g = -BQO_FIVE_THIRDS * lin;                             // k'(r) / r
+            }
             double other = 1.0;
             int ti = 0;
             if (d.kind == BQO_KIND_SCALED_MATERN52) other = h[BQO_H_SIGMA2];
@@ -85,8 +97,9 @@ __global__ void __launch_bounds__(256)
             }
         }
     }
-    const int nblk = gridDim.x * gridDim.y;
-    const int blk = blockIdx.y * gridDim.x + blockIdx.x;
+    }  // row of tiles
+    const int nblk = gridDim.y;
+    const int blk = by;
     for (int q = 0; q < nacc; ++q) {
         double tot = bqo_block_sum(acc[q], red);
         if (threadIdx.x == 0) partial[((int64_t)s * nacc + q) * nblk + blk] = tot;
@@ -186,11 +199,11 @@ extern "C" int bqo_loglik_grad_batched(const bqo_kernel_desc* desc, const double
     if (rc) return rc;
     if (desc->kind == BQO_KIND_PRODUCT_TASKS && !desc->same_corr)
         cudaMemsetAsync(Wtask, 0, sizeof(double) * S * desc->n_tasks * desc->n_tasks, cs);
-    dim3 grid(nb, nb, S);
+    dim3 grid(1, nb, S);
     const int64_t st = bqo_hyper_stride_impl(*desc);
+    bqo_ensure_global_exp_table(cs);
     loglik_grad_partial_kernel<<<grid, 256, 0, cs>>>(*desc, hyp, st, Xs, tid, n, Inv, alpha, partial,
                                                      Wtask);
-    loglik_grad_final_kernel<<<S, 256, 0, cs>>>(*desc, hyp, st, partial, (int)nblk, alpha, n, Wtask,
-                                                grad);
+    loglik_grad_final_kernel<<<S, 256, 0, cs>>>(*desc, hyp, st, partial, nb, alpha, n, Wtask, grad);
     BQO_RETURN_LAST_ERROR();
 }
