@@ -445,14 +445,17 @@ __global__ void __launch_bounds__(TRSV_THREADS) trsv_kernel(const double* __rest
          kb += FORWARD ? 1 : -1) {
         const int k0 = kb * NB;
         const int kv = (n - k0 < NB) ? n - k0 : NB;
-        // diagonal block (and the reciprocals of its diagonal) into shared memory
+        // diagonal block (and the reciprocals of its diagonal) into shared memory; the backward
+        // walk loads it one block ahead, behind the elimination step of the previous block
+        if (FORWARD || kb == kb1 - 1) {
 #pragma unroll
-        for (int e = t; e < NB * NB; e += TRSV_THREADS) {
-            int r = e / NB, c = e % NB;
-            double v = 0.0;
-            if (r < kv && c <= r) v = Lm[(int64_t)(k0 + r) * n + (k0 + c)];
-            Ls[r * LDT + c] = v;
-            if (r == c) rd[r] = (r < kv) ? 1.0 / v : 1.0;
+            for (int e = t; e < NB * NB; e += TRSV_THREADS) {
+                int r = e / NB, c = e % NB;
+                double v = 0.0;
+                if (r < kv && c <= r) v = Lm[(int64_t)(k0 + r) * n + (k0 + c)];
+                Ls[r * LDT + c] = v;
+                if (r == c) rd[r] = (r < kv) ? 1.0 / v : 1.0;
+            }
         }
         if (FORWARD && k0 > r0) {
             // rows k0 + warp*TRSV_ROWS + q: acc_q = sum_{c < k0} L[row][c] y[c]
@@ -515,20 +518,45 @@ __global__ void __launch_bounds__(TRSV_THREADS) trsv_kernel(const double* __rest
         }
         __syncthreads();
         if (!FORWARD && k0 > r0) {
-            // y[c] -= sum_j L[k0 + j][c] x[k0 + j] for every column r0 <= c < k0
-            for (int c = r0 + t; c < k0; c += TRSV_THREADS) {
-                double a0 = 0.0, a1 = 0.0;
-                const double* lc = Lm + (int64_t)k0 * n + c;
-                int j = 0;
-#pragma unroll 8
-                for (; j + 1 < kv; j += 2) {
-                    a0 = fma(lc[(int64_t)j * n], xs[k0 + j], a0);
-                    a1 = fma(lc[(int64_t)(j + 1) * n], xs[k0 + j + 1], a1);
-                }
-                if (j < kv) a0 = fma(lc[(int64_t)j * n], xs[k0 + j], a0);
-                xs[c] -= a0 + a1;
+            // next diagonal block: its global loads go out first, the stores follow the
+            // elimination below (the block just solved is not read any more)
+            const int kn0 = k0 - NB;  // a full block: kn0 >= r0
+            double nv[NB * NB / TRSV_THREADS];
+#pragma unroll
+            for (int q = 0; q < NB * NB / TRSV_THREADS; ++q) {
+                const int e = t + q * TRSV_THREADS;
+                const int r = e / NB, c = e % NB;
+                nv[q] = (c <= r) ? Lm[(int64_t)(kn0 + r) * n + (kn0 + c)] : 0.0;
             }
-            __syncthreads();
+            // y[c] -= sum_j L[k0 + j][c] x[k0 + j] for every column r0 <= c < k0: the CTA
+            // covers 128 columns x 4 row groups at a time, all loads of a thread in flight
+            __shared__ double part[4][128];
+            const int tx = t & 127, ty = t >> 7;
+            for (int c0 = r0; c0 < k0; c0 += 128) {
+                const int c = c0 + tx;
+                double a0 = 0.0, a1 = 0.0;
+                if (c < k0) {
+                    const double* lc = Lm + (int64_t)(k0 + ty * 16) * n + c;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 2) {
+                        const int jj = ty * 16 + j;
+                        if (jj < kv) a0 = fma(lc[(int64_t)j * n], xs[k0 + jj], a0);
+                        if (jj + 1 < kv) a1 = fma(lc[(int64_t)(j + 1) * n], xs[k0 + jj + 1], a1);
+                    }
+                }
+                part[ty][tx] = a0 + a1;
+                __syncthreads();
+                if (ty == 0 && c < k0)
+                    xs[c] -= (part[0][tx] + part[1][tx]) + (part[2][tx] + part[3][tx]);
+                __syncthreads();
+            }
+#pragma unroll
+            for (int q = 0; q < NB * NB / TRSV_THREADS; ++q) {
+                const int e = t + q * TRSV_THREADS;
+                const int r = e / NB, c = e % NB;
+                Ls[r * LDT + c] = nv[q];
+                if (r == c) rd[r] = 1.0 / nv[q];
+            }
         }
     }
     for (int i = r0 + t; i < r1; i += TRSV_THREADS) b[i] = xs[i];
