@@ -125,7 +125,22 @@ def _gloo_worker(rank, world_size, port, out):
                                 torch.tensor(pts[lo + loc]))
     part = torch.tensor(values[lo:hi].sum()).reshape(1)
     tot = D.allgather_ordered_sum(part)
-    out.put((rank, v, gi, p.tolist(), float(tot[0])))
+
+    # hyper-sample partition: a stand-in engine whose per-hyper-sample scores are known
+    thetas = np.arange(5 * 3, dtype=float).reshape(5, 3)
+
+    class FakeBQ(object):
+        def __init__(self, th):
+            self.th = th
+
+        def evaluate_candidates(self, cands, z, starts, max_mean=None, **kw):
+            per = torch.tensor(self.th.sum(1))[:, None] * torch.tensor(cands.sum(1))[None, :]
+            return {"evaluations": per.mean(0), "gradient": per.mean(0)[:, None] * torch.ones(1, 2)}
+
+    cands = rng.uniform(0, 1, (4, 2))
+    res = D.evaluate_candidates_hyper_sharded(lambda th: FakeBQ(th), thetas, cands, None, None)
+    out.put((rank, v, gi, p.tolist(), float(tot[0]), res["evaluations"].tolist(),
+             res["gradient"].tolist(), res["argmax"]))
     dist.destroy_process_group()
 
 
@@ -143,10 +158,18 @@ def test_world_size_two_gloo_selection():
     rng = np.random.RandomState(0)
     values = rng.normal(0, 1, 11)
     values[3] = values[9] = values.max() + 1.0
-    for rank, v, gi, p, tot in res:
+    pts = rng.uniform(0, 1, (11, 2))
+    cands = rng.uniform(0, 1, (4, 2))
+    thetas = np.arange(5 * 3, dtype=float).reshape(5, 3)
+    want = (thetas.sum(1)[:, None] * cands.sum(1)[None, :]).mean(0)
+    for rank, v, gi, p, tot, ev, gr, am in res:
         assert gi == 3 and v == values[3]          # np.argmax tie rule: first index
         lo0, hi0 = 0, 6
         assert tot == values[:6].sum() + values[6:].sum()
+        # hyper-samples 3 + 2 over the two ranks: same totals, bit-identical on both ranks
+        assert np.allclose(ev, want, rtol=1e-14) and am == int(np.argmax(want))
+        assert np.allclose(np.array(gr)[:, 0], want, rtol=1e-14)
+    assert res[0][5] == res[1][5] and res[0][6] == res[1][6]
 
 
 def test_host_sgd_matches_oracle_and_handles_unavailable_gradients():
