@@ -74,6 +74,56 @@ def kernel_kind(type_kernel, dimensions, **kernel_parameters):
     raise NameError(type_kernel[0] + " doesn't exist")
 
 
+class _ProbeBatcher(object):
+    """Rendezvous of the chains of sample_parameters_chains: every running chain hands in the
+    parameter vectors it needs next; when all of them wait, ONE batched log-probability call
+    serves everybody (the GPU work is issued by the chain that arrived last)."""
+
+    def __init__(self, model, n_chains):
+        import threading
+        self.model = model
+        self.cond = threading.Condition()
+        self.active = set(range(n_chains))
+        self.pending = {}
+        self.ready = {}
+
+    def _flush(self):
+        order = sorted(self.pending)
+        vectors = [v for c in order for v in self.pending[c]]
+        try:
+            import torch
+            # worker threads start on device 0: make the model's device current for the launch
+            with torch.cuda.device(self.model._engine().device):
+                values = list(self.model.log_prob_parameters_batch(vectors))
+        except BaseException as exc:
+            values = exc
+        k = 0
+        for c in order:
+            m = len(self.pending[c])
+            self.ready[c] = values if isinstance(values, BaseException) else values[k:k + m]
+            k += m
+        self.pending = {}
+        self.cond.notify_all()
+
+    def request(self, cid, vectors):
+        with self.cond:
+            self.pending[cid] = [np.asarray(v, dtype=float) for v in vectors]
+            if set(self.pending) >= self.active:
+                self._flush()
+            while cid not in self.ready:
+                self.cond.wait()
+            out = self.ready.pop(cid)
+        if isinstance(out, BaseException):
+            raise out
+        return out
+
+    def done(self, cid):
+        with self.cond:
+            self.active.discard(cid)
+            if self.pending and set(self.pending) >= self.active:
+                self._flush()
+
+
 class GPFittingGaussian(object):
 
     _possible_kernels_ = [MATERN52_NAME, TASKS_KERNEL_NAME, PRODUCT_KERNELS_SEPARABLE]
@@ -575,13 +625,21 @@ class GPFittingGaussian(object):
         if start_point is None:
             start_point = self.samples_parameters[-1]
         n_sweeps = int(n_samples * (self.thinning + 1))
+        samples = self._slice_sweeps(start_point, n_sweeps, self.slice_samplers)
+        samples_return = samples[::self.thinning + 1]
+        self.samples_parameters += samples_return
+        return samples_return
+
+    def _slice_sweeps(self, start_point, n_sweeps, samplers):
+        """n_sweeps sweeps of the block slice samplers from start_point -> list of points."""
+        from ..samplers.hyper_slice_sampler import separate_vector, combine_vectors
         samples = []
         for _ in range(n_sweeps):
             points = separate_vector(start_point, self.length_scale_indexes)  # [others, ls]
-            if self._two_blocks:
-                blocks = [(self.slice_samplers[0], 0), (self.slice_samplers[1], 1)]
+            if len(samplers) == 2:
+                blocks = [(samplers[0], 0), (samplers[1], 1)]
             else:
-                blocks = [(self.slice_samplers[0], 1)]
+                blocks = [(samplers[0], 1)]
             for sampler, which in blocks:
                 new_point, n_try = None, 0
                 while new_point is None and n_try < 10:
@@ -594,9 +652,65 @@ class GPFittingGaussian(object):
                 points[which] = new_point
             start_point = combine_vectors(points[1], points[0], self.length_scale_indexes)
             samples.append(start_point)
-        samples_return = samples[::self.thinning + 1]
-        self.samples_parameters += samples_return
-        return samples_return
+        return samples
+
+    def sample_parameters_chains(self, n_samples, n_chains=4, start_points=None, random_seed=None,
+                                 burn_in_sweeps=None):
+        """SURVEY 8f item 1, second half: `n_chains` INDEPENDENT slice-sampling chains advanced side
+        by side, their log-probability probes merged into one batched factorisation per round (a
+        batch of 8 matrices costs 1.3x one matrix at n = 2048, profiles/r01_stage_a.md).
+
+        Every chain is the reference's sequential algorithm with a numpy RandomState of its own
+        (seed = random_seed + chain index), so chain c reproduces exactly the chain a single
+        sampler with that RandomState would draw.  Each chain burns in for `burn_in_sweeps`
+        (default: n_burning / (thinning + 1), as start_new_chain does) and then keeps every
+        (thinning + 1)-th point until it has n_samples.  Returns the list of the n_chains *
+        n_samples kept points (chain-major) and appends them to samples_parameters.  This is an
+        extension: the reference runs one chain."""
+        import copy
+        import threading
+        if not self.slice_samplers:
+            self.set_samplers()
+        n_chains = int(n_chains)
+        base_seed = int(random_seed) if random_seed is not None else int(np.random.randint(0, 2 ** 31 - 1))
+        if start_points is None:
+            start_points = [np.array(self.samples_parameters[-1], dtype=float)] * n_chains
+        if burn_in_sweeps is None:
+            burn_in_sweeps = int(float(self.n_burning) / (self.thinning + 1)) if self.n_burning > 0 else 0
+        n_sweeps = int(n_samples * (self.thinning + 1))
+        batcher = _ProbeBatcher(self, n_chains)
+        results = [None] * n_chains
+        errors = []
+
+        def run(cid):
+            try:
+                rng = np.random.RandomState(base_seed + cid)
+                samplers = []
+                for sp in self.slice_samplers:
+                    sc = copy.copy(sp)
+                    sc.rng = rng
+                    sc.log_prob = lambda vector, model, cid=cid: batcher.request(cid, [vector])[0]
+                    sc.log_prob_batch = lambda vectors, model, cid=cid: batcher.request(cid, vectors)
+                    samplers.append(sc)
+                point = np.array(start_points[cid], dtype=float)
+                if burn_in_sweeps > 0:
+                    point = self._slice_sweeps(point, burn_in_sweeps, samplers)[-1]
+                results[cid] = self._slice_sweeps(point, n_sweeps, samplers)[::self.thinning + 1]
+            except BaseException as exc:  # a dead chain must not leave the others waiting
+                errors.append(exc)
+            finally:
+                batcher.done(cid)
+
+        threads = [threading.Thread(target=run, args=(c,)) for c in range(n_chains)]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+        if errors:
+            raise errors[0]
+        kept = [p for chain in results for p in chain]
+        self.samples_parameters += kept
+        return kept
 
     def sample_parameters_posterior(self, n_samples, random_seed=None, start_point=None):
         """:917-931 -> np.array(n_samples, n_parameters)."""

@@ -51,13 +51,16 @@ class SliceSampling(object):
         self.doubling_step = params.get('doubling_step', True)
         self.log_prob_batch = params.get('log_prob_batch')  # optional: (vectors, *args) -> values
         self.speculate = int(params.get('speculate', 4))
+        # random stream: the global numpy one (reference behaviour) or a RandomState of its own
+        # (independent chains running side by side, GPFittingGaussian.sample_parameters_chains)
+        self.rng = params.get('rng', npr)
 
     def slice_sample(self, point, fixed_parameters, *args_log_prob):
         point = np.asarray(point, dtype=float)
         dimensions = len(point)
         if self.component_wise:
             dims = np.arange(dimensions)
-            npr.shuffle(dims)
+            self.rng.shuffle(dims)
             new_point = point.copy()
             for d in dims:
                 if d not in self.ignore_index:
@@ -66,7 +69,7 @@ class SliceSampling(object):
                     new_point = self.direction_slice(direction, new_point, fixed_parameters,
                                                      *args_log_prob)
             return new_point
-        direction = npr.randn(dimensions)
+        direction = self.rng.randn(dimensions)
         for d in self.ignore_index:
             direction[d] = 0.0
         if np.all(direction == 0):
@@ -117,7 +120,7 @@ class SliceSampling(object):
             lp0, lp1 = self.directional_log_probs([lower, upper], direction, point,
                                                   fixed_parameters, *args)
             while (lp0 > llh or lp1 > llh) and (l_out + u_out < self.max_steps_out):
-                if npr.rand() < 0.5:
+                if self.rng.rand() < 0.5:
                     l_out += 1
                     lower -= (upper - lower)
                     lp0 = self.directional_log_prob(lower, direction, point, fixed_parameters, *args)
@@ -145,10 +148,10 @@ class SliceSampling(object):
             if not ahead and self.log_prob_batch is not None and self.speculate > 1:
                 # the next proposals if every one before them is rejected: their positions only
                 # depend on the positions of the rejected ones.  Draw, evaluate together, rewind.
-                state = npr.get_state()
+                state = self.rng.get_state()
                 zs, lo, up = [], lower, upper
                 for _ in range(self.speculate):
-                    z = (up - lo) * npr.rand() + lo
+                    z = (up - lo) * self.rng.rand() + lo
                     zs.append(z)
                     if z < 0:
                         lo = z
@@ -156,9 +159,9 @@ class SliceSampling(object):
                         up = z
                     else:
                         break
-                npr.set_state(state)
+                self.rng.set_state(state)
                 ahead = self.directional_log_probs(zs, direction, point, fixed_parameters, *args)
-            new_z = (upper - lower) * npr.rand() + lower
+            new_z = (upper - lower) * self.rng.rand() + lower
             if ahead:
                 new_llh = ahead.pop(0)
             else:
@@ -177,9 +180,9 @@ class SliceSampling(object):
                 raise Exception("Slice sampler shrank to zero!")
 
     def direction_slice(self, direction, point, fixed_parameters, *args):
-        upper = self.sigma * npr.rand()
+        upper = self.sigma * self.rng.rand()
         lower = upper - self.sigma
-        llh = np.log(npr.rand()) + self.directional_log_prob(0.0, direction, point,
+        llh = np.log(self.rng.rand()) + self.directional_log_prob(0.0, direction, point,
                                                              fixed_parameters, *args)
         if self.step_out:
             upper, lower = self.find_x_interval(llh, lower, upper, direction, point,

@@ -58,3 +58,18 @@ for batched in (True, False):
           "(%.2f ms per call); last sample %s"
           % (batched, n_sweeps, dt, n_sweeps / dt, probes["n"], probes["calls"],
              1e3 * dt / max(1, probes["calls"]), np.array2string(s[-1], precision=4)))
+
+# independent chains side by side (sample_parameters_chains): sweeps per second over all chains
+GPFittingGaussian.batched_slice_probes = True
+for n_chains in (4, 8, 16):
+    gp = GPFittingGaussian([SCALED_KERNEL, MATERN52_NAME], td, [bench.DX + bench.DW],
+                           bounds_domain=bounds, noise=True, kernel_values=list(wl["thetas"][0][2:]),
+                           mean_value=[0.0], var_noise_value=[1e-4], max_steps_out=1000,
+                           random_seed=1)
+    gp.sample_parameters_chains(1, n_chains=n_chains, random_seed=3, burn_in_sweeps=0)  # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    gp.sample_parameters_chains(2, n_chains=n_chains, random_seed=4, burn_in_sweeps=0)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    print("chains=%d: %d sweeps in %.3f s = %.2f sweeps/s" % (n_chains, 2 * n_chains, dt, 2 * n_chains / dt))

@@ -521,3 +521,44 @@ def _argmax_of(sbo, bq, cand, z, th):
                                    maxiter=10, factr=1e12, pgtol=sbo.inner_pgtol,
                                    max_ls=sbo.inner_max_ls, use_vertices=True)
     return arg.cpu().numpy()[0, 0].reshape(1, -1)
+
+
+def test_independent_chains_batched_equal_sequential_chains():
+    """sample_parameters_chains: chains advanced side by side with merged probes draw exactly what
+    the same chains draw one after the other (each with its own RandomState)."""
+    import copy
+    from bayesian_quadrature_optimization_b200.models.gp_fitting_gaussian import GPFittingGaussian
+    from bayesian_quadrature_optimization_b200.lib import constant as K
+    rng = np.random.RandomState(5)
+    n = 40
+    pts = rng.uniform(0, 1, (n, 3))
+    y = np.sin(3 * pts.sum(1)) + 0.1 * rng.normal(0, 1, n)
+    td = {"points": pts.tolist(), "evaluations": list(y), "var_noise": []}
+    gp = GPFittingGaussian([K.SCALED_KERNEL, K.MATERN52_NAME], td, [3], bounds_domain=[[0, 1]] * 3,
+                           thinning=1, n_burning=0, max_steps_out=10, random_seed=3, noise=True)
+    calls = {"n": 0, "vectors": 0}
+    orig = gp.log_likelihood_batch
+
+    def counting(th):
+        calls["n"] += 1
+        calls["vectors"] += len(th)
+        return orig(th)
+
+    gp.log_likelihood_batch = counting
+    start = gp.samples_parameters[-1].copy()
+    n_before = len(gp.samples_parameters)
+    got = gp.sample_parameters_chains(2, n_chains=3, random_seed=100, burn_in_sweeps=1)
+    assert len(got) == 6 and len(gp.samples_parameters) == n_before + 6
+    assert calls["vectors"] > calls["n"]  # probes of different chains shared factorisations
+    # the same three chains, one after the other
+    want = []
+    for cid in range(3):
+        chain_rng = np.random.RandomState(100 + cid)
+        samplers = []
+        for sp in gp.slice_samplers:
+            sc = copy.copy(sp)
+            sc.rng = chain_rng
+            samplers.append(sc)
+        point = gp._slice_sweeps(start, 1, samplers)[-1]
+        want += gp._slice_sweeps(point, 2 * (gp.thinning + 1), samplers)[::gp.thinning + 1]
+    assert_close(np.array(got), np.array(want), rtol=0, atol=0, what="batched independent chains")
