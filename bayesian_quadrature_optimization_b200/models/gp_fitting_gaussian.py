@@ -133,7 +133,8 @@ class GPFittingGaussian(object):
                  start_point_sampler=None, max_steps_out=1, data=None, random_seed=None,
                  type_bounds=None, training_name=None, problem_name=None,
                  name_model='gp_fitting_gaussian', samples_parameters=None, noise=False,
-                 simplex_domain=None, define_samplers=True, device=None, **kernel_parameters):
+                 simplex_domain=None, define_samplers=True, device=None, n_chains=1,
+                 **kernel_parameters):
         if random_seed is not None:
             np.random.seed(random_seed)
         if bounds_domain is None:
@@ -167,6 +168,9 @@ class GPFittingGaussian(object):
             raise ValueError("points have %d columns, kernel expects %d"
                              % (self.data['points'].shape[1], self._dim))
         self._device = device
+        # > 1: sample_parameters draws from that many independent chains advanced side by side
+        # (sample_parameters_chains); 1 = the reference's single chain
+        self.n_chains = int(n_chains)
         self._eng = None
         self._hb_cache = OrderedDict()
         self._hb_cache_size = 64
@@ -624,6 +628,18 @@ class GPFittingGaussian(object):
             np.random.seed(random_seed)
         if start_point is None:
             start_point = self.samples_parameters[-1]
+        if self.n_chains > 1 and float(n_samples).is_integer() and n_samples >= self.n_chains:
+            # every chain starts at the current state, decorrelates over its first (thinning + 1)
+            # sweeps and keeps ceil(n / chains) points; seeds come from the global stream so that
+            # np.random.seed still fixes the run
+            per = -(-int(n_samples) // self.n_chains)
+            seed = int(np.random.randint(0, 2 ** 31 - 1 - self.n_chains))
+            n_before = len(self.samples_parameters)
+            kept = self.sample_parameters_chains(per, self.n_chains, random_seed=seed,
+                                                 start_points=[start_point] * self.n_chains,
+                                                 burn_in_sweeps=0)[:int(n_samples)]
+            self.samples_parameters = self.samples_parameters[:n_before] + kept
+            return kept
         n_sweeps = int(n_samples * (self.thinning + 1))
         samples = self._slice_sweeps(start_point, n_sweeps, self.slice_samplers)
         samples_return = samples[::self.thinning + 1]

@@ -44,8 +44,11 @@ def bgo(objective_function, bounds_domain_x, integrand_function=None, simplex_do
         monte_carlo_sbo=True, n_samples_mc=5, n_restarts_mc=5, n_best_restarts_mc=0, factr_mc=1e12,
         maxiter_mc=10, method_opt_mc=LBFGS_NAME, n_restarts_mean=100, n_best_restarts_mean=10,
         n_samples_parameters_mean=5, maxepoch_mean=50, parallel_training=False,
-        default_n_samples_parameters=None, default_n_samples=None, device=None):
-    """Maximises the objective function (sbo/services/bgo.py:37-121 documents every argument)."""
+        default_n_samples_parameters=None, default_n_samples=None, device=None, n_chains=1):
+    """Maximises the objective function (sbo/services/bgo.py:37-121 documents every argument).
+    Two arguments are additions: `device` (CUDA device) and `n_chains` (> 1: the hyper-parameter
+    samples of every iteration come from that many independent slice-sampling chains advanced side
+    by side on the GPU instead of one sequential chain)."""
     np.random.seed(random_seed)
     dim_x = len(bounds_domain_x)
     x_domain = list(range(dim_x))
@@ -101,7 +104,7 @@ def bgo(objective_function, bounds_domain_x, integrand_function=None, simplex_do
         type_bounds=type_bounds, thinning=thinning, n_burning=n_burning,
         max_steps_out=max_steps_out, random_seed=random_seed, noise=noise,
         simplex_domain=simplex_domain, problem_name=problem_name or 'user_problem', device=device,
-        **kernel_parameters)
+        n_chains=n_chains, **kernel_parameters)
 
     if mle:  # GPFittingService.get_gp(..., mle=True): maximum-likelihood parameter values
         gp_model.fit_gp_regression(random_seed=random_seed)

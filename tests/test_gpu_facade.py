@@ -562,3 +562,42 @@ def test_independent_chains_batched_equal_sequential_chains():
         point = gp._slice_sweeps(start, 1, samplers)[-1]
         want += gp._slice_sweeps(point, 2 * (gp.thinning + 1), samplers)[::gp.thinning + 1]
     assert_close(np.array(got), np.array(want), rtol=0, atol=0, what="batched independent chains")
+
+
+def test_model_with_several_chains_samples_and_runs_bgo():
+    """n_chains > 1 routes sample_parameters through the side-by-side chains: right count, valid
+    parameters, reproducible under np.random.seed, and bgo() accepts the option."""
+    from bayesian_quadrature_optimization_b200.models.gp_fitting_gaussian import GPFittingGaussian
+    from bayesian_quadrature_optimization_b200.services.bgo import bgo
+    from bayesian_quadrature_optimization_b200.lib import constant as K
+    rng = np.random.RandomState(8)
+    pts = rng.uniform(0, 1, (30, 2))
+    y = np.cos(4 * pts[:, 0]) + pts[:, 1]
+    td = {"points": pts.tolist(), "evaluations": list(y), "var_noise": []}
+
+    def draw():
+        gp = GPFittingGaussian([K.SCALED_KERNEL, K.MATERN52_NAME], td, [2],
+                               bounds_domain=[[0, 1]] * 2, thinning=1, n_burning=2, max_steps_out=10,
+                               random_seed=3, noise=True, n_chains=3)
+        np.random.seed(12)
+        return gp, gp.sample_parameters(5)
+
+    gp, s1 = draw()
+    _, s2 = draw()
+    assert len(s1) == 5 and len(gp.samples_parameters) >= 5
+    assert_close(np.array(s1), np.array(s2), rtol=0, atol=0, what="seeded multi-chain draw")
+    for v in s1:
+        assert v[0] > 0 and np.all(v[2:] > 0) and np.isfinite(gp.log_prob_parameters(v))
+
+    def f(x):
+        return [-(x[0] - 0.3) ** 2]
+
+    def g(x):
+        return [-(x[0] - 0.3) ** 2 + 0.1 * (x[1] - 0.5)]
+
+    out = bgo(f, [(0.0, 1.0)], integrand_function=g, bounds_domain_w=[[0, 1]], type_bounds=[0, 1],
+              n_iterations=1, n_training=4, random_seed=2, n_samples_parameters=2, n_restarts=2,
+              n_restarts_mc=1, n_samples_mc=2, maxepoch=2, thinning=1, n_burning=2, max_steps_out=5,
+              n_restarts_mean=4, n_best_restarts_mean=2, n_samples_parameters_mean=2, maxepoch_mean=3,
+              default_n_samples_parameters=3, default_n_samples=3, n_chains=2)
+    assert out["optimal_solution"].shape == (1,) and 0.0 <= out["optimal_solution"][0] <= 1.0
