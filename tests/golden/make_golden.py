@@ -275,10 +275,36 @@ def case_scaled_gamma():
     return out
 
 
+def case_matern52_plain():
+    """Plain Matern52 GP (no scale, no tasks) in R^3 with a noise parameter: the GP-only rows
+    (covariance, gradients, Cholesky, log-likelihood, posterior, EI) for kernel kind 0."""
+    rng = np.random.RandomState(12)
+    n = 45
+    pts = rng.uniform(-1, 2, (n, 3))
+    y = np.cos(pts[:, 0]) * pts[:, 1] + 0.3 * pts[:, 2] + 0.05 * rng.normal(0, 1, n)
+    td = {"points": pts.tolist(), "evaluations": list(y), "var_noise": []}
+    gp = GPFittingGaussian([MATERN52_NAME], td, [3], bounds_domain=[[-1, 2]] * 3, noise=True,
+                           define_samplers=False)
+    thetas = np.array([[1e-3, 0.2, 0.8, 1.1, 0.6],
+                       [5e-3, -0.1, 1.5, 0.7, 0.9],
+                       [2e-4, 0.0, 0.5, 0.5, 2.0]])
+    query = rng.uniform(-1, 2, (5, 3))
+    out = dict(points=pts, evaluations=y, thetas=thetas, query=query, kind=0, n_tasks=0,
+               same_correlation=0, dx=3)
+    gp_outputs(gp, thetas, query, out)
+    ei_outputs(gp, thetas, query, out)
+    return out
+
+
 def main():
-    for name, fn in [("product_uniform", case_product_uniform),
-                     ("product_weighted", case_product_weighted),
-                     ("scaled_gamma", case_scaled_gamma)]:
+    cases = [("product_uniform", case_product_uniform),
+             ("product_weighted", case_product_weighted),
+             ("scaled_gamma", case_scaled_gamma),
+             ("matern52_plain", case_matern52_plain)]
+    only = set(sys.argv[1:])  # optional: regenerate the named cases only
+    for name, fn in cases:
+        if only and name not in only:
+            continue
         out = fn()
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **{k: np.asarray(v) for k, v in out.items()})

@@ -9,6 +9,7 @@ from oracle import bqo_oracle as orc
 from tests.helpers import assert_close, oracle_from_golden
 
 CASES = ["product_uniform", "product_weighted", "scaled_gamma"]
+GP_CASES = CASES + ["matern52_plain"]  # the last one has no quadrature part
 
 
 def test_matern_known_answers():
@@ -64,7 +65,7 @@ def test_hvoi_degenerate():
     assert orc.hvoi(np.array([1.0]), np.array([0.0, 1.0]), np.array([0])) == 0
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", GP_CASES)
 def test_gp_against_reference(golden, name):
     g = golden(name)
     spec, gp, _ = oracle_from_golden(g)
