@@ -264,7 +264,11 @@ def test_cholesky_solve_random_sizes():
     import ctypes as C
     rng = np.random.RandomState(0)
     eng = E.GPEngine(_cabi.KIND_MATERN52, 1)
-    for n, S, m in [(1, 2, 1), (63, 2, 3), (64, 1, 65), (65, 3, 7), (300, 2, 130), (517, 2, 5)]:
+    # m * S <= 512 takes the vector-solve kernels, above that the DMMA tile solve: both at ragged
+    # sizes, odd n (8-byte cp.async staging) and even n (16-byte staging)
+    for n, S, m in [(1, 2, 1), (63, 2, 3), (64, 1, 65), (65, 3, 7), (300, 2, 130), (517, 2, 5),
+                    (65, 3, 200), (300, 2, 300), (517, 2, 261), (130, 9, 64), (257, 1, 513),
+                    (64, 2, 300), (1, 3, 200)]:
         A = rng.normal(0, 1, (S, n, n + 5))
         A = A @ A.transpose(0, 2, 1) + 1e-3 * np.eye(n)
         Ad = eng.to_device(A.copy())
@@ -347,6 +351,13 @@ def test_large_size_properties():
     assert_close(llh, want, rtol=1e-9, what="llh n=2048")
     res = (Sigma @ hb.alpha.unsqueeze(2)).squeeze(2) - (eng.y.unsqueeze(0) - hb.theta[:, 1:2])
     assert (res.norm() / eng.y.norm()).item() < 1e-9
+    # many right-hand sides (DMMA tile solve, the stage-B shape of the benchmark)
+    import torch
+    B = torch.randn(2, 600, n, dtype=torch.float64, device=eng.device,
+                    generator=torch.Generator(device=eng.device).manual_seed(1))
+    X = hb.solve(B.clone())
+    resid = (X @ Sigma.transpose(1, 2)) - B  # rows are right-hand sides: X Sigma^T = B
+    assert (resid.norm() / B.norm()).item() < 1e-9
 
 
 def test_adam_step_matches_reference_sgd():
