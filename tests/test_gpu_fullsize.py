@@ -270,3 +270,27 @@ def test_c5_shape_cholesky_loglik_gradient_n8192():
         fd = (ll[0] - ll[1]) / (2 * h)
         assert_close(grad[j], fd, rtol=2e-4, atol=1e-4, what="d llh / d theta[%d]" % j)
         del hb2
+
+
+def test_many_factors_at_once_split_panel_path():
+    """32 hyper-samples at n = 1024: the panel kernels run in their factor / solve split form
+    (several waves of row tiles); factors against cuSOLVER's, log-likelihood gradient against the
+    same batch factorised four hyper-samples at a time (fused panel form)."""
+    import torch
+    from bayesian_quadrature_optimization_b200 import engine as E, _cabi
+    pts, y, thetas = _c3(n=1024, S=32, seed=5)
+    eng = E.GPEngine(_cabi.KIND_SCALED_MATERN52, 6)
+    eng.set_data(pts, y)
+    hb = eng.hypers(thetas)
+    Sigma = hb.cov(add_noise=True)
+    hb.factorize()
+    assert np.all(hb.info == 0)
+    ref = torch.linalg.cholesky(Sigma)
+    assert ((hb.L - ref).abs().max() / ref.abs().max()).item() < 1e-11
+    grad = hb.grad_log_likelihood().cpu().numpy()
+    llh = hb.log_likelihood().cpu().numpy()
+    for lo in range(0, 32, 4):
+        part = eng.hypers(thetas[lo:lo + 4]).factorize()
+        assert_close(part.log_likelihood().cpu().numpy(), llh[lo:lo + 4], rtol=1e-12, what="llh")
+        assert_close(part.grad_log_likelihood().cpu().numpy(), grad[lo:lo + 4], rtol=1e-9,
+                     atol=1e-9, what="grad llh")
