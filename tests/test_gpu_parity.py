@@ -440,3 +440,40 @@ def test_hot_path_is_bit_reproducible_and_independent_of_the_z_chunking(golden):
         c = bq.evaluate_candidates(g["cands"], zs, starts, z_per_cta=zc)
         assert torch.equal(a["max"], c["max"]) and torch.equal(a["optimum"], c["optimum"]), zc
         assert torch.equal(a["evaluations"], c["evaluations"])
+
+
+def test_inner_maximize_other_w_sample_counts(golden):
+    """M != 10 W samples (the rolled W loop without the distance table) and several W sets: the
+    device maxima against the CPU restatement of the optimiser on the oracle's a, b."""
+    from bayesian_quadrature_optimization_b200 import engine as E
+    g = golden("scaled_gamma")
+    eng = _engine(g)
+    hb = eng.hypers(g["thetas"])
+    dx = int(g["dx"])
+    lo, up = np.zeros(dx), np.ones(dx)
+    wsets = np.random.RandomState(31).gamma(2.0, 1.0, (2, 7, g["points"].shape[1] - dx))
+    bq = E.BQEngine(hb, dx, wsets=wsets, lower=lo, upper=up)
+    ub = bq.setup(g["cands"])
+    spec, ogp, obq = oracle_from_golden(g)
+    rng = np.random.RandomState(13)
+    zs = rng.normal(0, 1, 3)
+    starts = rng.uniform(lo, up, (2, dx))
+    out_max, out_arg, _ = bq.inner_maximize(ub, zs, starts, count_evals=True)
+    out_max, out_arg = out_max.cpu().numpy(), out_arg.cpu().numpy()
+    S = hb.S
+    for c in range(ub.C):
+        cand = g["cands"][c:c + 1, :]
+        w = wsets[c % 2]  # the unit's W set is candidate index % n_wsets
+        th = g["thetas"][0]
+        u = c * S
+
+        def ab(x, wset):
+            v = obq.compute_parameters_for_sample(x, cand, th[0], th[1], th[2:], w=w)
+            gr = obq.compute_gradient_parameters_for_sample(x, cand, th[0], th[1], th[2:], w=w)
+            return v["a"][0], np.asarray(v["b"]).reshape(-1)[0], gr["a"], gr["b"]
+
+        for i, z in enumerate(zs):
+            best, arg, _ = inner_opt.inner_maximize(ab, z, starts, lo, up)
+            assert_close(out_max[u, i], best, rtol=1e-9, atol=1e-12, what="inner max, M = 7")
+            a, b, _, _ = ab(out_arg[u, i], 0)
+            assert_close(a + z * b, out_max[u, i], rtol=1e-9, atol=1e-12, what="value at argmax")
