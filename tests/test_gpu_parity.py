@@ -477,3 +477,74 @@ def test_inner_maximize_other_w_sample_counts(golden):
             assert_close(out_max[u, i], best, rtol=1e-9, atol=1e-12, what="inner max, M = 7")
             a, b, _, _ = ab(out_arg[u, i], 0)
             assert_close(a + z * b, out_max[u, i], rtol=1e-9, atol=1e-12, what="value at argmax")
+
+
+@pytest.mark.parametrize("dx,dw", [(3, 1), (5, 2), (1, 2), (6, 1), (6, 0), (3, 0)])
+def test_stage_c_other_dimensions(dx, dw):
+    """Template instantiations the fixtures do not reach (x dimensions 1..6, w dimensions 0..2):
+    a, b and their gradients against the oracle, the maximiser's value reproduced at its argument."""
+    from bayesian_quadrature_optimization_b200 import engine as E, _cabi
+    rng = np.random.RandomState(10 * dx + dw)
+    n = 70
+    x = rng.uniform(0, 1, (n, dx))
+    lo, up = np.zeros(dx), np.ones(dx)
+    if dw > 0:
+        w = rng.gamma(2.0, 1.0, (n, dw))
+        pts = np.concatenate([x, w], 1)
+        y = np.sin(pts.sum(1)) + 0.05 * rng.normal(0, 1, n)
+        thetas = np.array([[1e-3, 0.1] + dx * [0.6] + dw * [2.0] + [1.2],
+                           [2e-3, 0.0] + dx * [0.9] + dw * [1.5] + [0.8]])
+        eng = E.GPEngine(_cabi.KIND_SCALED_MATERN52, dx + dw)
+        eng.set_data(pts, y)
+        wset = rng.gamma(2.0, 1.0, (10, dw))
+        bq = E.BQEngine(eng.hypers(thetas), dx, wsets=wset, lower=lo, upper=up)
+        spec = orc.KernelSpec(orc.SCALED_MATERN52, dx + dw)
+        ogp = orc.OracleGP(spec, pts, y)
+        obq = orc.OracleBQ(ogp, list(range(dx)), orc.GAMMA)
+        cands = np.concatenate([rng.uniform(0, 1, (2, dx)), rng.gamma(2.0, 1.0, (2, dw))], 1)
+    else:
+        T = 3
+        task = rng.randint(0, T, n).astype(float)
+        pts = np.concatenate([x, task[:, None]], 1)
+        y = np.sin(x.sum(1)) + 0.3 * task + 0.05 * rng.normal(0, 1, n)
+        thetas = np.array([[1e-3, 0.1] + dx * [0.6] + [0.2, -0.1, 0.3, 0.0, 0.1, -0.2],
+                           [2e-3, 0.0] + dx * [0.9] + [0.0, 0.1, -0.2, 0.3, -0.1, 0.2]])
+        eng = E.GPEngine(_cabi.KIND_PRODUCT_TASKS, dx + 1, T, False)
+        eng.set_data(pts, y)
+        wset = None
+        bq = E.BQEngine(eng.hypers(thetas), dx, lower=lo, upper=up)
+        spec = orc.KernelSpec(orc.PRODUCT_TASKS, dx + 1, n_tasks=T, same_correlation=False)
+        ogp = orc.OracleGP(spec, pts, y)
+        obq = orc.OracleBQ(ogp, list(range(dx)), orc.UNIFORM_FINITE)
+        cands = np.concatenate([rng.uniform(0, 1, (2, dx)), np.array([[0.0], [2.0]])], 1)
+    ub = bq.setup(cands)
+    S = 2
+    xq = rng.uniform(0, 1, (3, dx))
+    zs = np.array([-0.8, 1.1])
+    starts = rng.uniform(0, 1, (2, dx))
+    out_max, out_arg, _ = bq.inner_maximize(ub, zs, starts, count_evals=True)
+    out_max, out_arg = out_max.cpu().numpy(), out_arg.cpu().numpy()
+    for s in range(S):
+        th = thetas[s]
+        for c in range(2):
+            u = c * S + s
+            got = bq.sample_ab(ub, xq, np.full(len(xq), u, dtype=np.int32)).cpu().numpy()
+            for p in range(len(xq)):
+                v = obq.compute_parameters_for_sample(xq[p], cands[c:c + 1], th[0], th[1], th[2:], w=wset)
+                gr = obq.compute_gradient_parameters_for_sample(xq[p], cands[c:c + 1], th[0], th[1],
+                                                                th[2:], w=wset)
+                want = np.concatenate([[v["a"][0], np.asarray(v["b"]).reshape(-1)[0]],
+                                       np.asarray(gr["a"]).reshape(-1), np.asarray(gr["b"]).reshape(-1)])
+                assert_close(got[p], want, rtol=1e-8, atol=1e-10, what="ab dx=%d dw=%d" % (dx, dw))
+            for i, z in enumerate(zs):
+                v = obq.compute_parameters_for_sample(out_arg[u, i], cands[c:c + 1], th[0], th[1],
+                                                      th[2:], w=wset)
+                assert_close(v["a"][0] + z * np.asarray(v["b"]).reshape(-1)[0], out_max[u, i],
+                             rtol=1e-8, atol=1e-10, what="value at argmax")
+                assert np.all(out_arg[u, i] >= 0) and np.all(out_arg[u, i] <= 1)
+    gvb, is_nan = bq.grad_vector_b(ub, np.repeat(xq[None], 2 * S, axis=0))
+    assert not is_nan.cpu().numpy().any()
+    th = thetas[1]
+    gb = obq.gradient_vector_b(cands[1:2], xq, th[0], th[1], th[2:], w=wset)
+    assert_close(gvb.cpu().numpy()[1 * S + 1][:, :gb.shape[1]], gb[:, :gvb.shape[2]], rtol=1e-6,
+                 atol=1e-9, what="gvb dx=%d dw=%d" % (dx, dw))
