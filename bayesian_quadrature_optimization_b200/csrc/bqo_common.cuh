@@ -279,6 +279,7 @@ static inline void bqo_ensure_global_exp_table(cudaStream_t cs) {
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || done[dev]) return;
     bqo_exp_table_global_init_kernel<<<8, 256, 0, cs>>>();
+    cudaStreamSynchronize(cs);  // once per device: later callers may be on other streams
     done[dev] = true;
 }
 
