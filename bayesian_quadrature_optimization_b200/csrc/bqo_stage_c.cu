@@ -14,7 +14,9 @@
 // each lane loops over the M W samples of its point (the x part of the squared distance is
 // shared by the M samples, and d/dx only needs sum_m k'(r_m)/r_m), and ten partial sums are
 // combined with warp shuffles.  The inner maximiser keeps one warp per (Z sample, start) run;
-// a CTA serves one unit so that X/ls, alpha and s2 are staged once in shared memory.
+// a CTA serves one unit so that X/ls, alpha and s2 are staged once in shared memory.  The W part
+// of the squared distances does not depend on x and is read from a table built once per
+// (hyper-sample, W set) (bqo_wdist_precompute).
 #include "bqo_common.cuh"
 #include <float.h>
 
@@ -421,7 +423,7 @@ __device__ __forceinline__ void eval_ab_warp(const EvalPtrs& p, const UnitCtx<DX
 #pragma unroll
         for (int l = 0; l < DX; ++l) GC[l] = fma(gm, dxl[l], GC[l]);
     }
-    // d/dx: k'(r)/r * (x - X)/ls^2 = -(5/3) G * (dx'/sqrt5) / ls  with dx' the prescaled difference
+    // d/dx: k'(r)/r * (x - X)/ls^2 = -(5/3) G * (dx'/K) / ls  with dx' the difference in units of K
     const double gfac = BQO_GRAD_FAC;
     if (CMB) {
         Sa = bqo_warp_sum(Sa);
