@@ -382,16 +382,19 @@ class BQEngine(object):
             w = w / w.sum()
             v = torch.einsum('a,sab,b->s', w, C, w)
             return v.unsqueeze(1).expand(hb.S, P).contiguous()
-        ws = self.wsets[w_set]
-        M = int(ws.shape[0])
-        out = eng.empty(hb.S, P)
-        for p in range(P):
-            pts = torch.cat([xpts[p:p + 1].expand(M, self.dx), ws], dim=1).contiguous()
+        # stationary kernel: k((x, w), (x, w')) only depends on w - w', so the double mean over the
+        # W set is the same for every x; computed once per (engine, W set) and broadcast
+        cache = self.__dict__.setdefault("_prior_var_cache", {})
+        v = cache.get(int(w_set))
+        if v is None:
+            ws = self.wsets[w_set]
+            M = int(ws.shape[0])
+            pts = torch.cat([xpts[0:1].expand(M, self.dx), ws], dim=1).contiguous()
             tmp = GPEngine(d.kind, d.dim, d.n_tasks, bool(d.same_corr), device=eng.device)
             tmp.set_data(pts, torch.zeros(M, dtype=F64, device=eng.device))
-            hb2 = tmp.hypers(hb.theta)
-            out[:, p] = hb2.cov().mean(dim=(1, 2))
-        return out
+            v = tmp.hypers(hb.theta).cov().mean(dim=(1, 2))
+            cache[int(w_set)] = v
+        return v.unsqueeze(1).expand(hb.S, P).contiguous()
 
     def quadrature_posterior(self, xpts, w_set=0, var=True):
         """Posterior mean (and variance) of G at P points for every hyper-sample
