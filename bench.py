@@ -253,6 +253,10 @@ def workload_config():
                            % (N_RESTARTS_MC + 1, MAXITER_MC, FACTR_MC),
         "l2": "256 MiB buffer rewritten between steps (L2 flush); per-step inputs (20 factors, "
               "640 MB) exceed L2 as well",
+        "precomputed": "per (hyper-sample, W set): W part of the squared distances (26 MB table, built "
+                       "once with the engine, outside the timed steps like the factors); roofline "
+                       "flops keep SURVEY 8d's count, which includes that part",
+        "z_per_cta": Z_PER_CTA,
     }
 
 
