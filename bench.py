@@ -73,6 +73,29 @@ def f_eval_flops():
     return M_W * N_TRAIN * (2 * d + 10) + M_W * N_TRAIN * (3 * DX + 8) + 4 * N_TRAIN * (1 + DX)
 
 
+def issue_model(evals_per_launch, kernel_ms, clocks, dfma_peak_tflops=None):
+    """What the kernel EXECUTES, next to the algorithmic count above: SASS instruction counts of the
+    inner loop (one warp iteration = one training point x 10 W samples for the 32 evaluations held
+    by the lanes; profiles/r01_inner_maximize_v6.md) priced with
+    the measured issue costs (FP64 2 cycles, 3 with three register sources, others 1), against
+    the cycles the launch took at the sampled SM clock."""
+    fp64, fp64_3src, other = 182.7, 33.0, 144.0
+    cyc = 2.0 * fp64 + fp64_3src + other
+    out = {"fp64_instr_per_point": fp64, "other_instr_per_point": other,
+           "issue_cycles_per_point": cyc, "source": "SASS counts of the ncu capture in "
+           "profiles/r01_inner_maximize_v6.md; 148 SMs x 4 sub-partitions"}
+    mhz = (clocks or {}).get("sm_mhz")
+    if mhz:
+        need = evals_per_launch / 32.0 * N_TRAIN * cyc / (148 * 4)
+        # a ratio near (or a little above) 1: the launch takes what its instruction mix costs
+        out["model_cycles_over_elapsed_cycles"] = need / (kernel_ms * 1e-3 * mhz * 1e6)
+    rate = evals_per_launch * N_TRAIN * fp64 / (kernel_ms * 1e-3) / 1e12
+    out["executed_fp64_thread_instr_T_per_s"] = rate
+    if dfma_peak_tflops:
+        out["executed_frac_of_dfma_issue_rate"] = rate / (dfma_peak_tflops / 2.0)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 class ClockSampler(object):
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
@@ -481,6 +504,7 @@ def run_gpu(args):
             "flops_per_eval": f_eval_flops(), "evals_per_launch": evals / args.steps,
             "evals_per_unit_per_z": evals / args.steps / (units_per_step * N_Z),
             "kernel_ms": kern_avg_ms, "kernel_share_of_step": kern_avg_ms / (elapsed_ms / args.steps),
+            "issue_model": issue_model(evals / args.steps, kern_avg_ms, clocks, dfma_peak),
         },
         "secondary": {
             "metric": "gp_loglik_grad_per_s", "value": N_HYPER / (stage_a * 1e-3), "unit": "evals/s",
