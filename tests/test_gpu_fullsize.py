@@ -34,7 +34,7 @@ def _c3(n=2048, S=2, seed=0):
     return pts, y, thetas
 
 
-def _check_maximiser_properties(bq, ub, zs, starts, lo, up, n_units):
+def _check_maximiser_properties(bq, ub, zs, starts, lo, up, n_units, wset_of_unit=None):
     """Size-independent properties of the inner maximiser: its value is reproduced by a + Z b at
     the returned argument, the argument is in the box, and no start point or box vertex beats it."""
     dx = len(lo)
@@ -45,8 +45,12 @@ def _check_maximiser_properties(bq, ub, zs, starts, lo, up, n_units):
                       for v in range(1 << dx)], float)
     probe = np.concatenate([starts, verts], 0)
     for u in range(n_units):
-        ab = bq.sample_ab(ub, probe, np.full(len(probe), u, dtype=np.int32)).cpu().numpy()
-        at = bq.sample_ab(ub, out_arg[u], np.full(len(zs), u, dtype=np.int32)).cpu().numpy()
+        # the maximiser evaluates unit u with the W set of its candidate; sample_ab takes it per point
+        ws = 0 if wset_of_unit is None else wset_of_unit[u]
+        ab = bq.sample_ab(ub, probe, np.full(len(probe), u, dtype=np.int32),
+                          np.full(len(probe), ws, dtype=np.int32)).cpu().numpy()
+        at = bq.sample_ab(ub, out_arg[u], np.full(len(zs), u, dtype=np.int32),
+                          np.full(len(zs), ws, dtype=np.int32)).cpu().numpy()
         for i, z in enumerate(zs):
             assert_close(at[i, 0] + z * at[i, 1], out_max[u, i], rtol=1e-11, atol=1e-12,
                          what="value at argmax")
@@ -270,6 +274,42 @@ def test_c5_shape_cholesky_loglik_gradient_n8192():
         fd = (ll[0] - ll[1]) / (2 * h)
         assert_close(grad[j], fd, rtol=2e-4, atol=1e-4, what="d llh / d theta[%d]" % j)
         del hb2
+
+
+def test_inner_maximiser_beyond_shared_memory_ragged_n_and_several_w_sets():
+    """n = 4100 does not fit shared memory (the staged build holds about 3700 training points):
+    the maximiser streams its operands from L2 and reads the W-distance table of each unit's own
+    W set (three sets, unit u uses set (u // S) % 3; 4100 = 128 blocks of 32 + 4 points).
+    Size-independent properties of the maximiser, and the result does not depend on how the Z
+    samples are spread over CTAs."""
+    from bayesian_quadrature_optimization_b200 import engine as E, _cabi
+    n, S, dx = 4100, 2, 4
+    pts, y, thetas = _c3(n=n, S=S, seed=11)
+    eng = E.GPEngine(_cabi.KIND_SCALED_MATERN52, 6)
+    eng.set_data(pts, y)
+    hb = eng.hypers(thetas).factorize()
+    assert np.all(hb.info == 0)
+    lo, up = np.zeros(dx), np.ones(dx)
+    wsets = np.random.RandomState(4).gamma(2.0, 1.0, (3, 10, 2))
+    bq = E.BQEngine(hb, dx, wsets=wsets, lower=lo, upper=up)
+    r5 = np.random.RandomState(5)
+    cands = np.concatenate([r5.uniform(0, 1, (3, 4)), r5.gamma(2.0, 1.0, (3, 2))], 1)
+    ub = bq.setup(cands)
+    n_units = 3 * S
+    zs = np.array([-1.3, -0.2, 0.0, 0.7, 2.1])
+    starts = np.random.RandomState(6).uniform(0, 1, (5, dx))
+    out_max, out_arg = _check_maximiser_properties(bq, ub, zs, starts, lo, up, n_units,
+                                                   wset_of_unit=[(u // S) % 3 for u in range(n_units)])
+    m2, a2, _ = bq.inner_maximize(ub, zs, starts, z_per_cta=2, count_evals=True)
+    assert np.array_equal(m2.cpu().numpy(), out_max)
+    assert np.array_equal(a2.cpu().numpy(), out_arg)
+    # without the table the W part of the distances is recomputed in every evaluation
+    E.BQEngine.use_wdist = False
+    try:
+        m3, _, _ = bq.inner_maximize(ub, zs, starts, count_evals=True)
+    finally:
+        E.BQEngine.use_wdist = True
+    assert_close(m3.cpu().numpy(), out_max, rtol=1e-9, atol=1e-11, what="table vs recomputed maxima")
 
 
 def test_many_factors_at_once_split_panel_path():
