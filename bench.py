@@ -76,14 +76,15 @@ def f_eval_flops():
 def issue_model(evals_per_launch, kernel_ms, clocks, dfma_peak_tflops=None):
     """What the kernel EXECUTES, next to the algorithmic count above: SASS instruction counts of the
     inner loop (one warp iteration = one training point x 10 W samples for the 32 evaluations held
-    by the lanes; profiles/r01_inner_maximize_v6.md) priced with
+    by the lanes; profiles/r01_inner_maximize_final.md) priced with
     the measured issue costs (FP64 2 cycles, 3 with three register sources, others 1), against
     the cycles the launch took at the sampled SM clock."""
-    fp64, fp64_3src, other = 182.7, 33.0, 144.0
+    fp64, fp64_3src, other = 182.0, 35.3, 131.7
     cyc = 2.0 * fp64 + fp64_3src + other
     out = {"fp64_instr_per_point": fp64, "other_instr_per_point": other,
-           "issue_cycles_per_point": cyc, "source": "SASS counts of the ncu capture in "
-           "profiles/r01_inner_maximize_v6.md; 148 SMs x 4 sub-partitions"}
+           "issue_cycles_per_point": cyc, "fp64_3src_instr_per_point": fp64_3src,
+           "source": "executed-instruction counts of the ncu capture in "
+           "profiles/r01_inner_maximize_final.md; 148 SMs x 4 sub-partitions"}
     mhz = (clocks or {}).get("sm_mhz")
     if mhz:
         need = evals_per_launch / 32.0 * N_TRAIN * cyc / (148 * 4)
