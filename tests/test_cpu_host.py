@@ -222,3 +222,26 @@ def test_bayesian_evaluations_mean_and_std():
     g = lambda point, var_noise, mean, params: point * mean
     m2, s2 = BayesianEvaluations.evaluate(g, np.array([1.0, 2.0]), Model(), 3)
     assert np.allclose(m2, np.array([2.0, 4.0])) and m2.shape == (2,) and s2.shape == (2,)
+
+
+def test_bench_accounting_helpers():
+    """bench.py's flop count is SURVEY 8d's formula, and the issue-port model is plain arithmetic on
+    the committed instruction counts (no GPU needed): a launch that takes exactly the modelled
+    cycles reports a ratio of 1."""
+    import bench
+    d = bench.DX + bench.DW
+    want = (bench.M_W * bench.N_TRAIN * (2 * d + 10) + bench.M_W * bench.N_TRAIN * (3 * bench.DX + 8)
+            + 4 * bench.N_TRAIN * (1 + bench.DX))
+    assert bench.f_eval_flops() == want == 901120
+    cfg = bench.workload_config()
+    assert cfg["units_per_step"] == cfg["candidates_per_step"] * cfg["hyper_samples"]
+    evals = 1.0e7
+    m = bench.issue_model(evals, 100.0, None, 34.6)
+    assert "model_cycles_over_elapsed_cycles" not in m  # no clock sample, no cycle ratio
+    cyc = m["issue_cycles_per_point"]
+    assert cyc == 2.0 * m["fp64_instr_per_point"] + m["fp64_3src_instr_per_point"] + m["other_instr_per_point"]
+    mhz = 1965.0
+    ms = evals / 32.0 * bench.N_TRAIN * cyc / (148 * 4) / (mhz * 1e6) * 1e3
+    m = bench.issue_model(evals, ms, {"sm_mhz": mhz}, 34.6)
+    assert abs(m["model_cycles_over_elapsed_cycles"] - 1.0) < 1e-12
+    assert 0.0 < m["executed_frac_of_dfma_issue_rate"] < 1.0
