@@ -15,7 +15,7 @@ import numpy as np
 from scipy import linalg
 
 from .. import _cabi
-from ..engine import GPEngine
+from ..engine import GPEngine, kernel_desc
 from ..lib.constant import (
     MATERN52_NAME, TASKS_KERNEL_NAME, PRODUCT_KERNELS_SEPARABLE, SCALED_KERNEL, SAME_CORRELATION,
     MEAN_NAME, VAR_NOISE_NAME,
@@ -26,10 +26,13 @@ class ParameterEntity(object):
     """sbo/entities/parameter.py: name, value (np.array), prior, bounds."""
 
     def __init__(self, name, value, prior=None, bounds=None):
+        from ..lib.constant import SMALLEST_NUMBER, LARGEST_NUMBER
         self.name = name
         self.value = np.asarray(value, dtype=float)
         self.prior = prior
         self.dimension = len(self.value)
+        if bounds is None:  # entities/parameter.py:29-30,48-58
+            bounds = self.dimension * [(SMALLEST_NUMBER, LARGEST_NUMBER)]
         self.bounds = bounds
 
     def set_value(self, value):
@@ -153,6 +156,7 @@ class GPFittingGaussian(object):
         self.dimension_domain = len(bounds_domain)
         self.dimensions = dimensions
         self.type_bounds = type_bounds
+        self.training_data_as_array = self.convert_from_list_to_numpy(training_data)
         self.data = self.convert_from_list_to_numpy(training_data if data is None else data)
         self.thinning = thinning
         self.max_steps_out = max_steps_out
@@ -177,21 +181,33 @@ class GPFittingGaussian(object):
         self._hb_cache_bytes = int(float(os.environ.get("BQO_FACTOR_CACHE_GB", "24")) * 2 ** 30)
         self.best_solution = {}
 
-        # model values (reference: set_parameters_kernel, :355-422).  When the data carries
-        # observation noise, or the model is noise free, var_noise = mean = 0 (:363-365).
-        n_params = self._engine().desc.n_params
-        if kernel_values is None or len(kernel_values) == 0:
-            kernel_values = self._default_kernel_values()
+        # model values (set_parameters_kernel, :355-422, and get_values_parameters_from_data,
+        # :442-490): the data-driven defaults are computed from the arguments as given; only then
+        # are mean and var_noise forced to 0 for noise-free models and models with observed noise
+        n_params = kernel_desc(self._kind, self._dim, self._n_tasks, self._same_corr).n_params
+        if mean_value is not None and len(mean_value) == 0:
+            mean_value = None
+        if var_noise_value is not None and len(var_noise_value) == 0:
+            var_noise_value = None
+        if kernel_values is not None and len(kernel_values) == 0:
+            kernel_values = None
+        ev = self.training_data_as_array['evaluations']
+        prior_mean = [np.mean(ev)] if mean_value is None else mean_value
+        if var_noise_value is None:
+            prior_var_noise = [np.var(ev)] if len(ev) > 1 else [0.1]
+        else:
+            prior_var_noise = var_noise_value
+        if kernel_values is None:
+            kernel_values = self._default_kernel_values(prior_var_noise[0])
         if len(kernel_values) != n_params:
             raise ValueError("kernel_values must have %d entries" % n_params)
         if not self.noise or self.data.get('var_noise') is not None:
             mean_value = [0.0]
             var_noise_value = [0.0]
-        if mean_value is None or len(mean_value) == 0:
-            mean_value = [np.mean(self.data['evaluations'])]
-        if var_noise_value is None or len(var_noise_value) == 0:
-            ev = self.data['evaluations']
-            var_noise_value = [np.var(ev)] if len(ev) > 1 else [0.1]
+        if mean_value is None:
+            mean_value = list(prior_mean)
+        if var_noise_value is None:
+            var_noise_value = list(prior_var_noise)
         self.kernel = _KernelParameters(kernel_values, self._dim)
         self.mean = ParameterEntity(MEAN_NAME, np.array(mean_value, dtype=float))
         self.var_noise = ParameterEntity(VAR_NOISE_NAME, np.array(var_noise_value, dtype=float))
@@ -210,8 +226,6 @@ class GPFittingGaussian(object):
         self.slice_samplers = []
         if define_samplers:
             self.set_samplers()
-        elif len(self.samples_parameters) == 0:
-            self.samples_parameters.append(self.get_value_parameters_model)
 
     # -- data plumbing ----------------------------------------------------------------------------
     @staticmethod
@@ -224,30 +238,65 @@ class GPFittingGaussian(object):
         data['var_noise'] = np.array(vn, dtype=float) if vn is not None and len(vn) > 0 else None
         return data
 
-    def _default_kernel_values(self):
-        """Data-driven defaults in the spirit of define_prior_parameters (kernels/matern52.py:
-        298-326: mean |x - y| / 0.324 per coordinate); tasks / sigma2 defaults as in
-        lib/util_gp_fitting.py:161-240."""
-        pts = self.data['points']
+    def _default_kernel_values(self, sigma2):
+        """define_prior_parameters_using_data (lib/util_gp_fitting.py:161-240) followed by
+        get_default_values_kernel (lib/util.py:162-207): length scales = mean |x_i - x_j| over all
+        ordered pairs of training points / 0.324 per coordinate (kernels/matern52.py:298-326; the
+        O(n^2) list becomes a sorted-order sum), sigma2 of a scaled kernel = `sigma2`
+        (kernels/scaled_kernel.py:332-350), task parameters from the empirical covariance between
+        tasks (_default_task_values)."""
+        pts = self.training_data_as_array['points']
         dm = self._dim - 1 if self._kind == _cabi.KIND_PRODUCT_TASKS else self._dim
         ls = []
+        n = pts.shape[0]
         for l in range(dm):
-            x = np.sort(pts[:, l])
-            n = len(x)
             if n > 1:
+                x = np.sort(pts[:, l])
                 k = np.arange(n)
                 mean_abs = 2.0 * np.sum((2 * k - n + 1) * x) / (n * n)
-                ls.append(max(mean_abs / 0.324, 1e-10))
             else:
-                ls.append(1.0)
+                mean_abs = 0.324
+            ls.append(mean_abs / 0.324)
         if self._kind == _cabi.KIND_MATERN52:
             return ls
         if self._kind == _cabi.KIND_SCALED_MATERN52:
-            ev = self.data['evaluations']
-            return ls + [float(np.var(ev)) if len(ev) > 1 else 1.0]
+            return ls + [sigma2]
+        return ls + self._default_task_values(sigma2)
+
+    def _default_task_values(self, sigma2):
+        """TasksKernel.define_prior_parameters (kernels/tasks_kernel.py:404-521): log-Cholesky
+        entries (or the two same-correlation parameters) of the empirical covariance between the
+        tasks' evaluations, paired in observation order and truncated to the shorter task; zeros
+        when some task has fewer than two evaluations."""
+        from ..lib.constant import SMALLEST_POSITIVE_NUMBER
         T = self._n_tasks
-        nt = min(T, 2) if self._same_corr else T * (T + 1) // 2
-        return ls + nt * [0.0]
+        if T == 1:
+            return [sigma2]
+        data = self.training_data_as_array
+        ids = data['points'][:, self._dim - 1]
+        groups = [data['evaluations'][ids == t] for t in range(T)]
+        n_params = min(T, 2) if self._same_corr else T * (T + 1) // 2
+        if min(len(g) for g in groups) < 2:
+            return n_params * [0.0]
+        centred = [g - np.mean(g) for g in groups]
+        cov = np.zeros((T, T))
+        for i in range(T):
+            for j in range(i + 1):
+                d = min(len(centred[i]), len(centred[j]))
+                cov[i, j] = cov[j, i] = np.sum(centred[i][:d] * centred[j][:d]) / (d - 1.0)
+        if self._same_corr:
+            params = [np.log(max(np.mean(np.diag(cov)), 0.1))]
+            off = cov[~np.eye(T, dtype=bool)]
+            off = off[off != 0]
+            if np.all(off == 0):
+                return params
+            return params + [np.log(max(np.mean(off), 0.1))]
+        low = np.zeros((T, T))
+        for j in range(T):
+            low[j, j] = np.sqrt(max(cov[j, j] - np.sum(low[j, :j] ** 2), SMALLEST_POSITIVE_NUMBER))
+            for i in range(j + 1, T):
+                low[i, j] = (cov[i, j] - np.sum(low[i, :j] * low[j, :j])) / low[j, j]
+        return [np.log(max(low[i, j], 0.0001)) for i in range(T) for j in range(i + 1)]
 
     def _engine(self) -> GPEngine:
         if self._eng is None:
@@ -486,37 +535,44 @@ class GPFittingGaussian(object):
 
     # -- hyper-posterior: priors (host) + GPU likelihood, slice sampling ----------------------------
     def _define_priors(self):
-        """Priors of set_parameters_kernel (:355-422) and of the kernels' define_default_kernel
-        (matern52.py:124-161, scaled_kernel.py:124-175, tasks_kernel.py:129-189)."""
+        """Priors and bounds of set_parameters_kernel (:392-408) and of the kernels'
+        define_default_kernel (matern52.py:124-161, scaled_kernel.py:136-175,
+        tasks_kernel.py:146-189); `_kernel_priors` / `_kernel_bounds` follow the parameter order."""
         from ..priors.priors import (UniformPrior, GaussianPrior, LogNormalSquare, HorseShoePrior,
                                      NonNegativePrior, MultivariateNormalPrior, Constant)
-        from ..lib.constant import SMALLEST_POSITIVE_NUMBER, LARGEST_NUMBER
+        from ..lib.constant import SMALLEST_POSITIVE_NUMBER, SMALLEST_NUMBER, LARGEST_NUMBER
+        free = (SMALLEST_NUMBER, LARGEST_NUMBER)  # entities/parameter.py:48-58
         if self.noise and self.data.get('var_noise') is None:
             self.mean.prior = GaussianPrior(1, self.mean_value[0], 1.0)
             self.var_noise.prior = NonNegativePrior(1, HorseShoePrior(1, self.var_noise_value[0]))
             self.var_noise.bounds = [(SMALLEST_POSITIVE_NUMBER, None)]
         else:
+            self.mean.set_value([0.0])
+            self.var_noise.set_value([0.0])
             self.mean.prior = Constant(1, 0.0)
             self.var_noise.prior = Constant(1, 0.0)
             self.var_noise.bounds = [(0.0, 0.0)]
+        self.mean.bounds = [free]
         dm = self._dim - 1 if self._kind == _cabi.KIND_PRODUCT_TASKS else self._dim
-        if self.bounds is not None and len(self.bounds) >= dm:
-            diffs = [float(self.bounds[l][-1] - self.bounds[l][0]) / 0.001 for l in range(dm)]
-        else:
-            diffs = dm * [LARGEST_NUMBER]
+        diffs = [float(self.bounds[l][1] - self.bounds[l][0]) / 0.001 for l in range(dm)]
         self._kernel_priors = [(slice(0, dm), UniformPrior(dm, dm * [SMALLEST_POSITIVE_NUMBER], diffs))]
+        self._kernel_bounds = [(SMALLEST_POSITIVE_NUMBER, diff) for diff in diffs]
         kv = np.asarray(self.kernel_values, dtype=float)
         if self._kind == _cabi.KIND_SCALED_MATERN52:
             self._kernel_priors.append((slice(dm, dm + 1), LogNormalSquare(1, 1.0, np.sqrt(kv[dm]))))
+            self._kernel_bounds.append((SMALLEST_POSITIVE_NUMBER, None))
         elif self._kind == _cabi.KIND_PRODUCT_TASKS:
             tv = kv[dm:]
+            task_bounds = len(tv) * [free]
             if np.all(tv == 0.0):
                 prior = UniformPrior(len(tv), len(tv) * [-1.0], len(tv) * [1.0])
             elif self._n_tasks == 1:
                 prior = LogNormalSquare(1, 1.0, np.sqrt(tv[0]))
+                task_bounds = [(SMALLEST_POSITIVE_NUMBER, None)]
             else:
                 prior = MultivariateNormalPrior(len(tv), tv, np.eye(len(tv)))
             self._kernel_priors.append((slice(dm, len(kv)), prior))
+            self._kernel_bounds += task_bounds
         self.length_scale_indexes = list(range(2, 2 + dm))
 
     def _log_prior_parameters(self, parameters):
@@ -628,6 +684,10 @@ class GPFittingGaussian(object):
             np.random.seed(random_seed)
         if start_point is None:
             start_point = self.samples_parameters[-1]
+        if not self.slice_samplers:  # define_samplers=False: the reference's loop over no samplers
+            kept = [np.array(start_point, dtype=float)] * len(range(0, int(n_samples * (self.thinning + 1)), self.thinning + 1))
+            self.samples_parameters += kept
+            return kept
         if self.n_chains > 1 and float(n_samples).is_integer() and n_samples >= self.n_chains:
             # every chain starts at the current state, decorrelates over its first (thinning + 1)
             # sweeps and keeps ceil(n / chains) points; seeds come from the global stream so that
@@ -643,7 +703,8 @@ class GPFittingGaussian(object):
         n_sweeps = int(n_samples * (self.thinning + 1))
         samples = self._slice_sweeps(start_point, n_sweeps, self.slice_samplers)
         samples_return = samples[::self.thinning + 1]
-        self.samples_parameters += samples_return
+        if len(self.slice_samplers) != 1:  # the reference's one-sampler branch only returns (:319-336)
+            self.samples_parameters += samples_return
         return samples_return
 
     def _slice_sweeps(self, start_point, n_sweeps, samplers):
@@ -661,6 +722,8 @@ class GPFittingGaussian(object):
                 while new_point is None and n_try < 10:
                     try:
                         new_point = sampler.slice_sample(points[which], points[1 - which], self)
+                    except _cabi.BqoLibraryError:  # no device / no library: not a numerical failure
+                        raise
                     except Exception:
                         n_try += 1
                 if new_point is None:
@@ -738,19 +801,8 @@ class GPFittingGaussian(object):
     # -- maximum likelihood (a16) -------------------------------------------------------------------
     @property
     def get_bounds_parameters(self):
-        """:933-944: [(low, up)] for [var_noise, mean, kernel parameters]; length scales and
-        sigma2 are positive (matern52.py:150-151, scaled_kernel.py:150-152), task parameters free."""
-        from ..lib.constant import SMALLEST_POSITIVE_NUMBER
-        bounds = list(self.var_noise.bounds) if self.var_noise.bounds else [(None, None)]
-        bounds += list(self.mean.bounds) if self.mean.bounds else [(None, None)]
-        dm = self._dim - 1 if self._kind == _cabi.KIND_PRODUCT_TASKS else self._dim
-        bounds += dm * [(SMALLEST_POSITIVE_NUMBER, None)]
-        n_rest = self.dimension_parameters - 2 - dm
-        if self._kind == _cabi.KIND_SCALED_MATERN52:
-            bounds += [(SMALLEST_POSITIVE_NUMBER, None)]
-        else:
-            bounds += n_rest * [(None, None)]
-        return bounds
+        """:933-944: [(low, up)] for [var_noise, mean, kernel parameters]."""
+        return list(self.var_noise.bounds) + list(self.mean.bounds) + list(self._kernel_bounds)
 
     def objective_llh(self, params):
         """:946-960: log-likelihood, or -inf when the factorisation fails."""

@@ -80,6 +80,7 @@ class BayesianQuadrature(object):
         self.type_kernel = self.gp.type_kernel
 
         self.w_sets = None
+        self.w_double_sets = None
         if not finite:
             self.resample_w(n_w_sets)
         self._bq_cache = OrderedDict()
@@ -103,6 +104,22 @@ class BayesianQuadrature(object):
         w_sets = np.asarray(w_sets, dtype=float)
         self.w_sets = w_sets[None] if w_sets.ndim == 2 else w_sets
         self._bq_cache = OrderedDict()
+
+    def resample_w_double(self, n_samples=100):
+        """The two independent draws of the double expectation (gamma_expect with double=True,
+        sbo/lib/expectations.py:93-112: n_samples = 100, two gamma.rvs calls in this order)."""
+        a = self.parameters_distribution['a'][0]
+        scale = self.parameters_distribution['scale'][0]
+        dim_w = len(self.w_domain)
+        first = gamma.rvs(a, scale=scale, size=(n_samples, dim_w))
+        second = gamma.rvs(a, scale=scale, size=(n_samples, dim_w))
+        self.w_double_sets = np.stack([first, second])
+
+    def set_w_double_sets(self, w_double_sets):
+        w = np.asarray(w_double_sets, dtype=float)
+        if w.ndim != 3 or w.shape[0] != 2:
+            raise ValueError("w_double_sets must be [2][n_samples][d_w]")
+        self.w_double_sets = w
 
     # -- device objects ------------------------------------------------------------------------------
     def bounds_x(self):
@@ -186,11 +203,25 @@ class BayesianQuadrature(object):
             out[: g.shape[0], i] = g
         return out
 
-    def evaluate_quadrate_cov(self, point, parameters_kernel, w_set=0, w_set_2=0):
-        """E_W E_W' k: :282-306 -> float (finite W: exact weighted double sum)."""
-        p1 = self._new_points(point, w_set)
-        p2 = self._new_points(point, w_set_2)
-        vals = torch.as_tensor(self.gp.evaluate_cross_cov(p1, p2, parameters_kernel))
+    def evaluate_quadrate_cov(self, point, parameters_kernel):
+        """E_W E_W' k((x, W), (x, W')): :282-306 -> float.  Finite W: the exact (weighted) double
+        sum over tasks.  Gamma / exponential W: the mean of k over the full grid of two independent
+        sets of 100 draws (`w_double_sets`, drawn like the reference on first use unless given by
+        set_w_double_sets -- the reference redraws them at every call)."""
+        point = np.asarray(point, dtype=float).reshape(1, -1)
+        if self.w_sets is not None:
+            if self.w_double_sets is None:
+                self.resample_w_double()
+            both = []
+            for w in self.w_double_sets:
+                pts = np.zeros((w.shape[0], len(self.w_domain) + point.shape[1]))
+                pts[:, self.x_domain] = np.repeat(point, w.shape[0], axis=0)
+                pts[:, self.w_domain] = w
+                both.append(pts)
+            vals = torch.as_tensor(self.gp.evaluate_cross_cov(both[0], both[1], parameters_kernel))
+            return float(vals.mean())
+        p1 = self._new_points(point)
+        vals = torch.as_tensor(self.gp.evaluate_cross_cov(p1, p1, parameters_kernel))
         if self.weights is None:
             return float(vals.mean())
         w = torch.as_tensor(self.weights, dtype=vals.dtype)
@@ -218,7 +249,7 @@ class BayesianQuadrature(object):
         B = torch.as_tensor(self.evaluate_quadrature_cross_cov(
             points[0:1, :], self.gp.data['points'], theta[2:], w_set), device=bq.eng.device)
         sol = bq.hb.solve(B.reshape(1, 1, -1).clone())
-        cov = self.evaluate_quadrate_cov(points[0:1, :], theta[2:], w_set, w_set) - \
+        cov = self.evaluate_quadrate_cov(points[0:1, :], theta[2:]) - \
             float((B * sol[0, 0]).sum())
         return {'mean': mu_n, 'cov': cov}
 

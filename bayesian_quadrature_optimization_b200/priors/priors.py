@@ -121,7 +121,7 @@ class Constant(object):
         self.dimension, self.value = dimension, value
 
     def logprob(self, x):
-        return 0.0
+        return 0.0 if self.value == x[0] else -np.inf
 
     def sample(self, samples, random_seed=None):
-        return self.value * np.ones((samples, self.dimension))
+        return self.value * np.ones((samples, 1))

@@ -48,9 +48,17 @@ def test_no_cpu_fallback_without_cuda():
     with pytest.raises(_cabi.BqoLibraryError):
         engine.GPEngine(_cabi.KIND_MATERN52, 1)
     from bayesian_quadrature_optimization_b200.models.gp_fitting_gaussian import GPFittingGaussian
-    with pytest.raises(_cabi.BqoLibraryError):
-        GPFittingGaussian(["Matern52"], {"points": [[0.0], [1.0]], "evaluations": [0.0, 1.0],
-                                         "var_noise": []}, [1], bounds_domain=[[0, 1]])
+    # building the model is host-only work (defaults, priors, samplers); every number comes from
+    # the device, so the first numerical call fails loudly
+    gp = GPFittingGaussian(["Matern52"], {"points": [[0.0], [1.0]], "evaluations": [0.0, 1.0],
+                                          "var_noise": []}, [1], bounds_domain=[[0, 1]])
+    for call in (lambda: gp.log_likelihood(0.0, 0.0, np.array([1.0])),
+                 lambda: gp.log_prob_parameters(np.array([0.0, 0.0, 1.0])),
+                 lambda: gp.sample_parameters(1),
+                 lambda: gp.compute_posterior_parameters(np.array([[0.5]])),
+                 lambda: gp.evaluate_cov(np.array([[0.5]]), np.array([1.0]))):
+        with pytest.raises(_cabi.BqoLibraryError):
+            call()
 
 
 def test_product_has_no_oracle_import():

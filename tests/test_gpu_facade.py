@@ -47,6 +47,7 @@ def _models(g):
         bq = BayesianQuadrature(gp, list(range(dx)), K.GAMMA,
                                 parameters_distribution={"a": [2.0], "scale": [1.0]})
         bq.set_w_sets(g["wset"])
+        bq.set_w_double_sets(g["w100"])
     return gp, bq
 
 
@@ -101,9 +102,10 @@ def test_quadrature_and_sbo_facade_against_reference(golden, name):
             assert_close(post["mean"][0], g["q_mean"][s, p], rtol=1e-10)
             assert_close(bq.gradient_posterior_mean(x, vn, mu, pk), g["grad_q_mean"][s, p],
                          rtol=1e-9, atol=1e-13)
-            if "w100" not in g:  # finite W: the double expectation is exact
-                full = bq.compute_posterior_parameters(x, vn, mu, pk)
-                assert_close(full["cov"], g["q_var"][s, p], rtol=max(1e-8, tol), atol=1e-11)
+            # prior variance: exact double sum (finite W) or the 100 x 100 grid of the replayed
+            # gamma draws (a22, sbo/lib/expectations.py:93-112)
+            full = bq.compute_posterior_parameters(x, vn, mu, pk)
+            assert_close(full["cov"], g["q_var"][s, p], rtol=max(1e-8, tol), atol=1e-11)
         for c in range(cands.shape[0]):
             cand = cands[c:c + 1, :]
             par = bq.get_parameters_for_samples(True, cand, pk, vn, mu)
