@@ -206,4 +206,8 @@ class EI(object):
         return results[ind_max]
 
     def clean_cache(self):
-        self.gp.clean_cache() if hasattr(self.gp, 'clean_cache') else None
+        """ei.py:319-323; the GP keeps its device factors (GPFittingGaussian.clean_cache)."""
+        if hasattr(self.gp, 'gp'):  # EI on a BayesianQuadrature model
+            self.gp.clean_cache()
+        else:
+            self.gp.clean_cache(keep_factors=True)

@@ -401,10 +401,19 @@ class SBO(object):
             g[:, :dim_m] = -res['gradient']               # maximise: descend on -acquisition
             bad = torch.isnan(g).any(dim=1)
             if bool(bad.any()):
-                # gradient unavailable (den = 0): random perturbation of relative size 1e-6
-                # (stochastic_gradient_descent.py:51-75), no Adam step for those restarts
-                pert = 1e-6 * pts.norm(dim=1, keepdim=True) * (2 * torch.rand_like(pts) - 1)
-                pts = torch.where(bad.unsqueeze(1), torch.min(torch.max(pts + pert, lo_d), up_d), pts)
+                # gradient unavailable (den = 0): uniform perturbation of relative size 1e-6 inside
+                # the box (stochastic_gradient_descent.py:51-75), no Adam step for those restarts.
+                # Only the continuous coordinates move -- a task id must stay an integer -- and
+                # the draws come from numpy so that random_seed fixes the run.
+                rows = np.nonzero(bad.cpu().numpy())[0]
+                host = pts[bad].cpu().numpy()
+                for r in range(host.shape[0]):
+                    size = np.sqrt(np.sum(host[r] ** 2)) * 1e-6
+                    for i in range(dim_m):
+                        lb = min(size, host[r, i] - lo[i])
+                        ub = min(size, up[i] - host[r, i])
+                        host[r, i] += np.random.uniform(-lb, ub)
+                pts[torch.as_tensor(rows, device=eng.device)] = eng.to_device(host)
                 g = torch.where(bad.unsqueeze(1), torch.zeros_like(g), g)
             _cabi.check(eng.lib.bqo_adam_step_batched(
                 _cabi.ptr(pts), _cabi.ptr(g.contiguous()), _cabi.ptr(m0), _cabi.ptr(v0),

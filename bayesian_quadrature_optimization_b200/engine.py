@@ -165,6 +165,10 @@ class HyperBatch(object):
             raise ValueError("appended() needs a factorised batch and exactly one new point")
         n, S = eng.n, self.S
         hb2 = HyperBatch(eng2, self.theta)
+        if np.any(self.info != 0) or np.any(self.jitter > 0):
+            # a failed factor is not a factor, and a jittered one was built for the old mean(diag):
+            # the reference restarts the jitter policy from 0 on the new matrix (la_functions.py:8-38)
+            return hb2.factorize()
         knew = hb2.cross_cov(eng2.X[n:n + 1]).reshape(S, n + 1).clone()
         extra = self.theta[:, 0] + eng.to_device(self.jitter)
         if eng2.noise_obs is not None:
@@ -260,8 +264,9 @@ class BQEngine(object):
     """Bayesian-quadrature stage B/C on top of a factorised HyperBatch."""
 
     def __init__(self, hb: HyperBatch, dx: int, weights=None, wsets=None, lower=None, upper=None,
-                 bq_var_noise=None):
+                 bq_var_noise=None, w_double=None):
         self.hb = hb.factorize()
+        self.w_double = w_double  # [2][n_samples][d_w]: the two draws of the prior variance
         self.eng = eng = hb.eng
         d = eng.desc
         self.dx = int(dx)
@@ -383,17 +388,25 @@ class BQEngine(object):
             v = torch.einsum('a,sab,b->s', w, C, w)
             return v.unsqueeze(1).expand(hb.S, P).contiguous()
         # stationary kernel: k((x, w), (x, w')) only depends on w - w', so the double mean over the
-        # W set is the same for every x; computed once per (engine, W set) and broadcast
+        # two independent W draws (gamma_expect with double=True, sbo/lib/expectations.py:93-112;
+        # `w_double`, else the W set against itself) is the same for every x: computed once per
+        # engine and broadcast
         cache = self.__dict__.setdefault("_prior_var_cache", {})
-        v = cache.get(int(w_set))
+        key = "double" if self.w_double is not None else int(w_set)
+        v = cache.get(key)
         if v is None:
-            ws = self.wsets[w_set]
-            M = int(ws.shape[0])
-            pts = torch.cat([xpts[0:1].expand(M, self.dx), ws], dim=1).contiguous()
+            if self.w_double is not None:
+                wd = eng.to_device(self.w_double)
+                w1, w2 = wd[0], wd[1]
+            else:
+                w1 = w2 = self.wsets[w_set]
+            x0 = xpts[0:1]
+            p1 = torch.cat([x0.expand(int(w1.shape[0]), self.dx), w1], dim=1).contiguous()
+            p2 = torch.cat([x0.expand(int(w2.shape[0]), self.dx), w2], dim=1).contiguous()
             tmp = GPEngine(d.kind, d.dim, d.n_tasks, bool(d.same_corr), device=eng.device)
-            tmp.set_data(pts, torch.zeros(M, dtype=F64, device=eng.device))
-            v = tmp.hypers(hb.theta).cov().mean(dim=(1, 2))
-            cache[int(w_set)] = v
+            tmp.set_data(p2, torch.zeros(int(p2.shape[0]), dtype=F64, device=eng.device))
+            v = tmp.hypers(hb.theta).cross_cov(p1).mean(dim=(1, 2))
+            cache[key] = v
         return v.unsqueeze(1).expand(hb.S, P).contiguous()
 
     def quadrature_posterior(self, xpts, w_set=0, var=True):

@@ -382,17 +382,34 @@ class GPFittingGaussian(object):
         self.clean_cache()
         self._eng = None
         if point.shape[0] == 1 and old_eng is not None and self.incremental_updates:
-            factored = [(k, hb) for k, hb in old_cache.items() if hb.L is not None]
-            if factored:
+            # only the batches that are asked for again after the update: the model's own
+            # parameter values (fixed / MLE) and the state of the slice-sampling chain, which the
+            # next start_new_chain / sample_parameters call evaluates first.  Probe batches of past
+            # slice-sampling sweeps are dropped; the old factors are released one by one so that
+            # old and new copies of the whole cache never coexist.
+            wanted = [np.ascontiguousarray(self.get_value_parameters_model.reshape(1, -1)).tobytes()]
+            if len(self.samples_parameters) > 0:
+                last = np.asarray(self.samples_parameters[-1], dtype=float).reshape(1, -1)
+                wanted.append(np.ascontiguousarray(last).tobytes())
+            keep = [(k, old_cache[k]) for k in dict.fromkeys(wanted)
+                    if k in old_cache and old_cache[k].L is not None]
+            old_cache.clear()
+            if keep:
                 eng2 = self._engine()
-                for key, hb in factored:
+                while keep:
+                    key, hb = keep.pop()
                     self._hb_cache[key] = hb.appended(eng2)
+                    del hb
 
     incremental_updates = True  # class-level switch (tests compare both paths)
     batched_slice_probes = True  # slice sampler sends independent probes in one batched call
 
-    def clean_cache(self):
-        self._hb_cache = OrderedDict()
+    def clean_cache(self, keep_factors=False):
+        """:1628-1637.  `keep_factors=True` (used by the acquisition functions' clean_cache) keeps
+        the device-resident factors: they are keyed by parameter values and always belong to the
+        current data (add_points_evaluations rebuilds or extends them), so they never go stale."""
+        if not keep_factors:
+            self._hb_cache = OrderedDict()
         self._log_prob_memo = OrderedDict()
         self.best_solution = {}
 

@@ -83,6 +83,7 @@ class BayesianQuadrature(object):
         self.w_double_sets = None
         if not finite:
             self.resample_w(n_w_sets)
+            self.resample_w_double()
         self._bq_cache = OrderedDict()
         self.optimal_solutions = {}
         self.max_mean = {}
@@ -120,6 +121,7 @@ class BayesianQuadrature(object):
         if w.ndim != 3 or w.shape[0] != 2:
             raise ValueError("w_double_sets must be [2][n_samples][d_w]")
         self.w_double_sets = w
+        self._bq_cache = OrderedDict()
 
     # -- device objects ------------------------------------------------------------------------------
     def bounds_x(self):
@@ -137,10 +139,15 @@ class BayesianQuadrature(object):
             lower = np.array([b[0] for b in bx], dtype=float)
             upper = np.array([b[-1] for b in bx], dtype=float)
             bq = BQEngine(hb, len(self.x_domain), weights=self.weights, wsets=self.w_sets,
-                          lower=lower, upper=upper, bq_var_noise=self.var_noise)
+                          lower=lower, upper=upper, bq_var_noise=self.var_noise,
+                          w_double=self.w_double_sets)
             self._bq_cache[key] = bq
             while len(self._bq_cache) > 8:
                 self._bq_cache.popitem(last=False)
+        # a batch the GP has evicted from its factor cache must not stay alive through this one
+        alive = set(id(h) for h in self.gp._hb_cache.values())
+        for k in [k for k in self._bq_cache if k not in alive]:
+            del self._bq_cache[k]
         return bq
 
     def _theta(self, var_noise, mean, parameters_kernel):
@@ -148,8 +155,15 @@ class BayesianQuadrature(object):
         return np.concatenate([[var_noise, mean], parameters_kernel])
 
     def clean_cache(self):
+        """:1579-1588: quadrature caches; the GP keeps its device factors (GPFittingGaussian.clean_cache)."""
         self._bq_cache = OrderedDict()
-        self.gp.clean_cache()
+        self.optimal_solutions = {}
+        self.max_mean = {}
+        self.best_solution = {}
+        self.var_noise = None
+        if self.gp.noise and self.gp.data.get('var_noise') is not None:
+            self.var_noise = np.mean(self.gp.data.get('var_noise'))
+        self.gp.clean_cache(keep_factors=True)
 
     # -- expectations of the kernel ------------------------------------------------------------------
     def _new_points(self, point, w_set=0):

@@ -358,35 +358,63 @@ def test_mle_parameters_and_serialisation_roundtrip(golden):
 
 
 def test_add_points_extends_cached_factors(golden):
-    """add_points_evaluations keeps the cached hyper-sample batches alive by appending to their
-    factors; results equal those of the invalidate-and-refactorise path of the reference."""
+    """add_points_evaluations extends the factors that are asked for again after the update -- the
+    model's own parameter values and the state of the slice-sampling chain -- in O(n^2) and drops
+    every other cached batch; results equal the invalidate-and-refactorise path of the reference."""
     from bayesian_quadrature_optimization_b200.models.gp_fitting_gaussian import GPFittingGaussian
     g = golden("scaled_gamma")
     gp_inc, _ = _models(g)
     gp_ref, _ = _models(g)
     gp_ref.incremental_updates = False
     thetas = g["thetas"]
-    for gp in (gp_inc, gp_ref):
-        gp.log_likelihood_batch(thetas)  # factors of all hyper-samples become resident
     rng = np.random.RandomState(9)
     for it in range(3):
+        for gp in (gp_inc, gp_ref):
+            gp.samples_parameters = [thetas[1].copy()]
+            gp.log_likelihood_batch(thetas)          # a probe batch: not reused after the update
+            for th in thetas:                        # single-theta batches (model values = thetas[0])
+                gp.log_likelihood(th[0], th[1], th[2:])
+        assert len(gp_inc._hb_cache) == 4
         p = np.concatenate([rng.uniform(0, 1, int(g["dx"])),
                             rng.gamma(2.0, 1.0, g["points"].shape[1] - int(g["dx"]))]).reshape(1, -1)
         v = np.array([np.sin(p.sum())])
         gp_inc.add_points_evaluations(p, v)
         gp_ref.add_points_evaluations(p, v)
-        assert len(gp_inc._hb_cache) >= 1 and len(gp_ref._hb_cache) == 0
+        assert len(gp_inc._hb_cache) == 2 and len(gp_ref._hb_cache) == 0
         for hb in gp_inc._hb_cache.values():
-            assert hb.L is not None and hb.eng.n == len(gp_inc.data['evaluations'])
-        a = gp_inc.log_likelihood_batch(thetas)
-        b = gp_ref.log_likelihood_batch(thetas)
-        assert_close(a, b, rtol=1e-11, what="llh after %d appended points" % (it + 1))
+            assert hb.S == 1 and hb.L is not None and hb.eng.n == len(gp_inc.data['evaluations'])
+        kept = [hb.theta.cpu().numpy()[0] for hb in gp_inc._hb_cache.values()]
+        assert sorted(map(tuple, kept)) == sorted(map(tuple, thetas[:2]))
+        for th in thetas[:2]:
+            n_cached = len(gp_inc._hb_cache)
+            a = gp_inc.log_likelihood(th[0], th[1], th[2:])
+            assert len(gp_inc._hb_cache) == n_cached  # served by the extended factor
+            b = gp_ref.log_likelihood(th[0], th[1], th[2:])
+            assert_close(a, b, rtol=1e-11, what="llh after %d appended points" % (it + 1))
         q = g["query"][0:2]
         th = thetas[0]
         pa = gp_inc.compute_posterior_parameters(q, th[0], th[1], th[2:])
         pb = gp_ref.compute_posterior_parameters(q, th[0], th[1], th[2:])
         assert_close(pa["mean"], pb["mean"], rtol=1e-9, atol=1e-12)
         assert_close(pa["cov"], pb["cov"], rtol=1e-7, atol=1e-11)
+
+
+def test_acquisition_clean_cache_keeps_the_extended_factors(golden):
+    """The BO loop (services/bgo.py) calls acquisition_function.clean_cache() right after
+    add_points_evaluations: the quadrature caches go, the GP's device factors stay."""
+    from bayesian_quadrature_optimization_b200.acquisition_functions.sbo import SBO
+    g = golden("scaled_gamma")
+    gp, bq = _models(g)
+    sbo = SBO(bq)
+    th = gp.get_value_parameters_model
+    gp.log_likelihood(th[0], th[1], th[2:])
+    bq.max_mean[(th[0], th[1], tuple(th[2:]))] = 1.0
+    p = np.concatenate([[0.3, 0.6], [1.0, 2.0]]).reshape(1, -1)
+    gp.add_points_evaluations(p, np.array([0.5]))
+    sbo.clean_cache()
+    assert len(gp._hb_cache) == 1 and bq.max_mean == {} and len(bq._bq_cache) == 0
+    hb = next(iter(gp._hb_cache.values()))
+    assert hb.L is not None and hb.eng.n == len(gp.data['evaluations'])
 
 
 def test_batched_slice_probes_give_the_sequential_chain():
