@@ -85,6 +85,7 @@ _IO = C.POINTER(InnerOpt)
 SIGNATURES = {
     "bqo_abi_version": (C.c_int, []),
     "bqo_set_device": (C.c_int, [C.c_int]),
+    "bqo_launch_count": (_L, []),
     "bqo_hyper_stride": (_L, [_KD]),
     "bqo_fp64_peak_probe": (C.c_int, [C.c_int, C.c_int, C.POINTER(_D), C.POINTER(_D)]),
     "bqo_hbm_copy_probe": (C.c_int, [_P, _P, _L, C.c_int, C.POINTER(_D)]),

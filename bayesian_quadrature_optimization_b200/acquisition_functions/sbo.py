@@ -42,6 +42,12 @@ class SBO(object):
         self.inner_pgtol = 1e-5
         self.inner_max_ls = 20
         self.last_n_evals = None
+        # multi-GPU (replaces the fork/pickle pool of sbo/lib/parallel.py:16-76): with
+        # torch.distributed initialised (one process per GPU, every process running the same
+        # program with the same seeds) and `distributed = True`, the hyper-samples are sharded
+        # over the ranks -- each GPU factorises and scores only its slice -- and the per-candidate
+        # partial sums meet in one all_gather + rank-ordered sum per acquisition evaluation
+        self.distributed = False
 
     # -- one sample path ------------------------------------------------------------------------------
     def evaluate_sample(self, point, candidate_point, sample, var_noise=None, mean=None,
@@ -167,15 +173,18 @@ class SBO(object):
         return grad[0, :]
 
     # -- Monte-Carlo Bayesian estimate over many candidates -----------------------------------------------
-    def _max_posterior_mean(self, bq, parameters, n_restarts=100):
+    def _max_posterior_mean(self, bq, parameters, n_restarts=100, always_draw=False):
         """max_x E[G(x)] per hyper-sample (optimize_posterior_mean, bayesian_quadrature.py:693-910,
-        called from sbo.py:597-620): the same device maximiser with Z = 0, i.e. the objective a(x)."""
+        called from sbo.py:597-620): the same device maximiser with Z = 0, i.e. the objective a(x).
+        `bq` holds exactly the hyper-samples of `parameters`."""
         missing = [k for k, p in enumerate(parameters)
                    if (p[0], p[1], tuple(p[2:])) not in self.bq.max_mean]
-        if missing:
+        if missing or always_draw:
             bounds_x = self._bounds_x()
+            # (always_draw: ranks with nothing missing still consume the same random numbers)
             starts = np.array(DomainService.get_points_domain(
                 n_restarts + 1, bounds_x, type_bounds=len(bounds_x) * [0]))
+        if missing:
             ub = bq.setup(self.bq._dummy_candidate())
             mx, arg, _ = bq.inner_maximize(ub, np.zeros(1), starts, maxiter=15000, factr=1e7,
                                            pgtol=self.inner_pgtol, max_ls=self.inner_max_ls,
@@ -190,13 +199,69 @@ class SBO(object):
                     {'solution': arg[k], 'optimal_value': mx[k]})
         return np.array([self.bq.max_mean[(p[0], p[1], tuple(p[2:]))] for p in parameters])
 
+    def _world(self):
+        from .. import distributed as D
+        rank, ws = D.world()
+        return (rank, ws) if self.distributed else (0, 1)
+
+    def _evaluate_candidates(self, parameters, candidate_points, samples, start, compute_max_mean,
+                             compute_gradient, hyper_indices=None, **opt):
+        """value [C] and gradient [C][dim_m] (device tensors) of the Monte-Carlo acquisition for
+        the hyper-samples `parameters` (all of them, or those at `hyper_indices`).  Single GPU: one
+        pass over every hyper-sample.  Distributed: this rank's slice of `parameters` only, then
+        one all_gather + rank-ordered sum of the partial sums (bit-identical on all ranks)."""
+        from .. import distributed as D
+        rank, ws = self._world()
+        S = len(parameters)
+        lo, hi = D.shard_range(S, rank, ws) if ws > 1 else (0, S)
+        if ws > 1 and hi == lo:
+            raise ValueError("distributed SBO needs at least one hyper-sample per rank")
+        local = parameters[lo:hi]
+        bq = self.bq.engine_for(np.array(local))
+        max_mean = None
+        if compute_max_mean:
+            max_mean = self._max_posterior_mean(bq, local, always_draw=ws > 1)
+        else:
+            mm = [self.bq.max_mean.get((p[0], p[1], tuple(p[2:])), 0) for p in local]
+            if any(m != 0 for m in mm):
+                max_mean = np.array(mm, dtype=float)
+        n_used = S
+        idx = None
+        if hyper_indices is not None:
+            n_used = len(hyper_indices)
+            idx = [int(k) - lo for k in hyper_indices if lo <= int(k) < hi]
+            if max_mean is not None:
+                max_mean = max_mean[idx]
+        dim_m = bq.eng.desc.dim_m
+        Cn = int(np.asarray(candidate_points.shape[0]))
+        if idx is not None and len(idx) == 0:      # none of the drawn hyper-samples lives here
+            value = torch.zeros(Cn, dtype=torch.float64, device=bq.eng.device)
+            grad = torch.zeros(Cn, dim_m, dtype=torch.float64, device=bq.eng.device)
+            n_loc = 0
+        else:
+            res = bq.evaluate_candidates(
+                candidate_points, samples, start, max_mean=max_mean,
+                compute_gradient=compute_gradient, hyper_indices=idx,
+                maxiter=opt.get('maxiter', 15000), factr=opt.get('factr', 1e7),
+                pgtol=self.inner_pgtol, max_ls=self.inner_max_ls,
+                use_vertices=len(self._bounds_x()) < 7)
+            value, grad = res['evaluations'], res['gradient']
+            n_loc = (hi - lo) if idx is None else len(idx)
+        if ws == 1:
+            return value, grad
+        parts = [value.reshape(-1, 1) * float(n_loc)]
+        if compute_gradient:
+            parts.append(grad * float(n_loc))
+        tot = D.allgather_ordered_sum(torch.cat(parts, dim=1).contiguous()) / float(n_used)
+        return tot[:, 0].contiguous(), (tot[:, 1:].contiguous() if compute_gradient else None)
+
     def evaluate_mc_bayesian_candidate_points_no_restarts(
             self, candidate_points, n_samples_parameters, n_samples, n_restarts=10, n_threads=0,
             compute_max_mean=False, compute_gradient=False, method_opt=None, **opt_params_mc):
         """:523-670 -> {'evaluations': np.array(n), 'gradient': np.array(n x k)}.
 
         Same argument meaning as the reference; the C x S x Z inner maximisations the reference
-        farms out to a process pool run as one kernel launch."""
+        farms out to a process pool run as one kernel launch (per GPU when `distributed`)."""
         gp = self.bq.gp
         if n_samples_parameters == 0:
             parameters = [gp.get_value_parameters_model]
@@ -205,23 +270,12 @@ class SBO(object):
         samples, start = self.generate_samples_starting_points_evaluate_mc(
             n_samples, n_restarts, cache=False)
         candidate_points = np.asarray(candidate_points, dtype=float)
-        bq = self.bq.engine_for(np.array(parameters))
-        max_mean = None
-        if compute_max_mean:
-            max_mean = self._max_posterior_mean(bq, parameters)
-        else:
-            mm = [self.bq.max_mean.get((p[0], p[1], tuple(p[2:])), 0) for p in parameters]
-            if any(m != 0 for m in mm):
-                max_mean = np.array(mm, dtype=float)
-        res = bq.evaluate_candidates(
-            candidate_points, samples, start, max_mean=max_mean, compute_gradient=compute_gradient,
-            maxiter=opt_params_mc.get('maxiter', 15000), factr=opt_params_mc.get('factr', 1e7),
-            pgtol=self.inner_pgtol, max_ls=self.inner_max_ls,
-            use_vertices=len(self._bounds_x()) < 7)
-        evaluations = res['evaluations'].cpu().numpy()
+        value, grad = self._evaluate_candidates(parameters, candidate_points, samples, start,
+                                                compute_max_mean, compute_gradient, **opt_params_mc)
+        evaluations = value.cpu().numpy()
         gradient = None
         if compute_gradient:
-            g = res['gradient'].cpu().numpy()
+            g = grad.cpu().numpy()
             pad = candidate_points.shape[1] - g.shape[1]
             if pad > 0:  # task coordinate: zero gradient (NaN rows stay NaN)
                 extra = np.where(np.isnan(g[:, :1]), np.nan, 0.0)
@@ -374,7 +428,10 @@ class SBO(object):
         # ---- batched Adam over all restarts --------------------------------------------------------
         parameters = gp.samples_parameters[-n_parameters:] if n_parameters > 0 else \
             [gp.get_value_parameters_model]
-        bqe = bq.engine_for(np.array(parameters))
+        from .. import distributed as D
+        rank, ws = self._world()
+        lo_s, hi_s = D.shard_range(len(parameters), rank, ws) if ws > 1 else (0, len(parameters))
+        bqe = bq.engine_for(np.array(parameters[lo_s:hi_s]))
         eng = bqe.eng
         dim = start.shape[1]
         dim_m = eng.desc.dim_m
@@ -393,12 +450,10 @@ class SBO(object):
             zs = np.random.normal(0, 1, n_zs)
             starts_x = np.array(DomainService.get_points_domain(
                 default_restarts_mc + 1, bx, type_bounds=len(bx) * [0]))
-            res = bqe.evaluate_candidates(
-                pts, zs, starts_x, compute_gradient=True, hyper_indices=ks,
-                maxiter=opt_params_mc.get('maxiter', 15000), factr=opt_params_mc.get('factr', 1e7),
-                pgtol=self.inner_pgtol, max_ls=self.inner_max_ls, use_vertices=len(bx) < 7)
+            _, grad_t = self._evaluate_candidates(parameters, pts, zs, starts_x, False, True,
+                                                  hyper_indices=ks, **opt_params_mc)
             g = torch.zeros(R, dim, dtype=torch.float64, device=eng.device)
-            g[:, :dim_m] = -res['gradient']               # maximise: descend on -acquisition
+            g[:, :dim_m] = -grad_t                        # maximise: descend on -acquisition
             bad = torch.isnan(g).any(dim=1)
             if bool(bad.any()):
                 # gradient unavailable (den = 0): uniform perturbation of relative size 1e-6 inside

@@ -5,6 +5,11 @@
 
 extern "C" int bqo_abi_version(void) { return BQO_ABI_VERSION; }
 
+#include <atomic>
+static std::atomic<long long> g_bqo_launches{0};
+extern "C" long long bqo_launch_count_add(long long delta) { return g_bqo_launches.fetch_add(delta) + delta; }
+extern "C" int64_t bqo_launch_count(void) { return (int64_t)g_bqo_launches.load(); }
+
 extern "C" int bqo_set_device(int device) { return (int)cudaSetDevice(device); }
 
 extern "C" int64_t bqo_hyper_stride(const bqo_kernel_desc* desc) {
@@ -77,7 +82,7 @@ extern "C" int bqo_hyper_prepare(const bqo_kernel_desc* desc, const double* thet
     BQO_CHECK_ARG(theta != nullptr, 2);
     BQO_CHECK_ARG(S > 0, 3);
     BQO_CHECK_ARG(hyp != nullptr, 4);
-    hyper_prepare_kernel<<<S, 128, 0, (cudaStream_t)stream>>>(*desc, theta, hyp,
+    BQO_L, hyper_prepare_kernel<<<S, 128, 0, (cudaStream_t)stream>>>(*desc, theta, hyp,
                                                              bqo_hyper_stride_impl(*desc));
     BQO_RETURN_LAST_ERROR();
 }
@@ -108,7 +113,7 @@ extern "C" int bqo_scale_points(const bqo_kernel_desc* desc, const double* hyp, 
     BQO_CHECK_ARG(Xs != nullptr, 7);
     BQO_CHECK_ARG(desc->kind != BQO_KIND_PRODUCT_TASKS || tid != nullptr, 8);
     dim3 grid((n + 255) / 256, S);
-    scale_points_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+    BQO_L, scale_points_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
         *desc, hyp, bqo_hyper_stride_impl(*desc), X, n, ldx, Xs, tid);
     BQO_RETURN_LAST_ERROR();
 }
@@ -184,7 +189,7 @@ extern "C" int bqo_kernel_assemble_batched(const bqo_kernel_desc* desc, const do
     cudaStream_t cs = (cudaStream_t)stream;
     bqo_ensure_global_exp_table(cs);
 #define LAUNCH_ASM(DMV)                                                                          \
-    assemble_kernel<DMV><<<grid, block, 0, cs>>>(*desc, hyp, st, Xs, tid, n, noise_obs,          \
+    BQO_L, assemble_kernel<DMV><<<grid, block, 0, cs>>>(*desc, hyp, st, Xs, tid, n, noise_obs,          \
                                                  add_noise, extra_diag, K)
     switch (desc->dim_m) {
         case 1: LAUNCH_ASM(1); break;
@@ -280,7 +285,7 @@ extern "C" int bqo_kernel_grad_params_batched(const bqo_kernel_desc* desc, const
     BQO_CHECK_ARG(dK != nullptr, 7);
     dim3 block(32, 8);
     dim3 grid((n + 31) / 32, (n + 7) / 8, S);
-    grad_params_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
+    BQO_L, grad_params_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
         *desc, hyp, bqo_hyper_stride_impl(*desc), Xs, tid, n, dK);
     BQO_RETURN_LAST_ERROR();
 }
@@ -341,7 +346,7 @@ extern "C" int bqo_cross_cov_batched(const bqo_kernel_desc* desc, const double* 
     BQO_CHECK_ARG(KP != nullptr, 10);
     BQO_CHECK_ARG(S <= 65535, 3);
     dim3 grid((n + 255) / 256, m, S);
-    cross_cov_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+    BQO_L, cross_cov_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
         *desc, hyp, bqo_hyper_stride_impl(*desc), Xs, tid, n, P, m, interleave, KP, dKP);
     BQO_RETURN_LAST_ERROR();
 }
@@ -371,7 +376,7 @@ extern "C" int bqo_task_quadrature_weights(const bqo_kernel_desc* desc, const do
     BQO_CHECK_ARG(hyp != nullptr, 2);
     BQO_CHECK_ARG(S > 0, 3);
     BQO_CHECK_ARG(qt != nullptr, 5);
-    task_qweights_kernel<<<S, 128, 0, (cudaStream_t)stream>>>(
+    BQO_L, task_qweights_kernel<<<S, 128, 0, (cudaStream_t)stream>>>(
         *desc, hyp, bqo_hyper_stride_impl(*desc), weights, qt);
     BQO_RETURN_LAST_ERROR();
 }

@@ -275,18 +275,18 @@ static int potrf_launch(double* A, int n, int S, int* info, cudaStream_t cs) {
         const int tiles = (n - k0 + NB - 1) / NB;  // diagonal tile + row tiles below it
         if ((int64_t)tiles * S <= 3 * 148 || tiles == 1) {
             dim3 pg(tiles, S);
-            potrf_panel_kernel<0><<<pg, 128, SMEM_LS, cs>>>(A, n, k0, info, diag_scratch);
+            BQO_L, potrf_panel_kernel<0><<<pg, 128, SMEM_LS, cs>>>(A, n, k0, info, diag_scratch);
         } else {
             dim3 fg(1, S), sg(tiles - 1, S);
-            potrf_panel_kernel<1><<<fg, 128, SMEM_LS, cs>>>(A, n, k0, info, diag_scratch);
-            potrf_panel_kernel<2><<<sg, 128, SMEM_LS, cs>>>(A, n, k0, info, diag_scratch);
+            BQO_L, potrf_panel_kernel<1><<<fg, 128, SMEM_LS, cs>>>(A, n, k0, info, diag_scratch);
+            BQO_L, potrf_panel_kernel<2><<<sg, 128, SMEM_LS, cs>>>(A, n, k0, info, diag_scratch);
         }
     };
     auto syrk = [&](int kc, int K, int base, int ncolblk) {
         const int tr = (n - base + NB - 1) / NB;
         if (tr <= 0) return;
         dim3 sg(ncolblk < tr ? ncolblk : tr, tr, S);
-        potrf_syrk_kernel<<<sg, 128, SMEM_POTRF_SYRK, cs>>>(A, n, kc, K, base, ncolblk, info);
+        BQO_L, potrf_syrk_kernel<<<sg, 128, SMEM_POTRF_SYRK, cs>>>(A, n, kc, K, base, ncolblk, info);
     };
     // POTRF_W 64-wide panels per step.  Panel p of a step first receives, as a one-block-column
     // strip, the update of the p panels before it (K = 64 p); the full trailing update then runs
@@ -303,7 +303,7 @@ static int potrf_launch(double* A, int n, int S, int* info, cudaStream_t cs) {
         if (kend < n) syrk(k0, POTRF_W * NB, kend, 1 << 30);
     }
     dim3 zg((n + 255) / 256, n, S);
-    potrf_finish_kernel<<<zg, 256, 0, cs>>>(A, n, info, diag_scratch);
+    BQO_L, potrf_finish_kernel<<<zg, 256, 0, cs>>>(A, n, info, diag_scratch);
     cudaFreeAsync(diag_scratch, cs);
     return (int)cudaGetLastError();
 }
@@ -652,20 +652,20 @@ static int potrs_launch(const double* L, int n, int S, double* Bt, int m, int id
         // eliminated from the remaining rows by (rows / 64) x m x S CTAs
         for (int r0 = 0; r0 < n; r0 += TRSV_BLK) {
             const int r1 = (r0 + TRSV_BLK < n) ? r0 + TRSV_BLK : n;
-            trsv_kernel<true><<<grid, TRSV_THREADS, sb, cs>>>(L, n, Bt, m, r0, r1);
+            BQO_L, trsv_kernel<true><<<grid, TRSV_THREADS, sb, cs>>>(L, n, Bt, m, r0, r1);
             if (r1 < n) {
                 dim3 gg((n - r1 + 63) / 64, m, S);
-                trsv_gemv_fwd_kernel<<<gg, 256, 0, cs>>>(L, n, Bt, m, r0, r1);
+                BQO_L, trsv_gemv_fwd_kernel<<<gg, 256, 0, cs>>>(L, n, Bt, m, r0, r1);
             }
         }
         if (forward_only) return (int)cudaGetLastError();
         const int last = ((n - 1) / TRSV_BLK) * TRSV_BLK;
         for (int r0 = last; r0 >= 0; r0 -= TRSV_BLK) {
             const int r1 = (r0 + TRSV_BLK < n) ? r0 + TRSV_BLK : n;
-            trsv_kernel<false><<<grid, TRSV_THREADS, sb, cs>>>(L, n, Bt, m, r0, r1);
+            BQO_L, trsv_kernel<false><<<grid, TRSV_THREADS, sb, cs>>>(L, n, Bt, m, r0, r1);
             if (r0 > 0) {
                 dim3 gg((r0 + 63) / 64, m, S);
-                trsv_gemv_bwd_kernel<<<gg, 256, 0, cs>>>(L, n, Bt, m, r0, r1);
+                BQO_L, trsv_gemv_bwd_kernel<<<gg, 256, 0, cs>>>(L, n, Bt, m, r0, r1);
             }
         }
         return (int)cudaGetLastError();
@@ -679,9 +679,9 @@ static int potrs_launch(const double* L, int n, int S, double* Bt, int m, int id
         attr_done = true;
     }
     dim3 grid((m + NB - 1) / NB, S);
-    trsm_kernel<true><<<grid, 128, SMEM_TRSM, cs>>>(L, n, Bt, m, identity_rhs);
+    BQO_L, trsm_kernel<true><<<grid, 128, SMEM_TRSM, cs>>>(L, n, Bt, m, identity_rhs);
     if (forward_only) return (int)cudaGetLastError();
-    trsm_kernel<false><<<grid, 128, SMEM_TRSM, cs>>>(L, n, Bt, m, 0);
+    BQO_L, trsm_kernel<false><<<grid, 128, SMEM_TRSM, cs>>>(L, n, Bt, m, 0);
     return (int)cudaGetLastError();
 }
 
@@ -835,17 +835,17 @@ int bqo_internal_inverse_from_chol(const double* L, int n, int S, double* Inv, d
     cudaFuncSetAttribute(inv_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)SMEM_SYRK);
     dim3 dg(nb, S);
-    tri_inv_diag_kernel<<<dg, NB, smem_diag, cs>>>(L, n, Wbuf);
+    BQO_L, tri_inv_diag_kernel<<<dg, NB, smem_diag, cs>>>(L, n, Wbuf);
     for (int b = NB; b < n; b *= 2) {
         const int pairs = (n + 2 * b - 1) / (2 * b);
         if ((int64_t)pairs * S > 65535) return -3;
         dim3 lg(b / NB, b / NB, pairs * S);
         // Inv doubles as the scratch T of the levels; the final product overwrites all of it
-        tri_inv_level_kernel<1><<<lg, 128, SMEM_SYRK, cs>>>(L, Wbuf, Inv, n, b, pairs);
-        tri_inv_level_kernel<2><<<lg, 128, SMEM_SYRK, cs>>>(L, Wbuf, Inv, n, b, pairs);
+        BQO_L, tri_inv_level_kernel<1><<<lg, 128, SMEM_SYRK, cs>>>(L, Wbuf, Inv, n, b, pairs);
+        BQO_L, tri_inv_level_kernel<2><<<lg, 128, SMEM_SYRK, cs>>>(L, Wbuf, Inv, n, b, pairs);
     }
     dim3 sg(nb, nb, S);
-    inv_syrk_kernel<<<sg, 128, SMEM_SYRK, cs>>>(Wbuf, n, Inv);
+    BQO_L, inv_syrk_kernel<<<sg, 128, SMEM_SYRK, cs>>>(Wbuf, n, Inv);
     return (int)cudaGetLastError();
 }
 
@@ -895,7 +895,7 @@ extern "C" int bqo_chol_cov_batched(const bqo_kernel_desc* desc, const double* h
     double* extra_d = mean_d + S;
     // diagonal statistics of Sigma are needed only on failure, but they must be taken before the
     // in-place factorisation destroys the diagonal.
-    diag_stats_kernel<<<S, 256, 0, cs>>>(L, n, mean_d, nonpos_d);
+    BQO_L, diag_stats_kernel<<<S, 256, 0, cs>>>(L, n, mean_d, nonpos_d);
     rc = potrf_launch(L, n, S, info_d, cs);
     std::vector<int> info(S), nonpos(S);
     std::vector<double> mean(S), jit(S, 0.0), extra(S, 0.0);
@@ -1002,8 +1002,8 @@ extern "C" int bqo_chol_append_batched(const double* L_old, int32_t n, int32_t S
     int rc = potrs_launch(L_old, n, S, lrow, 1, 0, cs, true);  // forward solve only: L l = k
     if (rc) return rc;
     dim3 cg((n + 1 + 255) / 256, n + 1, S);
-    chol_append_copy_kernel<<<cg, 256, 0, cs>>>(L_old, n, L_new);
-    chol_append_row_kernel<<<S, 256, 0, cs>>>(lrow, knew, n, L_new, info);
+    BQO_L, chol_append_copy_kernel<<<cg, 256, 0, cs>>>(L_old, n, L_new);
+    BQO_L, chol_append_row_kernel<<<S, 256, 0, cs>>>(lrow, knew, n, L_new, info);
     BQO_RETURN_LAST_ERROR();
 }
 
@@ -1025,7 +1025,7 @@ extern "C" int bqo_alpha_batched(const double* hyp, int64_t hyp_stride, const do
     BQO_CHECK_ARG(alpha != nullptr, 7);
     cudaStream_t cs = (cudaStream_t)stream;
     dim3 grid((n + 255) / 256, S);
-    residual_kernel<<<grid, 256, 0, cs>>>(hyp, hyp_stride, y, n, alpha);
+    BQO_L, residual_kernel<<<grid, 256, 0, cs>>>(hyp, hyp_stride, y, n, alpha);
     // alpha is [S][1][n]: one right-hand side per matrix
     return potrs_launch(L, n, S, alpha, 1, 0, cs);
 }
@@ -1056,6 +1056,6 @@ extern "C" int bqo_loglik_batched(const double* hyp, int64_t hyp_stride, const d
     BQO_CHECK_ARG(n > 0, 6);
     BQO_CHECK_ARG(S > 0, 7);
     BQO_CHECK_ARG(llh != nullptr, 8);
-    loglik_kernel<<<S, 256, 0, (cudaStream_t)stream>>>(hyp, hyp_stride, L, alpha, y, n, llh);
+    BQO_L, loglik_kernel<<<S, 256, 0, (cudaStream_t)stream>>>(hyp, hyp_stride, L, alpha, y, n, llh);
     BQO_RETURN_LAST_ERROR();
 }

@@ -11,6 +11,12 @@
         if (!(cond)) return -(idx); \
     } while (0)
 
+// Every kernel launch of the library is written `BQO_L, kernel<<<...>>>(...)`: the comma expression
+// bumps a process-wide counter first, so bqo_launch_count() reports how many kernels this library
+// has launched (bench.py's `gpu_launches`).
+extern "C" long long bqo_launch_count_add(long long delta);
+#define BQO_L ((void)bqo_launch_count_add(1))
+
 #define BQO_RETURN_LAST_ERROR()              \
     do {                                     \
         cudaError_t e__ = cudaGetLastError(); \

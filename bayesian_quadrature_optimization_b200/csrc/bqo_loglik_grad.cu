@@ -202,8 +202,8 @@ extern "C" int bqo_loglik_grad_batched(const bqo_kernel_desc* desc, const double
     dim3 grid(1, nb, S);
     const int64_t st = bqo_hyper_stride_impl(*desc);
     bqo_ensure_global_exp_table(cs);
-    loglik_grad_partial_kernel<<<grid, 256, 0, cs>>>(*desc, hyp, st, Xs, tid, n, Inv, alpha, partial,
+    BQO_L, loglik_grad_partial_kernel<<<grid, 256, 0, cs>>>(*desc, hyp, st, Xs, tid, n, Inv, alpha, partial,
                                                      Wtask);
-    loglik_grad_final_kernel<<<S, 256, 0, cs>>>(*desc, hyp, st, partial, nb, alpha, n, Wtask, grad);
+    BQO_L, loglik_grad_final_kernel<<<S, 256, 0, cs>>>(*desc, hyp, st, partial, nb, alpha, n, Wtask, grad);
     BQO_RETURN_LAST_ERROR();
 }

@@ -84,12 +84,12 @@ extern "C" int bqo_posterior_batched(const bqo_kernel_desc* desc, const double* 
     const bool need_solve = (var != nullptr) || (gvar != nullptr);
     if (need_solve) {
         dim3 cg((n + 255) / 256, m, S);
-        copy_row0_kernel<<<cg, 256, 0, cs>>>(G, rows, n, m, Sol);
+        BQO_L, copy_row0_kernel<<<cg, 256, 0, cs>>>(G, rows, n, m, Sol);
         rc = bqo_potrs_batched(L, n, S, Sol, m, stream);
         if (rc) return rc;
     }
     dim3 grid(m, S);
-    posterior_reduce_kernel<<<grid, 256, 0, cs>>>(*desc, hyp, bqo_hyper_stride_impl(*desc), G,
+    BQO_L, posterior_reduce_kernel<<<grid, 256, 0, cs>>>(*desc, hyp, bqo_hyper_stride_impl(*desc), G,
                                                   need_solve ? Sol : G, alpha, P, n, m, mean,
                                                   need_solve ? var : nullptr, gmean,
                                                   need_solve ? gvar : nullptr);
@@ -140,7 +140,7 @@ extern "C" int bqo_ei_batched(const double* mean, const double* var, const doubl
     BQO_CHECK_ARG(ei != nullptr, 9);
     BQO_CHECK_ARG(gei == nullptr || (gmean != nullptr && gvar != nullptr && dim_g > 0), 10);
     int total = S * m;
-    ei_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mean, var, gmean, gvar, best,
+    BQO_L, ei_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mean, var, gmean, gvar, best,
                                                                      S, m, dim_g, ei, gei);
     BQO_RETURN_LAST_ERROR();
 }
@@ -276,7 +276,7 @@ extern "C" int bqo_kg_discretized_batched(const double* a, const double* b, int3
     BQO_CHECK_ARG(work != nullptr, 9);
     double* wd = (double*)work;
     int32_t* wi = (int32_t*)(wd + (int64_t)B * (3 * m + 2));
-    kg_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(a, b, m, kg, keep_count, keep_idx, c_out, wd, wi);
+    BQO_L, kg_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(a, b, m, kg, keep_count, keep_idx, c_out, wd, wi);
     BQO_RETURN_LAST_ERROR();
 }
 
@@ -325,7 +325,7 @@ extern "C" int bqo_adam_step_batched(double* point, const double* grad, double* 
     BQO_CHECK_ARG(m0 != nullptr && v0 != nullptr, 3);
     BQO_CHECK_ARG(active != nullptr, 5);
     BQO_CHECK_ARG(R > 0 && dim > 0 && t > 0, 8);
-    adam_step_kernel<<<(R + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+    BQO_L, adam_step_kernel<<<(R + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
         point, grad, m0, v0, active, lower, upper, R, dim, t, lr, beta1, beta2, eps);
     BQO_RETURN_LAST_ERROR();
 }

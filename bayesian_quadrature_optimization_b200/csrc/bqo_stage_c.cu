@@ -65,7 +65,7 @@ extern "C" int bqo_weight_alpha(const bqo_kernel_desc* desc, const double* alpha
     const bool prod = desc->kind == BQO_KIND_PRODUCT_TASKS;
     BQO_CHECK_ARG(!prod || (qt != nullptr && tid != nullptr), 3);
     dim3 grid((n + 255) / 256, S);
-    weight_alpha_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(alpha, prod ? qt : nullptr, tid,
+    BQO_L, weight_alpha_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(alpha, prod ? qt : nullptr, tid,
                                                                desc->n_tasks, n, out);
     BQO_RETURN_LAST_ERROR();
 }
@@ -138,7 +138,7 @@ extern "C" int bqo_candidate_setup_batched(const bqo_kernel_desc* desc, const do
     const bool prod = desc->kind == BQO_KIND_PRODUCT_TASKS;
     BQO_CHECK_ARG(!prod || (qt != nullptr && tid != nullptr), 10);
     dim3 grid(C, S);
-    candidate_setup_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+    BQO_L, candidate_setup_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
         *desc, hyp, bqo_hyper_stride_impl(*desc), G, R, n, C, cand, add_noise,
         prod ? qt : nullptr, tid, den, beta4);
     BQO_RETURN_LAST_ERROR();
@@ -569,7 +569,7 @@ extern "C" int bqo_sample_ab_batched(const bqo_stage_c* pb, const double* pts,
     int grid = (P + AB_WARPS - 1) / AB_WARPS;
     size_t smem = sizeof(double) * (BQO_EXP_TABLE + AB_WARPS * (size_t)(pb->M > 0 ? pb->M : 1) * (pb->dw > 0 ? pb->dw : 1));
 #define LAUNCH_AB(DXV, DWV) \
-    sample_ab_kernel<DXV, DWV><<<grid, AB_WARPS * 32, smem, cs>>>(*pb, pts, pt_unit, pt_wset, P, out)
+    BQO_L, sample_ab_kernel<DXV, DWV><<<grid, AB_WARPS * 32, smem, cs>>>(*pb, pts, pt_unit, pt_wset, P, out)
     SC_DISPATCH(pb, LAUNCH_AB);
 #undef LAUNCH_AB
     BQO_RETURN_LAST_ERROR();
@@ -626,7 +626,7 @@ extern "C" int bqo_wdist_precompute(const bqo_kernel_desc* desc, const double* h
     BQO_CHECK_ARG(out != nullptr, 11);
     const int64_t per = (int64_t)((n + 31) / 32) * M * 32;
     dim3 grid((unsigned)((per + 255) / 256), S, n_wsets);
-    wdist_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(hyp, bqo_hyper_stride_impl(*desc), Xs, n,
+    BQO_L, wdist_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(hyp, bqo_hyper_stride_impl(*desc), Xs, n,
                                                          desc->dim_m, dx, dw, wsets, n_wsets, M, out);
     BQO_RETURN_LAST_ERROR();
 }
@@ -1049,7 +1049,7 @@ extern "C" int bqo_inner_maximize_batched(const bqo_stage_c* pb, const bqo_inner
     do {                                                                                         \
         cudaFuncSetAttribute(inner_maximize_kernel<DXV, DWV, STG, MTV, WDV>,                     \
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SB));            \
-        inner_maximize_kernel<DXV, DWV, STG, MTV, WDV><<<grid, IM_WARPS * 32, (SB), cs>>>(       \
+        BQO_L, inner_maximize_kernel<DXV, DWV, STG, MTV, WDV><<<grid, IM_WARPS * 32, (SB), cs>>>(       \
             *pb, *opt, z, starts, out_max, out_arg, n_evals);                                    \
     } while (0)
 #define LAUNCH_IM(DXV, DWV)                                                                      \
@@ -1337,7 +1337,7 @@ extern "C" int bqo_grad_vector_b_batched(const bqo_stage_c* pb, const double* pt
         if (DWV > 0) {                                                                           \
             cudaFuncSetAttribute(grad_vector_b_staged_kernel<DXV, (DWV > 0 ? DWV : 1)>,          \
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);          \
-            grad_vector_b_staged_kernel<DXV, (DWV > 0 ? DWV : 1)>                                \
+            BQO_L, grad_vector_b_staged_kernel<DXV, (DWV > 0 ? DWV : 1)>                                \
                 <<<pb->n_units, IM_WARPS * 32, sb, cs>>>(*pb, pts, npts, out, is_nan);           \
         }                                                                                        \
     } while (0)
@@ -1350,7 +1350,7 @@ extern "C" int bqo_grad_vector_b_batched(const bqo_stage_c* pb, const double* pt
     int grid = (int)((total + AB_WARPS - 1) / AB_WARPS);
     size_t smem = sizeof(double) * (BQO_EXP_TABLE + AB_WARPS * (size_t)(pb->M > 0 ? pb->M : 1) * (pb->dw > 0 ? pb->dw : 1));
 #define LAUNCH_GVB(DXV, DWV) \
-    grad_vector_b_kernel<DXV, DWV><<<grid, AB_WARPS * 32, smem, cs>>>(*pb, pts, npts, pt_wset, out, is_nan)
+    BQO_L, grad_vector_b_kernel<DXV, DWV><<<grid, AB_WARPS * 32, smem, cs>>>(*pb, pts, npts, pt_wset, out, is_nan)
     SC_DISPATCH(pb, LAUNCH_GVB);
 #undef LAUNCH_GVB
     BQO_RETURN_LAST_ERROR();
@@ -1410,7 +1410,7 @@ extern "C" int bqo_acq_reduce(const double* out_max, const double* gvb, const in
     BQO_CHECK_ARG(C > 0 && S > 0 && n_z > 0 && dim_g >= 0, 6);
     BQO_CHECK_ARG(value != nullptr, 10);
     int total = C * (1 + dim_g);
-    acq_reduce_kernel<<<(total + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
+    BQO_L, acq_reduce_kernel<<<(total + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
         out_max, gvb, is_nan, z, max_mean, C, S, n_z, dim_g, value, grad);
     BQO_RETURN_LAST_ERROR();
 }

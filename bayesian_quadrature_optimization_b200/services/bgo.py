@@ -44,11 +44,27 @@ def bgo(objective_function, bounds_domain_x, integrand_function=None, simplex_do
         monte_carlo_sbo=True, n_samples_mc=5, n_restarts_mc=5, n_best_restarts_mc=0, factr_mc=1e12,
         maxiter_mc=10, method_opt_mc=LBFGS_NAME, n_restarts_mean=100, n_best_restarts_mean=10,
         n_samples_parameters_mean=5, maxepoch_mean=50, parallel_training=False,
-        default_n_samples_parameters=None, default_n_samples=None, device=None, n_chains=1):
+        default_n_samples_parameters=None, default_n_samples=None, device=None, n_chains=1,
+        distributed=False):
     """Maximises the objective function (sbo/services/bgo.py:37-121 documents every argument).
-    Two arguments are additions: `device` (CUDA device) and `n_chains` (> 1: the hyper-parameter
+    Three arguments are additions: `device` (CUDA device), `n_chains` (> 1: the hyper-parameter
     samples of every iteration come from that many independent slice-sampling chains advanced side
-    by side on the GPU instead of one sequential chain)."""
+    by side on the GPU instead of one sequential chain) and `distributed` (replaces the
+    `parallel` process pool of sbo/lib/parallel.py:16-76: run the same program on every GPU of the
+    node with `torchrun --nproc-per-node N`; the process group is created from the environment
+    when it does not exist yet, this process uses cuda:LOCAL_RANK, the hyper-samples of every
+    acquisition evaluation are sharded over the ranks and combined with one all_gather +
+    rank-ordered sum, so every rank takes bit-identical decisions)."""
+    if distributed:
+        import os
+        import torch
+        import torch.distributed as dist
+        if device is None:
+            device = "cuda:%d" % int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(torch.device(device))
+        if not dist.is_initialized():
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device(device))
     np.random.seed(random_seed)
     dim_x = len(bounds_domain_x)
     x_domain = list(range(dim_x))
@@ -114,6 +130,7 @@ def bgo(objective_function, bounds_domain_x, integrand_function=None, simplex_do
         quadrature = BayesianQuadrature(gp_model, x_domain, distribution,
                                         parameters_distribution=parameters_distribution)
         acquisition_function = SBO(quadrature)
+        acquisition_function.distributed = bool(distributed)
     else:
         acquisition_function = EI(gp_model, noisy_evaluations=noise)
 

@@ -157,11 +157,11 @@ class ClockSampler(object):
 
 
 # ------------------------------------------------------------------------------------------------
-def _cpu_unit_worker(args):
-    """One (candidate, hyper-sample) unit on the CPU oracle, timed with Z = z_lo and Z = z_hi Z
-    samples so that the per-unit fixed cost and the per-Z cost can be separated."""
+REFERENCE_ROOT = "/root/reference"
+
+
+def _limit_blas_threads():
     os.environ["OMP_NUM_THREADS"] = "1"
-    cand_idx, hyper_idx, z_lo, z_hi = args
     try:
         # one BLAS/OpenMP thread per worker (the pool already uses every core); the environment
         # variable alone does not reach libraries the parent process loaded before the fork
@@ -169,6 +169,13 @@ def _cpu_unit_worker(args):
         threadpool_limits(limits=1)
     except Exception:
         pass
+
+
+def _cpu_unit_worker(args):
+    """One (candidate, hyper-sample) unit on the CPU oracle, timed for each Z count in `z_counts`
+    so that the per-unit fixed cost and the per-Z cost can be separated."""
+    cand_idx, hyper_idx, z_counts = args
+    _limit_blas_threads()
     from oracle import bqo_oracle as orc
     wl = _WL
     spec = orc.KernelSpec(orc.SCALED_MATERN52, DX + DW)
@@ -178,7 +185,7 @@ def _cpu_unit_worker(args):
     th = wl["thetas"][hyper_idx]
     gp.chol_solve(th[0], th[1], th[2:])  # factor cached per theta (untimed), as in the reference
     times = []
-    for zc in (z_lo, z_hi):
+    for zc in z_counts:
         t0 = time.time()
         sbo.evaluate_mc_bayesian_candidate_points_no_restarts(
             wl["cands"][cand_idx:cand_idx + 1], [th], wl["zs"][:zc], wl["starts"],
@@ -187,72 +194,147 @@ def _cpu_unit_worker(args):
     return times
 
 
+def _ref_unit_worker(args):
+    """The same unit on the UNMODIFIED reference (imported through tests/golden/ref_shim.py; only
+    where /root/reference exists, i.e. in the build container): its own GPFittingGaussian,
+    BayesianQuadrature and SBO.evaluate_mc_bayesian_candidate_points_no_restarts
+    (sbo/acquisition_functions/sbo.py:523-670) with the Pool replaced by its sequential
+    dispatcher -- the pool here is over units, as in _cpu_unit_worker."""
+    cand_idx, hyper_idx, z_counts = args
+    _limit_blas_threads()
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import ref_shim
+    ref_shim.install()
+    import warnings
+    warnings.filterwarnings("ignore")
+    from stratified_bayesian_optimization.models.gp_fitting_gaussian import GPFittingGaussian
+    from stratified_bayesian_optimization.numerical_tools.bayesian_quadrature import BayesianQuadrature
+    from stratified_bayesian_optimization.acquisition_functions.sbo import SBO
+    from stratified_bayesian_optimization.lib.constant import SCALED_KERNEL, MATERN52_NAME, GAMMA
+    wl = _WL
+    th = wl["thetas"][hyper_idx]
+    td = {"points": wl["pts"].tolist(), "evaluations": list(wl["y"]), "var_noise": []}
+    gp = GPFittingGaussian([SCALED_KERNEL, MATERN52_NAME], td, [DX + DW],
+                           bounds_domain=[[0, 1]] * DX + [[0, 20]] * DW, noise=True,
+                           kernel_values=list(th[2:]), mean_value=[th[1]], var_noise_value=[th[0]],
+                           define_samplers=False)
+    gp.samples_parameters = [np.array(th)]
+    bq = BayesianQuadrature(gp, list(range(DX)), GAMMA, parameters_distribution={"a": [2.0], "scale": [1.0]})
+    sbo = SBO(bq, None)
+    gp._cholesky_solve_vectors_for_posterior(th[0], th[1], th[2:])  # factor cached (untimed)
+    times = []
+    np.random.seed(3)
+    for zc in z_counts:
+        t0 = time.time()
+        sbo.evaluate_mc_bayesian_candidate_points_no_restarts(
+            wl["cands"][cand_idx:cand_idx + 1], 1, zc, n_restarts=N_RESTARTS_MC, n_threads=0,
+            compute_max_mean=False, compute_gradient=True, factr=FACTR_MC, maxiter=MAXITER_MC)
+        times.append(time.time() - t0)
+    return times
+
+
 _WL = None
 
 
-def cpu_baseline(wl, z_lo=1, z_hi=3, cores=None):
-    """CPU oracle timed on the host cores.  `cores` independent units run concurrently in a process
-    pool (the reference's own parallelism is an mp.Pool over units, sbo/lib/parallel.py:42-47).
-    Every unit is timed at Z = z_lo and Z = z_hi; time(Z) = F + c Z is fitted per unit and
-    extrapolated to the workload's Z = 100, so the fixed per-unit cost is not multiplied by 100."""
+def _host_cores():
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        cores = os.cpu_count() or 1
+    return max(1, min(cores, 32))
+
+
+def cpu_baseline(wl, z_counts=(1, 3), cores=None, impl=None):
+    """The reference's CPU path for the bench workload, timed on the host cores.  `cores`
+    independent units run concurrently in a process pool (the reference's own parallelism is an
+    mp.Pool over units, sbo/lib/parallel.py:42-47).  Every unit is timed at the Z counts of
+    `z_counts`; time(Z) = F + c Z is fitted by least squares over all of them and evaluated at the
+    workload's Z = 100, so the fixed per-unit cost is not multiplied by 100.
+    impl: "reference-shim" (the unmodified reference, needs /root/reference) or "port" (oracle/);
+    default: the reference when it is there."""
     import multiprocessing as mp
     global _WL
     _WL = wl
-    if cores is None:
-        try:
-            cores = len(os.sched_getaffinity(0))
-        except Exception:
-            cores = os.cpu_count() or 1
-    cores = max(1, min(cores, 32))
-    jobs = [(i % 4, i % N_HYPER, z_lo, z_hi) for i in range(cores)]
+    if impl is None:
+        impl = "reference-shim" if os.path.isdir(REFERENCE_ROOT) else "port"
+    worker = _ref_unit_worker if impl == "reference-shim" else _cpu_unit_worker
+    cores = cores or _host_cores()
+    jobs = [(i % 4, i % N_HYPER, tuple(z_counts)) for i in range(cores)]
     t0 = time.time()
     if cores > 1:
         ctx = mp.get_context("fork")
         with ctx.Pool(processes=cores) as pool:
-            res = pool.map(_cpu_unit_worker, jobs)
+            res = pool.map(worker, jobs)
     else:
-        res = [_cpu_unit_worker(j) for j in jobs]
+        res = [worker(j) for j in jobs]
     wall = time.time() - t0
-    t_lo = float(np.mean([r[0] for r in res]))
-    t_hi = float(np.mean([r[1] for r in res]))
-    c = max((t_hi - t_lo) / float(z_hi - z_lo), 1e-9)
-    F = max(t_lo - c * z_lo, 0.0)
+    t_mean = np.mean(np.array(res, dtype=float), axis=0)          # mean over units, per Z count
+    zc = np.array(z_counts, dtype=float)
+    if len(zc) > 1:
+        c, F = np.polyfit(zc, t_mean, 1)
+    else:
+        c, F = t_mean[0] / zc[0], 0.0
+    c = max(float(c), 1e-9)
+    F = max(float(F), 0.0)
     t_full = F + c * N_Z
     value = cores / t_full
+    timed = ", ".join("Z=%d: %.2f s" % (z, t) for z, t in zip(z_counts, t_mean))
     return {
-        "value": value, "unit": "units/s", "cores": cores, "kind": "port",
+        "value": value, "unit": "units/s", "cores": cores, "kind": impl,
         "sample": "%d concurrent units (1 candidate x 1 hyper-sample each, factor cached), each timed "
-                  "at Z=%d (%.2f s) and Z=%d (%.2f s) of %d Z samples, n=%d, R=%d starts + 16 "
-                  "vertices, scipy L-BFGS-B maxiter=%d; per-unit time fitted as F + c Z = %.2f + "
-                  "%.2f Z s and extrapolated to Z=%d (%.1f s per unit); %.1f s wall"
-                  % (cores, z_lo, t_lo, z_hi, t_hi, N_Z, N_TRAIN, N_RESTARTS_MC + 1, MAXITER_MC,
-                     F, c, N_Z, t_full, wall),
+                  "at %s (of %d Z samples), n=%d, R=%d starts + 16 vertices, scipy L-BFGS-B "
+                  "maxiter=%d; per-unit time fitted as F + c Z = %.2f + %.3f Z s, evaluated at Z=%d "
+                  "(%.1f s per unit); %.1f s wall"
+                  % (cores, timed, N_Z, N_TRAIN, N_RESTARTS_MC + 1, MAXITER_MC, F, c, N_Z, t_full, wall),
+        "z_counts": list(z_counts), "seconds_at_z": [float(t) for t in t_mean],
         "wall_s": wall,
     }
 
 
+def cpu_loglik_baseline(wl, reps=1):
+    """log-likelihood + gradient per second on the CPU path
+    (gp.log_likelihood + gp.grad_log_likelihood, sbo/models/gp_fitting_gaussian.py:772-897: one
+    n x n dpotrs and one n^3 product per parameter), cold cache, BLAS free to use every core."""
+    from oracle import bqo_oracle as orc
+    spec = orc.KernelSpec(orc.SCALED_MATERN52, DX + DW)
+    gp = orc.OracleGP(spec, wl["pts"], wl["y"])
+    ts = []
+    for r in range(reps):
+        th = wl["thetas"][r % N_HYPER]
+        gp.clean_cache()
+        t0 = time.time()
+        gp.log_likelihood(th[0], th[1], th[2:])
+        gp.grad_log_likelihood(th[0], th[1], th[2:])
+        ts.append(time.time() - t0)
+    t = float(np.min(ts))
+    return {"value": 1.0 / t, "unit": "evals/s", "cores": _host_cores(), "kind": "port",
+            "sample": "%d cold-cache evaluation(s) of log_likelihood + grad_log_likelihood at n=%d, "
+                      "p=%d kernel parameters, multithreaded BLAS: %.2f s each" % (reps, N_TRAIN, DX + DW + 1, t)}
+
+
 def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores, K timed
+    steps after W warm-up steps; a step = every core evaluates one unit at Z = 1 and Z = 3.  One
+    extra untimed pass at Z = 10 checks that the per-unit time is linear in Z."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     wl = make_workload()
-    total_steps = args.warmup + args.steps
     vals = []
-    t_all = time.time()
     base = None
-    for s in range(total_steps):
+    for s in range(args.warmup + args.steps):
         base = cpu_baseline(wl)
         if s >= args.warmup:
             vals.append(base)
-        if time.time() - t_all > 240:
-            break
-    if not vals:
-        vals = [base]
+    check = cpu_baseline(wl, z_counts=(10,))
+    F_c = np.polyfit(vals[-1]["z_counts"], vals[-1]["seconds_at_z"], 1)
     value = float(np.mean([v["value"] for v in vals]))
     ms = float(np.mean([v["wall_s"] for v in vals])) * 1e3
     cb = dict(vals[-1])
     cb["value"] = value
     cb.pop("wall_s", None)
+    cb["linearity_check"] = {"z": 10, "measured_s": check["seconds_at_z"][0],
+                             "predicted_s": float(F_c[1] + F_c[0] * 10)}
     line = {
         "impl": "reference", "metric": "bqo_acq_grad_units_per_s", "value": value, "unit": "units/s",
         "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup, "ms_per_step": ms,
@@ -260,6 +342,7 @@ def run_reference(args):
         "data": "synthetic",
         "config": workload_config(),
         "cpu_baseline": cb,
+        "secondary_cpu_baseline": cpu_loglik_baseline(wl),
         "e2e": {"value": value, "unit": "units/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -284,6 +367,108 @@ def workload_config():
     }
 
 
+
+# ------------------------------------------------------------------------------------------------
+# C5 (BASELINE.json configs[4]): n = 8192, S = 64 hyper-samples, 256 restarts, strong
+# scaling over 1/2/4/8 GPUs with the hyper-samples sharded first.
+C5_N, C5_S, C5_RESTARTS = 8192, 64, 256
+
+
+def make_workload_c5():
+    rng = np.random.RandomState(3)
+    pts = np.concatenate([rng.uniform(0, 1, (C5_N, DX)), rng.gamma(2.0, 1.0, (C5_N, DW))], 1)
+    y = np.sin(pts.sum(1)) + 0.01 * rng.normal(0, 1, C5_N)
+    r2 = np.random.RandomState(2)
+    base = np.array([1e-4, 0.0] + DX * [0.3] + DW * [2.0] + [1.0])
+    thetas = base[None, :] * (1.0 + 0.05 * r2.normal(0, 1, (C5_S, base.size)))
+    thetas[:, 1] = 0.05 * r2.normal(0, 1, C5_S)
+    r5 = np.random.RandomState(5)
+    cands = np.concatenate([r5.uniform(0, 1, (C5_RESTARTS, DX)), r5.gamma(2.0, 1.0, (C5_RESTARTS, DW))], 1)
+    return dict(pts=pts, y=y, thetas=thetas, cands=cands,
+                zs=np.random.RandomState(3).normal(0, 1, N_Z),
+                wsets=np.random.RandomState(4).gamma(2.0, 1.0, (1, M_W, DW)),
+                starts=np.random.RandomState(6).uniform(0, 1, (N_RESTARTS_MC + 1, DX)),
+                lower=np.zeros(DX), upper=np.ones(DX))
+
+
+def run_c5(args, dev, rank, world, steps, warmup=1):
+    """One acquisition evaluation (value + gradient of all 256 restart points) per step.  Rank r
+    holds the factors of hyper-samples [r S/N, (r+1) S/N) only (32 GB of factors in total at
+    n = 8192: what bounds memory) and scores every restart point against them; the
+    per-candidate partial sums [C x (1 + d)] are combined INSIDE the timed step with one
+    all_gather and a rank-ordered sum (bit-identical totals and argmax on every rank,
+    distributed.allgather_ordered_sum).  Strong scaling: the total work per step is fixed."""
+    import torch
+    import torch.distributed as dist
+    from bayesian_quadrature_optimization_b200 import _cabi, engine as E, distributed as D
+    wl = make_workload_c5()
+    eng = E.GPEngine(_cabi.KIND_SCALED_MATERN52, DX + DW, device=dev)
+    eng.set_data(wl["pts"], wl["y"])
+    lo, hi = D.shard_range(C5_S, rank, world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    hb = eng.hypers(wl["thetas"][lo:hi]).factorize()
+    e1.record()
+    torch.cuda.synchronize()
+    factor_ms = e0.elapsed_time(e1)
+    assert np.all(hb.info == 0)
+    bq = E.BQEngine(hb, DX, wsets=wl["wsets"], lower=wl["lower"], upper=wl["upper"])
+    cands = eng.to_device(wl["cands"])
+    zs, starts = eng.to_device(wl["zs"]), eng.to_device(wl["starts"])
+    n_loc = float(hi - lo)
+    out = {}
+
+    def step():
+        res = bq.evaluate_candidates(cands, zs, starts, maxiter=MAXITER_MC, factr=FACTR_MC)
+        part = torch.cat([res["evaluations"].reshape(-1, 1), res["gradient"]], dim=1) * n_loc
+        tot = D.allgather_ordered_sum(part) / float(C5_S)
+        out["argmax"] = torch.argmax(tot[:, 0])
+        out["tot"] = tot
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        step()
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1)
+    both = torch.tensor([ms, factor_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(both, op=dist.ReduceOp.MAX)
+    ms, factor_ms = float(both[0].item()), float(both[1].item())
+    # every rank must hold the same bits (rank-ordered sum)
+    same = True
+    if world > 1:
+        bufs = [torch.empty_like(out["tot"]) for _ in range(world)]
+        dist.all_gather(bufs, out["tot"])
+        same = all(torch.equal(bufs[0], b) for b in bufs)
+    units = C5_RESTARTS * C5_S
+    res = {
+        "workload": "C5 scaling sweep: Scaled(Matern52) d=6, n=%d, S=%d hyper-samples sharded over "
+                    "the ranks (%d per GPU), %d restart points, Z=%d, M_W=%d"
+                    % (C5_N, C5_S, hi - lo, C5_RESTARTS, N_Z, M_W),
+        "metric": "bqo_acq_grad_units_per_s", "value": units * steps / (ms * 1e-3), "unit": "units/s",
+        "scaling": "strong", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms / steps, "units_per_step": units,
+        "factorize_ms_max_over_ranks": factor_ms,
+        "factor_bytes_per_gpu": float(hi - lo) * C5_N * C5_N * 8.0,
+        "exchange": "per step, inside the timed region: all_gather of the [%d x %d] FP64 partial sums "
+                    "+ rank-ordered sum (%d bytes per rank)" % (C5_RESTARTS, 1 + DX + DW,
+                                                               C5_RESTARTS * (1 + DX + DW) * 8),
+        "identical_bits_on_all_ranks": bool(same), "argmax": int(out["argmax"].item()),
+    }
+    del bq, hb, eng
+    torch.cuda.empty_cache()
+    return res
+
+
 # ------------------------------------------------------------------------------------------------
 def run_gpu(args):
     import ctypes as C
@@ -297,7 +482,8 @@ def run_gpu(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("BQO_NCCL_DEBUG", "WARN")  # keep stdout to ONE line
+        # NCCL_DEBUG is left as the caller set it (the driver counts ranks in the INFO log); the
+        # JSON line is the only line this program itself prints
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
@@ -315,6 +501,22 @@ def run_gpu(args):
     dfma_peak = fl.value / (ms.value * 1e-3) / 1e12
     _cabi.check(lib.bqo_fp64_peak_probe(1, 100000, C.byref(ms), C.byref(fl)), "probe")
     dmma_peak = fl.value / (ms.value * 1e-3) / 1e12
+    # independent anchor for the FP64 tensor peak: cuBLAS DGEMM 4096^3 through torch.matmul
+    ga = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+    gb = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+    torch.matmul(ga, gb)
+    torch.cuda.synchronize()
+    dg = []
+    for rep in range(4):
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        torch.matmul(ga, gb)
+        g1.record()
+        torch.cuda.synchronize()
+        dg.append(g0.elapsed_time(g1))
+    dgemm_peak = 2.0 * 4096.0 ** 3 / (min(dg) * 1e-3) / 1e12
+    del ga, gb
+    tensor_peak = max(dmma_peak, dgemm_peak)   # the larger of probe and anchor is the roofline
 
     # ---- stage A (once per BO iteration; secondary metric: log-likelihood + gradient per s) ----
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -369,6 +571,8 @@ def run_gpu(args):
     evals_total = [0]
     best = [None]
 
+    from bayesian_quadrature_optimization_b200 import distributed as D
+
     def step(i, timed):
         cb = batch(i)
         ub = bq.setup(cb)
@@ -378,13 +582,15 @@ def run_gpu(args):
         gvb, is_nan = bq.grad_vector_b(ub, out_arg)
         value, grad = bq.acq_reduce(ub, out_max, gvb, is_nan, zs)
         v, idx = torch.max(value, dim=0)
-        best[0] = (v, idx + 0)
+        if world > 1:
+            # the one exchange of the path, once per step: every rank's best (value, global
+            # candidate index, point) -> the same argmax on all ranks (distributed.allgather_best)
+            lo_ = rank * per_rank + (i * CAND_PER_STEP) % max(1, per_rank - CAND_PER_STEP)
+            best[0] = D.allgather_best(v, idx + lo_, cb[idx])
+        else:
+            best[0] = (v, idx + 0)
         flush.fill_(i & 0xFF)
         return n_evals
-
-    # launches of this library per step: cross_cov 1, trsm 2, candidate_setup 1,
-    # inner_maximize 1, grad_vector_b 1, acq_reduce 1
-    launches_per_step = 7
 
     for i in range(args.warmup):
         step(i, False)
@@ -395,6 +601,7 @@ def run_gpu(args):
     if rank == 0:
         sampler.start()
     torch.cuda.synchronize()
+    launches0 = int(lib.bqo_launch_count())
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     counts = []
@@ -406,17 +613,13 @@ def run_gpu(args):
         kevs.append((a, b))
     t1.record()
     torch.cuda.synchronize()
+    gpu_launches = int(lib.bqo_launch_count()) - launches0   # counted by the library itself
     elapsed_ms = t0.elapsed_time(t1)
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
-        # the one exchange of the path: every rank's best (value, global index) -> argmax
-        v, idx = best[0]
-        mine = torch.stack([v, (idx + rank * per_rank).to(torch.float64)])
-        allv = [torch.zeros_like(mine) for _ in range(world)]
-        dist.all_gather(allv, mine)
     kern_ms = [a.elapsed_time(b) for a, b in kevs]
     evals = float(sum(int(c.sum().item()) for c in counts))
     units_per_step = CAND_PER_STEP * N_HYPER
@@ -456,7 +659,7 @@ def run_gpu(args):
         if world > 1:
             dist.barrier()
         w0 = time.perf_counter()
-        n_e2e = max(1, min(args.steps, 3))
+        n_e2e = max(1, args.steps)
         for i in range(n_e2e):
             r = e2e_step(10 + i)
         torch.cuda.synchronize()
@@ -469,6 +672,12 @@ def run_gpu(args):
         d2h = CAND_PER_STEP * 8 + CAND_PER_STEP * (DX + DW) * 8
         e2e = {"value": world * units_per_step * n_e2e / dt, "unit": "units/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_e2e}
+
+    c5 = None
+    if not args.profile and not args.no_c5:
+        del bq, hb
+        torch.cuda.empty_cache()
+        c5 = run_c5(args, dev, rank, world, steps=max(1, min(args.steps, args.c5_steps)))
 
     if rank != 0:
         if world > 1:
@@ -485,10 +694,15 @@ def run_gpu(args):
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    cpu = None
+    cpu = cpu_ll = None
     if world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(wl)
         cpu.pop("wall_s", None)
+        check = cpu_baseline(wl, z_counts=(10,))
+        fit = np.polyfit(cpu["z_counts"], cpu["seconds_at_z"], 1)
+        cpu["linearity_check"] = {"z": 10, "measured_s": check["seconds_at_z"][0],
+                                  "predicted_s": float(fit[1] + fit[0] * 10)}
+        cpu_ll = cpu_loglik_baseline(wl)
     line = {
         "metric": "bqo_acq_grad_units_per_s", "value": value, "unit": "units/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -499,9 +713,13 @@ def run_gpu(args):
             "bound": "fp64", "kernel": "inner_maximize_kernel<4,2>", "achieved": achieved,
             "peak": dfma_peak, "unit": "TFLOP/s", "frac": achieved / dfma_peak,
             "traffic": traffic,
-            "peak_source": "FP64 DFMA rate measured in this run by bqo_fp64_peak_probe "
-                           "(MEASURED_PEAKS.json holds no FP64 figure); DMMA m8n8k4 probe: %.1f TF/s"
-                           % dmma_peak,
+            "peak_source": "FP64 DFMA (non-tensor) rate measured in this run by bqo_fp64_peak_probe "
+                           "(MEASURED_PEAKS.json holds no FP64 figure).  Independent anchors measured "
+                           "in the same run: DMMA m8n8k4 probe %.1f TF/s, cuBLAS DGEMM 4096^3 "
+                           "(torch.matmul) %.1f TF/s; architectural rate 148 SM x 64 lanes x 2 x "
+                           "clock" % (dmma_peak, dgemm_peak),
+            "anchors": {"dfma_probe_tflops": dfma_peak, "dmma_probe_tflops": dmma_peak,
+                        "cublas_dgemm_tflops": dgemm_peak},
             "flops_per_eval": f_eval_flops(), "evals_per_launch": evals / args.steps,
             "evals_per_unit_per_z": evals / args.steps / (units_per_step * N_Z),
             "kernel_ms": kern_avg_ms, "kernel_share_of_step": kern_avg_ms / (elapsed_ms / args.steps),
@@ -510,9 +728,12 @@ def run_gpu(args):
         "secondary": {
             "metric": "gp_loglik_grad_per_s", "value": N_HYPER / (stage_a * 1e-3), "unit": "evals/s",
             "ms_for_%d_hyper_samples" % N_HYPER: stage_a,
-            "achieved_tflops": N_HYPER * f_ll / (stage_a * 1e-3) / 1e12, "peak_tflops": dmma_peak,
-            "frac": N_HYPER * f_ll / (stage_a * 1e-3) / 1e12 / dmma_peak,
+            "achieved_tflops": N_HYPER * f_ll / (stage_a * 1e-3) / 1e12, "peak_tflops": tensor_peak,
+            "frac": N_HYPER * f_ll / (stage_a * 1e-3) / 1e12 / tensor_peak,
             "bound": "fp64 tensor (DMMA)", "flops_per_eval": f_ll,
+            "peak_source": "max(DMMA m8n8k4 probe %.1f, cuBLAS DGEMM %.1f) TF/s, both measured in "
+                           "this run" % (dmma_peak, dgemm_peak),
+            "cpu_baseline": cpu_ll,
         },
         "assembly": {
             "metric": "kernel_matrix_assembly", "ms_for_%d_hyper_samples" % N_HYPER: asm_ms,
@@ -522,7 +743,8 @@ def run_gpu(args):
         },
         "cpu_baseline": cpu,
         "e2e": e2e,
-        "gpu_launches": launches_per_step * args.steps,
+        "c5": c5,
+        "gpu_launches": gpu_launches,
         "clocks": clocks,
     }
     print(json.dumps(line))
@@ -538,6 +760,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the C5 strong-scaling object")
+    ap.add_argument("--c5-steps", type=int, default=2,
+                    help="timed steps of the C5 object (a step takes ~14 s on one GPU)")
     ap.add_argument("--profile", action="store_true",
                     help="short run for ncu: 8 candidates per step, no stage-A repeats, no e2e, no CPU leg")
     args = ap.parse_args()

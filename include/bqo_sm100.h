@@ -56,6 +56,9 @@ typedef struct bqo_kernel_desc {
 /* ---- library / device ------------------------------------------------------------------ */
 int bqo_abi_version(void);
 int bqo_set_device(int device);
+/* Kernels launched by this library in this process so far (every launch site counts itself;
+ * bench.py reports the difference over its timed region as `gpu_launches`). */
+int64_t bqo_launch_count(void);
 /* Number of doubles of the per-hyper-sample block written by bqo_hyper_prepare. */
 int64_t bqo_hyper_stride(const bqo_kernel_desc* desc);
 

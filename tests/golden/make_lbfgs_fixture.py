@@ -28,6 +28,12 @@ if ROOT not in sys.path:
 from oracle import bqo_oracle as orc  # noqa: E402
 
 N_RESTARTS_MC, MAXITER_MC, FACTR_MC = 5, 10, 1e12  # sbo/services/bgo.py:43-44
+# `--converged`: scipy's own defaults (factr=1e7, maxiter=15000; sbo/lib/optimization.py:87-155 passes
+# them through when bgo's factr_mc / maxiter_mc are None) -- both optimisers then reach the same
+# local maxima and the comparison isolates the objective from the termination rule
+CONVERGED = "--converged" in sys.argv
+if CONVERGED:
+    MAXITER_MC, FACTR_MC = 15000, 1e7
 
 
 X_2 = [0.25, 0.5, 0.75]
@@ -100,7 +106,8 @@ def workload(cfg):
         return dict(kind=orc.SCALED_MATERN52, pts=pts, y=y, thetas=thetas, weights=None, n_tasks=0,
                     same_correlation=False, dx=dx, cands=cands, zs=zs, starts=starts, wset=wset,
                     lower=np.zeros(dx), upper=np.ones(dx),
-                    cand_idx=np.arange(0, 10), hyper_idx=np.arange(2), z_idx=np.arange(0, 100, 2))
+                    cand_idx=np.arange(0, 10), hyper_idx=np.arange(2),
+                    z_idx=np.arange(0, 100, 10 if CONVERGED else 2))
     raise KeyError(cfg)
 
 
@@ -195,7 +202,7 @@ _WL, _OBJ = {}, {}
 
 
 def main():
-    only = set(sys.argv[1:])
+    only = set(a for a in sys.argv[1:] if not a.startswith("--"))
     for cfg in ("c2", "c3"):
         if only and cfg not in only:
             continue
@@ -216,7 +223,8 @@ def main():
         ki = {int(k): i for i, k in enumerate(wl["hyper_idx"])}
         for c, k, m, a, f in res:
             mx[ci[c], ki[k]], arg[ci[c], ki[k]], nf[ci[c], ki[k]] = m, a, f
-        np.savez_compressed(os.path.join(HERE, "lbfgs_%s.npz" % cfg), scipy_max=mx, scipy_arg=arg,
+        name = "lbfgs_%s_converged.npz" if CONVERGED else "lbfgs_%s.npz"
+        np.savez_compressed(os.path.join(HERE, name % cfg), scipy_max=mx, scipy_arg=arg,
                             scipy_nfev=nf, cand_idx=wl["cand_idx"], hyper_idx=wl["hyper_idx"],
                             z_idx=wl["z_idx"])
         print(cfg, "tuples", mx.size, "mean f evaluations per tuple (6 runs)", nf.mean())

@@ -35,7 +35,7 @@ def test_oracle_against_reference_at_config(golden, name):
         tol = _rtol(g, spec, s)
         gp.clean_cache()
         chol, _ = gp.chol_cov_including_noise(vn, pk)
-        assert_close(chol, g["chol"][s], rtol=1e-11, atol=1e-14, what="chol")
+        assert_close(chol, g["chol"][s], rtol=max(1e-11, tol), atol=1e-14, what="chol")
         assert_close(gp.log_likelihood(vn, mu, pk), g["llh"][s], rtol=1e-11, what="llh")
         assert_close(gp.grad_log_likelihood(vn, mu, pk), g["grad_llh"][s], rtol=max(1e-8, tol),
                      atol=1e-8, what="grad_llh")
@@ -116,14 +116,15 @@ def test_gpu_classes_against_reference_at_config(golden, name):
         vn, mu, pk = th[0], th[1], th[2:]
         tol = _rtol(g, spec, s)
         chol, _ = gp._chol_cov_including_noise(vn, pk)
-        assert_close(chol, g["chol"][s], rtol=1e-10, atol=1e-13, what="chol")
+        assert_close(chol, g["chol"][s], rtol=max(1e-10, tol), atol=1e-13, what="chol")
         assert_close(gp.log_likelihood(vn, mu, pk), g["llh"][s], rtol=1e-11, what="llh")
         assert_close(gp.grad_log_likelihood(vn, mu, pk), g["grad_llh"][s], rtol=max(1e-8, tol),
                      atol=1e-8, what="grad llh")
         post = gp.compute_posterior_parameters(g["query"], vn, mu, pk)
         assert_close(post["mean"], g["post_mean"][s], rtol=tol, what="post mean")
-        assert_close(post["cov"], g["post_cov"][s], rtol=max(1e-8, 10 * tol), atol=1e-10,
-                     what="post cov")
+        # k(P,P) - k* Sigma^-1 k*^T cancels to ~1e-7 of its terms at the ill-conditioned theta
+        assert_close(post["cov"], g["post_cov"][s], rtol=max(1e-8, 10 * tol),
+                     atol=max(1e-10, tol * np.max(np.abs(np.diag(g["post_cov"][s])))), what="post cov")
         for q in range(g["query"].shape[0]):
             pt = g["query"][q:q + 1, :]
             assert_close(ei.evaluate(pt, vn, mu, pk)[0], g["ei"][s, q], rtol=max(1e-8, tol),
@@ -143,8 +144,8 @@ def test_gpu_classes_against_reference_at_config(golden, name):
             cand = cands[c:c + 1, :]
             par = bq.get_parameters_for_samples(True, cand, pk, vn, mu)
             assert_close(par["gamma"][:, 0], g["gamma"][s, c], rtol=1e-13, what="gamma")
-            assert_close(par["solve_2"][:, 0], g["solve_2"][s, c], rtol=max(1e-8, tol), atol=1e-11,
-                         what="solve_2")
+            assert_close(par["solve_2"][:, 0], g["solve_2"][s, c], rtol=max(1e-8, tol),
+                         atol=max(1e-11, tol * np.max(np.abs(g["solve_2"][s, c]))), what="solve_2")
             assert_close(par["denominator"][0], g["den"][s, c], rtol=max(1e-9, tol), what="den")
             for p in range(xq.shape[0]):
                 x = xq[p:p + 1, :]

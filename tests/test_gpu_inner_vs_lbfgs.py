@@ -6,10 +6,21 @@ sbo.py:237-366, sbo/lib/optimization.py:87-155).  tests/golden/make_lbfgs_fixtur
 that on the CPU oracle for 1200 (C2 shape) and 1000 (C3 shape) (candidate, hyper-sample, Z)
 tuples; here the device maximiser runs on the same tuples from the same starts.
 
-Asserted: the device maximum is at least the scipy maximum minus 1e-6 relative in >= 99 % of the
-tuples, and the acquisition value (mean over hyper-samples and Z of the maxima, sbo.py:640-650)
-differs from the scipy-based one by a stated bound.  The measured distribution is written to
-gpurun_out/inner_vs_lbfgs_<cfg>.json (summarised in profiles/r02_inner_vs_lbfgs.md).
+Two settings:
+
+* bgo's defaults maxiter=10, factr=1e12 (sbo/services/bgo.py:43-44).  Both optimisers are cut
+  off long before convergence (factr * eps = 2.2e-4 relative decrease, or the 10-iteration cap), so
+  their maxima differ by the progress of the last iteration.  Measured on the B200
+  (profiles/r02_inner_vs_lbfgs.md): device - scipy between -5.7e-5 and +2.4e-5 relative, median
+  -9e-7 at C3; the acquisition value (mean over hyper-samples and Z of the maxima,
+  sbo.py:640-650) differs by at most 2.8e-6 relative.  Asserted: device >= scipy - 1e-5 |scipy| in
+  >= 99 % of the tuples, >= scipy - 1e-4 |scipy| in all of them (half the termination tolerance),
+  acquisition value within 1e-5 relative.
+* scipy's own defaults (maxiter=15000, factr=1e7), where both reach the local maxima: the maxima
+  agree to 1e-7 relative in >= 99 % of the tuples -- the objective is the same function and the
+  difference above is the termination rule, not the arithmetic.
+
+The measured distributions are written to gpurun_out/inner_vs_lbfgs_<cfg>[_converged].json.
 """
 import json
 import os
@@ -23,7 +34,7 @@ from tests.golden.make_lbfgs_fixture import workload, oracle_objects, UnitObject
 pytestmark = pytest.mark.gpu
 
 
-def _device_maxima(wl, fx):
+def _device_maxima(wl, fx, maxiter=10, factr=1e12):
     from bayesian_quadrature_optimization_b200 import engine as E, _cabi
     from oracle import bqo_oracle as orc
     kind = _cabi.KIND_PRODUCT_TASKS if wl["kind"] == orc.PRODUCT_TASKS else _cabi.KIND_SCALED_MATERN52
@@ -37,7 +48,7 @@ def _device_maxima(wl, fx):
     cands = wl["cands"][fx["cand_idx"]]
     ub = bq.setup(cands)
     zs = wl["zs"][fx["z_idx"]]
-    mx, arg, n_evals = bq.inner_maximize(ub, zs, wl["starts"], maxiter=10, factr=1e12,
+    mx, arg, n_evals = bq.inner_maximize(ub, zs, wl["starts"], maxiter=maxiter, factr=factr,
                                          count_evals=True)
     S = len(fx["hyper_idx"])
     C = len(fx["cand_idx"])
@@ -92,6 +103,46 @@ def test_device_maxima_are_as_good_as_scipy_lbfgsb(cfg):
     with open(os.path.join(out_dir, "inner_vs_lbfgs_%s.json" % cfg), "w") as f:
         json.dump(summary, f, indent=1)
     print(json.dumps(summary))
-    assert frac_ok >= 0.99, summary
-    # the acquisition value the user sees: never below scipy's by more than 1e-6 relative
-    assert acq_rel.min() >= -1e-6, summary
+    summary["frac_device_ge_scipy_minus_1e-5_rel"] = float(np.mean(rel >= -1e-5))
+    with open(os.path.join(out_dir, "inner_vs_lbfgs_%s.json" % cfg), "w") as f:
+        json.dump(summary, f, indent=1)
+    assert np.mean(rel >= -1e-5) >= 0.99, summary
+    assert rel.min() >= -1e-4, summary           # factr * eps = 2.2e-4 is where both stop trying
+    # the acquisition value the user sees
+    assert np.max(np.abs(acq_rel)) <= 1e-5, summary
+
+
+@pytest.mark.parametrize("cfg", ["c2", "c3"])
+def test_device_maxima_equal_scipy_when_both_converge(cfg):
+    with np.load(os.path.join(GOLDEN_DIR, "lbfgs_%s_converged.npz" % cfg)) as f:
+        fx = {k: f[k] for k in f.files}
+    import tests.golden.make_lbfgs_fixture as gen
+    old = gen.CONVERGED
+    gen.CONVERGED = True     # the converged fixture of C3 uses a sparser Z grid
+    try:
+        wl = workload(cfg)
+    finally:
+        gen.CONVERGED = old
+    assert np.array_equal(wl["z_idx"], fx["z_idx"])
+    dev_max, _, n_evals = _device_maxima(wl, fx, maxiter=15000, factr=1e7)
+    sc = fx["scipy_max"]
+    rel = (dev_max - sc) / np.abs(sc)
+    summary = {
+        "cfg": cfg, "tuples": int(sc.size), "setting": "maxiter=15000, factr=1e7 (scipy defaults)",
+        "frac_abs_rel_diff_le_1e-7": float(np.mean(np.abs(rel) <= 1e-7)),
+        "frac_abs_rel_diff_le_1e-9": float(np.mean(np.abs(rel) <= 1e-9)),
+        "rel_diff_percentiles": {"min": float(rel.min()), "p1": float(np.percentile(rel, 1)),
+                                 "p50": float(np.percentile(rel, 50)),
+                                 "p99": float(np.percentile(rel, 99)), "max": float(rel.max())},
+        "acq_value_rel_diff_min_max": [float(v) for v in (
+            ((dev_max.mean(axis=(1, 2)) - sc.mean(axis=(1, 2))) / np.abs(sc.mean(axis=(1, 2)))).min(),
+            ((dev_max.mean(axis=(1, 2)) - sc.mean(axis=(1, 2))) / np.abs(sc.mean(axis=(1, 2)))).max())],
+        "device_evals_per_tuple": float(n_evals.sum() / sc.size),
+        "scipy_f_evals_per_tuple": float(fx["scipy_nfev"].mean()) + 2 ** wl["dx"],
+    }
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out_dir, exist_ok=True)
+    with open(os.path.join(out_dir, "inner_vs_lbfgs_%s_converged.json" % cfg), "w") as f:
+        json.dump(summary, f, indent=1)
+    print(json.dumps(summary))
+    assert np.mean(np.abs(rel) <= 1e-7) >= 0.99, summary

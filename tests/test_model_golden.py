@@ -58,6 +58,18 @@ def build_model(name, g, ser, **extra):
     raise KeyError(name)
 
 
+def lp_rtol(g, theta, base=1e-9):
+    """log-probabilities pass through the Cholesky factor of Sigma(theta): two correct
+    factorisations differ by about cond(Sigma) * eps (tests/helpers.py:cond_rtol); the
+    data-driven default length scale of the n = 30 toy (106) makes Sigma nearly singular."""
+    spec = spec_from_golden(g)
+    theta = np.asarray(theta, dtype=float)
+    cov = spec.cov(theta[2:], g["points"]) + theta[0] * np.eye(len(g["evaluations"]))
+    if "var_noise_obs" in g:
+        cov = cov + np.diag(g["var_noise_obs"])
+    return max(base, 8.0 * np.linalg.cond(cov) * np.finfo(float).eps)
+
+
 def enc_bounds(bounds):
     out = np.full((len(bounds), 2), np.nan)
     for i, b in enumerate(bounds):
@@ -213,14 +225,16 @@ def test_deserialize_a_reference_dict(name):
 def test_gpu_log_prob_parameters(name):
     g, ser = load_model(name)
     gp = build_model(name, g, ser)
-    got = np.array([gp.log_prob_parameters(th) for th in g["thetas_lp"]], dtype=float)
+    got = np.array([gp.log_prob_parameters(th) for th in g["thetas_lp"]], dtype=float).reshape(-1)
     assert np.array_equal(np.isneginf(got), np.isneginf(g["log_prob"]))
-    fin = np.isfinite(g["log_prob"])
-    assert_close(got[fin], g["log_prob"][fin], rtol=1e-9, what="log_prob_parameters")
     gp.clean_cache()
-    got_b = np.array(gp.log_prob_parameters_batch(list(g["thetas_lp"])), dtype=float)
-    assert_close(got_b[fin], g["log_prob"][fin], rtol=1e-9, what="log_prob_parameters_batch")
+    got_b = np.array(gp.log_prob_parameters_batch(list(g["thetas_lp"])), dtype=float).reshape(-1)
     assert np.array_equal(np.isneginf(got_b), np.isneginf(g["log_prob"]))
+    for i, th in enumerate(g["thetas_lp"]):
+        if np.isfinite(g["log_prob"][i]):
+            rt = lp_rtol(g, th)
+            assert_close(got[i], g["log_prob"][i], rtol=rt, what="log_prob_parameters[%d]" % i)
+            assert_close(got_b[i], g["log_prob"][i], rtol=rt, what="log_prob_parameters_batch[%d]" % i)
 
 
 @pytest.mark.gpu
@@ -239,8 +253,10 @@ def test_gpu_slice_chain_is_the_reference_chain(name, batched):
         GPFittingGaussian.batched_slice_probes = old
     assert_close(chain, g["chain"], rtol=1e-9, atol=1e-12, what="chain")
     assert after == float(g["chain_rand_after"])
-    lp = np.array([gp.log_prob_parameters(c) for c in chain])
-    assert_close(lp, g["chain_log_prob"], rtol=1e-9, what="chain log prob")
+    lp = np.array([gp.log_prob_parameters(c) for c in chain], dtype=float).reshape(-1)
+    want = np.asarray(g["chain_log_prob"], dtype=float).reshape(-1)
+    for i, c in enumerate(chain):
+        assert_close(lp[i], want[i], rtol=lp_rtol(g, g["chain"][i]), what="chain log prob[%d]" % i)
 
 
 @pytest.mark.gpu
