@@ -23,6 +23,7 @@ SOURCES = [
     "bqo_loglik_grad.cu",
     "bqo_stage_c.cu",
     "bqo_posterior.cu",
+    "bqo_hessian.cu",
 ]
 
 NVCC_FLAGS = [

@@ -94,6 +94,7 @@ SIGNATURES = {
     "bqo_kernel_assemble_batched": (C.c_int, [_KD, _P, _I, _P, _P, _I, _P, _I, _P, _P, _P]),
     "bqo_kernel_grad_params_batched": (C.c_int, [_KD, _P, _I, _P, _P, _I, _P, _P]),
     "bqo_cross_cov_batched": (C.c_int, [_KD, _P, _I, _P, _P, _I, _P, _I, _I, _P, _P, _P]),
+    "bqo_cross_cov_hessian_batched": (C.c_int, [_KD, _P, _I, _P, _P, _I, _P, _I, _P, _P]),
     "bqo_potrf_batched": (C.c_int, [_P, _I, _I, _P, _P]),
     "bqo_potrs_batched": (C.c_int, [_P, _I, _I, _P, _I, _P]),
     "bqo_chol_cov_batched": (
@@ -118,6 +119,7 @@ SIGNATURES = {
     "bqo_weight_alpha": (C.c_int, [_KD, _P, _P, _P, _I, _I, _P, _P]),
     "bqo_wdist_precompute": (C.c_int, [_KD, _P, _I, _P, _I, _I, _I, _P, _I, _I, _P, _P]),
     "bqo_sample_ab_batched": (C.c_int, [_SC, _P, _P, _P, _I, _P, _P]),
+    "bqo_sample_ab_hess_batched": (C.c_int, [_SC, _P, _P, _P, _I, _P, _P]),
     "bqo_inner_maximize_batched": (C.c_int, [_SC, _IO, _P, _P, _P, _P, _P, _P]),
     "bqo_grad_vector_b_batched": (C.c_int, [_SC, _P, _I, _P, _P, _P, _P]),
     "bqo_acq_reduce": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),

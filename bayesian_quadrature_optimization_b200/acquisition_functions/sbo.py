@@ -73,6 +73,28 @@ class SBO(object):
             parameters_kernel=parameters_kernel, w_set=w_set)
         return g['a'] + sample * g['b']
 
+    def evaluate_hessian_sample(self, point, candidate_point, sample, var_noise=None, mean=None,
+                                parameters_kernel=None, cache=True, w_set=0):
+        """:196-235 -> np.array(n x n): Hessian of a + Z b, with the reference's jitter on a
+        slightly negative diagonal."""
+        point = np.asarray(point, dtype=float)
+        if len(point.shape) == 1:
+            point = point.reshape((1, len(point)))
+        h = self.bq.compute_hessian_parameters_for_sample(
+            point, candidate_point, var_noise=var_noise, mean=mean,
+            parameters_kernel=parameters_kernel, w_set=w_set)
+        hessian = h['a'] + sample * h['b']
+        diag_cov = np.diag(hessian)
+        if np.any(diag_cov < 0.) and np.min(diag_cov) > -1e-6:
+            max_tries, n_tries = 6, 0
+            jitter = min(np.mean(diag_cov[np.where(diag_cov < 0)]) * 1e-6, 1e-6)
+            while np.any(diag_cov < 0.) and n_tries < max_tries and np.isfinite(jitter):
+                hessian += np.eye(hessian.shape[0]) * jitter
+                diag_cov = np.diag(hessian)
+                n_tries += 1
+                jitter *= 10
+        return hessian
+
     def _bounds_x(self):
         return [self.bounds_opt[i] for i in range(len(self.bounds_opt)) if i in self.bq.x_domain]
 

@@ -135,6 +135,18 @@ class HyperBatch(object):
             0, ptr(KP), ptr(dKP), _stream()), "bqo_cross_cov_batched")
         return (KP, dKP) if grad else KP
 
+    def cross_cov_hessian(self, P):
+        """d2 k(P_q, X_i) / dP dP: [S][m][dim_m][dim_m][n] (a5)."""
+        eng = self.eng
+        P = eng.to_device(P).reshape(-1, eng.desc.dim)
+        m = int(P.shape[0])
+        dm = eng.desc.dim_m
+        out = eng.empty(self.S, m, dm, dm, eng.n)
+        check(eng.lib.bqo_cross_cov_hessian_batched(
+            C.byref(eng.desc), ptr(self.hyp), self.S, ptr(self.Xs), ptr(self.tid), eng.n, ptr(P), m,
+            ptr(out), _stream()), "bqo_cross_cov_hessian_batched")
+        return out
+
     # -- factorisation ----------------------------------------------------------------------------
     def factorize(self, max_tries=7):
         """Sigma_s = K_s + noise; L_s with the reference's jitter policy; alpha_s."""
@@ -489,6 +501,19 @@ class BQEngine(object):
         pb = self._stage_c(ub)
         check(eng.lib.bqo_sample_ab_batched(C.byref(pb), ptr(pts), ptr(pt_unit), ptr(pt_wset), P,
                                             ptr(out), _stream()), "bqo_sample_ab_batched")
+        return out
+
+    def sample_ab_hess(self, ub, pts, pt_unit, pt_wset=None):
+        """[P][2][dx][dx]: Hessians of a and b at P points (unit and W set per point; a31)."""
+        eng = self.eng
+        pts = eng.to_device(pts).reshape(-1, self.dx)
+        P = int(pts.shape[0])
+        pt_unit = eng.to_device(pt_unit, I32).reshape(-1)
+        pt_wset = None if pt_wset is None else eng.to_device(pt_wset, I32).reshape(-1)
+        out = eng.empty(P, 2, self.dx, self.dx)
+        pb = self._stage_c(ub)
+        check(eng.lib.bqo_sample_ab_hess_batched(C.byref(pb), ptr(pts), ptr(pt_unit), ptr(pt_wset), P,
+                                                 ptr(out), _stream()), "bqo_sample_ab_hess_batched")
         return out
 
     def inner_maximize(self, ub, z, starts, maxiter=10, factr=1e12, pgtol=1e-5, max_ls=20,

@@ -22,26 +22,7 @@ from ..lib.constant import (
 )
 
 
-class ParameterEntity(object):
-    """sbo/entities/parameter.py: name, value (np.array), prior, bounds."""
-
-    def __init__(self, name, value, prior=None, bounds=None):
-        from ..lib.constant import SMALLEST_NUMBER, LARGEST_NUMBER
-        self.name = name
-        self.value = np.asarray(value, dtype=float)
-        self.prior = prior
-        self.dimension = len(self.value)
-        if bounds is None:  # entities/parameter.py:29-30,48-58
-            bounds = self.dimension * [(SMALLEST_NUMBER, LARGEST_NUMBER)]
-        self.bounds = bounds
-
-    def set_value(self, value):
-        self.value = np.asarray(value, dtype=float)
-
-    def log_prior(self, value=None):
-        if self.prior is None:
-            return 0.0
-        return self.prior.logprob(self.value if value is None else value)
+from ..entities.parameter import ParameterEntity  # noqa: E402,F401
 
 
 class _KernelParameters(object):
@@ -442,6 +423,19 @@ class GPFittingGaussian(object):
         if g.shape[1] < self._dim:
             g = np.concatenate([g, np.zeros((g.shape[0], self._dim - g.shape[1]))], axis=1)
         return g
+
+    def evaluate_hessian_cross_cov_respect_point(self, points_1, points_2, parameters_kernel):
+        """:1174-1200 -> np.array(m x k x k): Hessians of k(points_1, points_2[i]) with respect to
+        the single point points_1 (zero rows / columns for a task coordinate)."""
+        eng = self._temp_engine(points_2)
+        hb = eng.hypers(np.concatenate([[0.0, 0.0], np.asarray(parameters_kernel, dtype=float)]))
+        H = hb.cross_cov_hessian(np.asarray(points_1, dtype=float).reshape(1, -1))
+        H = H.cpu().numpy()[0, 0].transpose(2, 0, 1)  # m x dim_m x dim_m
+        if H.shape[1] < self._dim:
+            full = np.zeros((H.shape[0], self._dim, self._dim))
+            full[:, :H.shape[1], :H.shape[2]] = H
+            H = full
+        return H
 
     # -- factorisation, likelihood ------------------------------------------------------------------
     def _chol_cov_including_noise(self, var_noise, parameters_kernel, historical_points=None,

@@ -202,6 +202,16 @@ class BayesianQuadrature(object):
         _, dKP = hb.cross_cov(self._new_points(point, w_set), grad=True)
         return self._average(dKP[0])[: len(self.x_domain)].cpu().numpy()
 
+    def evaluate_hessian_cross_cov(self, point, points_2, parameters_kernel, w_set=0):
+        """hess_x B(x, z_j): :364-386 with hessian_uniform_finite / hessian_gamma
+        (sbo/lib/expectations.py:260-324) -> np.array(m x k x k)."""
+        eng = self.gp._temp_engine(points_2)
+        hb = eng.hypers(np.concatenate([[0.0, 0.0], np.asarray(parameters_kernel, dtype=float)]))
+        H = hb.cross_cov_hessian(self._new_points(point, w_set))[0]   # [M][dm][dm][m]
+        dx = len(self.x_domain)
+        H = self._average(H)[:dx, :dx]                               # [dx][dx][m]
+        return H.permute(2, 0, 1).contiguous().cpu().numpy()
+
     def evaluate_grad_quadrature_cross_cov_resp_candidate(self, candidate_point, points,
                                                           parameters_kernel, w_set=0):
         """grad_c B(x_p, c): :388-415 -> np.array(k x m)."""
@@ -444,6 +454,20 @@ class BayesianQuadrature(object):
         out = self._ab(point, candidate_point, self._theta(var_noise, mean, parameters_kernel), w_set)
         dx = len(self.x_domain)
         return {'a': out[0, 2:2 + dx], 'b': out[0, 2 + dx:2 + 2 * dx]}
+
+    def compute_hessian_parameters_for_sample(self, point, candidate_point, var_noise=None,
+                                              mean=None, parameters_kernel=None, cache=True,
+                                              w_set=0):
+        """:1241-1286 -> {'a': np.array(n x n), 'b': np.array(n x n)} (b = 0 when den = 0)."""
+        theta = self._theta(var_noise, mean, parameters_kernel)
+        bq = self.engine_for(theta)
+        ub = bq.setup(np.asarray(candidate_point, dtype=float).reshape(1, -1))
+        dx = len(self.x_domain)
+        pts = np.asarray(point, dtype=float).reshape(1, dx)
+        out = bq.sample_ab_hess(ub, pts, np.zeros(1, dtype=np.int32),
+                                np.full(1, w_set, dtype=np.int32) if self.w_sets is not None else None)
+        out = out.cpu().numpy()[0]
+        return {'a': out[0], 'b': out[1]}
 
     def gradient_vector_b(self, candidate_point, points, var_noise=None, mean=None,
                           parameters_kernel=None, cache=True, keep_indexes=None, parallel=True,

@@ -106,6 +106,16 @@ int bqo_cross_cov_batched(const bqo_kernel_desc* desc, const double* hyp, int32_
                           const double* Xs, const int32_t* tid, int32_t n, const double* P,
                           int32_t m, int32_t interleave, double* KP, double* dKP, void* stream);
 
+/* Second derivatives of k(P_q, X_i) with respect to the point P_q
+ * (GradientLSMatern52.hessian_respect_point, sbo/kernels/matern52.py:466-503, with
+ * Distances.gradient_distance_length_scale_respect_point(second=True), sbo/lib/distances.py:70-116;
+ * ScaledKernel / ProductKernels wrappers scaled_kernel.py:229-270, product_kernels.py:327-481).
+ * out[S][m][dim_m][dim_m][n]; only the Matern coordinates are differentiated.  Finite at r = 0
+ * (the reference divides by r there). */
+int bqo_cross_cov_hessian_batched(const bqo_kernel_desc* desc, const double* hyp, int32_t S,
+                                  const double* Xs, const int32_t* tid, int32_t n, const double* P,
+                                  int32_t m, double* out, void* stream);
+
 /* ---- Cholesky / solves / likelihood (a10-a13, a17) ------------------------------------- */
 /* In-place lower Cholesky of S row-major n x n matrices (lower triangle read; strict upper
  * triangle zeroed like scipy dpotrf clean=1, sbo/lib/la_functions.py:17).
@@ -235,6 +245,14 @@ int bqo_wdist_precompute(const bqo_kernel_desc* desc, const double* hyp, int32_t
  * sbo/numerical_tools/bayesian_quadrature.py:1148-1239).  out[q] = {a, b, ga[dx], gb[dx]}. */
 int bqo_sample_ab_batched(const bqo_stage_c* pb, const double* pts, const int32_t* pt_unit,
                           const int32_t* pt_wset, int32_t P, double* out, void* stream);
+
+/* Hessians of a and b with respect to x at P points (compute_hessian_parameters_for_sample,
+ * sbo/numerical_tools/bayesian_quadrature.py:1241-1286, through evaluate_hessian_cross_cov :364-386
+ * and hessian_uniform_finite / hessian_gamma, sbo/lib/expectations.py:260-324; only the Newton /
+ * dogleg inner optimisers use them).  out[q] = {hess a [dx][dx], hess b [dx][dx]}; hess b = 0 when
+ * den = 0. */
+int bqo_sample_ab_hess_batched(const bqo_stage_c* pb, const double* pts, const int32_t* pt_unit,
+                               const int32_t* pt_wset, int32_t P, double* out, void* stream);
 
 typedef struct bqo_inner_opt {
     int32_t n_z;        /* Z samples (DEFAULT_N_SAMPLES = 100) */

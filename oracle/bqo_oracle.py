@@ -101,6 +101,29 @@ def matern52_grad_respect_point(ls, point, inputs):
 
 # --------------------------------------------------------------------------------------------
 # tasks kernel
+def matern52_hessian_respect_point(ls, point, inputs):
+    """Hessians of k(point, inputs_i) with respect to point -> n x d x d:
+    GradientLSMatern52.hessian_respect_point (sbo/kernels/matern52.py:466-503) =
+    hess(r) k'(r) + grad r grad r^T k''(r) with r = dist(point, x)
+    (Distances.gradient_distance_length_scale_respect_point(second=True), sbo/lib/distances.py:70-116).
+    Written in the equivalent form without the 1/r and 1/r^3 factors:
+    d2k/dx_l dx_m = g(r) delta_lm / ls_l^2 + h(r) u_l u_m / (ls_l ls_m), u = (point - x) / ls,
+    g = k'(r)/r = -5/3 (1 + sqrt5 r) e^{-sqrt5 r}, h = g'(r)/r = 25/3 e^{-sqrt5 r}."""
+    ls = np.asarray(ls, dtype=float)
+    point = np.asarray(point, dtype=float).reshape(1, -1)
+    inputs = np.asarray(inputs, dtype=float)
+    u = (point - inputs) / ls                                   # n x d
+    r = np.sqrt(np.sum(u * u, axis=1))
+    e = np.exp(-np.sqrt(5.0) * r)
+    g = -(5.0 / 3.0) * (1.0 + np.sqrt(5.0) * r) * e
+    h = (25.0 / 3.0) * e
+    v = u / ls
+    hess = h[:, None, None] * v[:, :, None] * v[:, None, :]
+    d = len(ls)
+    hess[:, np.arange(d), np.arange(d)] += g[:, None] / (ls * ls)[None, :]
+    return hess
+
+
 def tasks_cov_matrix(params, n_tasks, same_correlation=False):
     """TasksKernel.compute_cov_matrix, sbo/kernels/tasks_kernel.py:198-239 -> (covM, L)."""
     params = np.asarray(params, dtype=float)
@@ -226,6 +249,26 @@ class KernelSpec(object):
         covM, _ = tasks_cov_matrix(params[dm:], self.n_tasks, self.same_correlation)
         kt = covM[np.ix_(point[:, dm].astype(int), inputs[:, dm].astype(int))].T  # n x 1
         return np.concatenate([g * kt, np.zeros((inputs.shape[0], 1))], axis=1)
+
+
+    def hessian_respect_point(self, params, point, inputs):
+        """evaluate_hessian_respect_point -> n x dim x dim (sbo/kernels/scaled_kernel.py:229-270,
+        product_kernels.py:327-481: the Matern block times the other factor; rows and columns of
+        the task coordinate are zero because its gradient and Hessian vanish)."""
+        params = np.asarray(params, dtype=float)
+        point = np.asarray(point, dtype=float).reshape(1, -1)
+        inputs = np.asarray(inputs, dtype=float)
+        dm = self.dim_m
+        hm = matern52_hessian_respect_point(params[:dm], point[:, :dm], inputs[:, :dm])
+        if self.kind == MATERN52:
+            return hm
+        if self.kind == SCALED_MATERN52:
+            return hm * params[dm]
+        covM, _ = tasks_cov_matrix(params[dm:], self.n_tasks, self.same_correlation)
+        kt = covM[point[0, dm].astype(int), inputs[:, dm].astype(int)]
+        out = np.zeros((inputs.shape[0], self.dim, self.dim))
+        out[:, :dm, :dm] = hm * kt[:, None, None]
+        return out
 
 
 # --------------------------------------------------------------------------------------------
@@ -569,6 +612,36 @@ class OracleBQ(object):
         else:
             gradient_b = np.zeros(len(gradient_a))
         return {"a": gradient_a, "b": gradient_b}
+
+    def evaluate_hessian_cross_cov(self, point, points_2, params, w=None):
+        """hess_x B(x, z_j) -> (m, d_x, d_x): bayesian_quadrature.py:364-386 with
+        hessian_uniform_finite / hessian_gamma (expectations.py:260-324)."""
+        new_points = self._new_points(point, w)
+        points_2 = np.asarray(points_2, dtype=float)
+        dx = len(self.x_domain)
+        hess = np.zeros((new_points.shape[0], points_2.shape[0], dx, dx))
+        for i in range(new_points.shape[0]):
+            value = self.spec.hessian_respect_point(params, new_points[i : i + 1, :], points_2)
+            hess[i] = value[:, self.x_domain][:, :, self.x_domain]
+        if self.distribution == GAMMA:
+            return np.mean(hess, axis=0)
+        return np.average(hess, axis=0, weights=self.weights)
+
+    def compute_hessian_parameters_for_sample(self, point, candidate_point, var_noise, mean,
+                                              params, w=None):
+        """hess a, hess b: :1241-1286."""
+        ap = self.get_parameters_for_samples(candidate_point, var_noise, mean, params)
+        candidate_point = np.asarray(candidate_point, dtype=float).reshape(1, -1)
+        point = np.asarray(point, dtype=float).reshape(1, -1)
+        hessian = self.evaluate_hessian_cross_cov(point, self.gp.points, params, w=w)
+        hessian_a = np.einsum("ijk,i->jk", hessian, ap["solve"])
+        if ap["denominator"] != 0:
+            hessian_new = self.evaluate_hessian_cross_cov(point, candidate_point, params, w=w)[0]
+            hessian_b = (hessian_new - np.einsum("ijk,i->jk", hessian, ap["solve_2"][:, 0])) \
+                / ap["denominator"]
+        else:
+            hessian_b = np.zeros(hessian_a.shape)
+        return {"a": hessian_a, "b": hessian_b}
 
     def gradient_vector_b(self, candidate_point, points, var_noise, mean, params, w=None):
         """grad_c b(x_p; c) -> (m, dim) or np.nan: :1447-1519 (solves Sigma^-1 B^T with m
