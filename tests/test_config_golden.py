@@ -152,12 +152,15 @@ def test_gpu_classes_against_reference_at_config(golden, name):
                 v = bq.compute_parameters_for_sample(x, cand, vn, mu, pk)
                 gr = bq.compute_gradient_parameters_for_sample(x, cand, vn, mu, pk)
                 got = np.concatenate([v["a"], v["b"].reshape(-1), gr["a"], gr["b"]])
-                assert_close(got, g["ab"][s, c, p], rtol=tol, atol=1e-11, what="ab")
+                # entries of one vector share the rounding error of the largest (cancellation)
+                assert_close(got, g["ab"][s, c, p], rtol=tol,
+                             atol=max(1e-11, tol * np.max(np.abs(g["ab"][s, c, p]))), what="ab")
                 for iz, z in enumerate(zs):
                     assert_close(sbo.evaluate_sample(x, cand, z, vn, mu, pk),
                                  g["sample_val"][s, c, p, iz], rtol=tol, atol=1e-11, what="a + Z b")
             gvb = bq.gradient_vector_b(cand, xq, vn, mu, pk)
-            assert_close(gvb, g["gvb"][s, c], rtol=10 * tol, atol=1e-11, what="gvb")
+            assert_close(gvb, g["gvb"][s, c], rtol=10 * tol,
+                         atol=max(1e-11, 10 * tol * np.max(np.abs(g["gvb"][s, c]))), what="gvb")
             assert_close(sbo.evaluate(cand, vn, mu, pk), g["kg"][s, c], rtol=max(1e-8, tol),
                          atol=1e-12, what="kg")
             assert_close(sbo.evaluate_gradient(cand, vn, mu, pk), g["grad_kg"][s, c],
