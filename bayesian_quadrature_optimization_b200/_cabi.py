@@ -95,17 +95,18 @@ SIGNATURES = {
     "bqo_kernel_grad_params_batched": (C.c_int, [_KD, _P, _I, _P, _P, _I, _P, _P]),
     "bqo_cross_cov_batched": (C.c_int, [_KD, _P, _I, _P, _P, _I, _P, _I, _I, _P, _P, _P]),
     "bqo_cross_cov_hessian_batched": (C.c_int, [_KD, _P, _I, _P, _P, _I, _P, _I, _P, _P]),
-    "bqo_potrf_batched": (C.c_int, [_P, _I, _I, _P, _P]),
+    "bqo_potrf_batched": (C.c_int, [_P, _I, _I, _P, _P, _P]),
+    "bqo_potrf_workspace_bytes": (_L, [_I, _I]),
+    "bqo_potrf_set_multi_launch": (C.c_int, [C.c_int]),
+    "bqo_potrf_profile": (C.c_int, [_P, _I, _I, _P, _P, _P, _P]),
     "bqo_potrs_batched": (C.c_int, [_P, _I, _I, _P, _I, _P]),
-    "bqo_chol_cov_batched": (
-        C.c_int,
-        [_KD, _P, _I, _P, _P, _I, _P, _I, _P, C.POINTER(_I), C.POINTER(_D), _P],
-    ),
+    "bqo_chol_cov_batched": (C.c_int, [_KD, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "bqo_chol_cov_retry": (C.c_int, [_KD, _P, _I, _P, _P, _I, _P, _D, _P, _P, _P, _P, _P]),
     "bqo_chol_append_batched": (C.c_int, [_P, _I, _I, _P, _P, _P, _P, _P]),
     "bqo_alpha_batched": (C.c_int, [_P, _L, _P, _I, _I, _P, _P, _P]),
     "bqo_loglik_batched": (C.c_int, [_P, _L, _P, _P, _P, _I, _I, _P, _P]),
     "bqo_loglik_grad_workspace_bytes": (_L, [_I, _I]),
-    "bqo_loglik_grad_batched": (C.c_int, [_KD, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P]),
+    "bqo_loglik_grad_batched": (C.c_int, [_KD, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P]),
     "bqo_posterior_batched": (
         C.c_int,
         [_KD, _P, _I, _P, _P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P],

@@ -9,10 +9,25 @@
 //     columns itself (left-looking): tile = B_tile - Y[:, :k0] L[kb, :k0]^T on DMMA, then a
 //     64x64 substitution in shared memory.  No cross-CTA dependency, one launch per direction.
 #include "bqo_gemm.cuh"
+#include "bqo_potrf_persistent.cuh"
+#include <cstdlib>
 #include <vector>
 
 #define NB BQO_TILE
 #define LDT (NB + 1)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute of one kernel: set it once
+// per (kernel, device) and again only when a larger size is asked for.
+template <auto Kernel>
+static void bqo_smem_opt_in(size_t bytes) {
+    static int granted[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || granted[dev] < (int)bytes) {
+        cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (dev >= 0 && dev < 64) granted[dev] = (int)bytes;
+    }
+}
 
 // ---------------------------------------------------------------------------------------------
 // 1/sqrt(d) to full precision: MUFU.RSQ64H seed (2^-22) and two Newton steps.
@@ -263,13 +278,33 @@ __global__ void potrf_finish_kernel(double* __restrict__ A, int n, const int* __
 #ifndef POTRF_W
 #define POTRF_W 4
 #endif
-static int potrf_launch(double* A, int n, int S, int* info, cudaStream_t cs) {
+// Workspace of one factorisation call: S * nb * 64 * 64 doubles (inverses of the diagonal blocks;
+// the multi-launch path keeps its factored diagonal blocks there) followed by S * nb + S + 4 ints
+// (tile-row progress counters, per-matrix stop flags, task counter and abort flag).
+static size_t potrf_workspace_doubles(int n, int S) {
+    const size_t nb = (size_t)(n + NB - 1) / NB;
+    return (size_t)S * nb * NB * NB;
+}
+static size_t potrf_workspace_ints(int n, int S) {
+    const size_t nb = (size_t)(n + NB - 1) / NB;
+    return 2 * (size_t)S * nb + (size_t)S + 4;
+}
+extern "C" int64_t bqo_potrf_workspace_bytes(int32_t n, int32_t S) {
+    if (n <= 0 || S <= 0) return 0;
+    return (int64_t)(potrf_workspace_doubles(n, S) * sizeof(double) +
+                     ((potrf_workspace_ints(n, S) * sizeof(int) + 15) / 16) * 16);
+}
+
+// Multi-launch right-looking factorisation (round 1): kept for odd n (rows not 16-byte aligned:
+// the persistent kernel reads finished tiles with L2-only 16-byte copies) and as the reference
+// the persistent kernel is tested against (environment variable BQO_POTRF_LEGACY=1).
+static int potrf_launch_multi(double* A, int n, int S, int* info, double* diag_scratch,
+                              cudaStream_t cs) {
     const int nb = (n + NB - 1) / NB;
-    cudaFuncSetAttribute(potrf_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)SMEM_POTRF_SYRK);
-    double* diag_scratch = nullptr;
-    cudaError_t e = cudaMallocAsync((void**)&diag_scratch, sizeof(double) * (size_t)S * nb * NB * NB, cs);
-    if (e != cudaSuccess) return (int)e;
+    bqo_smem_opt_in<potrf_syrk_kernel>(SMEM_POTRF_SYRK);
+    bqo_smem_opt_in<potrf_panel_kernel<0>>(SMEM_LS);
+    bqo_smem_opt_in<potrf_panel_kernel<1>>(SMEM_LS);
+    bqo_smem_opt_in<potrf_panel_kernel<2>>(SMEM_LS);
     cudaMemsetAsync(info, 0, sizeof(int) * S, cs);
     auto panel = [&](int k0) {
         const int tiles = (n - k0 + NB - 1) / NB;  // diagonal tile + row tiles below it
@@ -304,16 +339,103 @@ static int potrf_launch(double* A, int n, int S, int* info, cudaStream_t cs) {
     }
     dim3 zg((n + 255) / 256, n, S);
     BQO_L, potrf_finish_kernel<<<zg, 256, 0, cs>>>(A, n, info, diag_scratch);
-    cudaFreeAsync(diag_scratch, cs);
     return (int)cudaGetLastError();
 }
 
-extern "C" int bqo_potrf_batched(double* A, int32_t n, int32_t S, int32_t* info, void* stream) {
+// One persistent cooperative launch (bqo_potrf_persistent.cuh).
+static unsigned long long* g_potrf_prof = nullptr;   // debug: bqo_potrf_profile
+static int potrf_launch_persistent(double* A, int n, int S, int* info, double* Wd, int* ints,
+                                   double* Winv, cudaStream_t cs) {
+    const int nb = (n + NB - 1) / NB;
+    static int ctas_per_sm[64] = {0}, sms[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return -100;
+    bqo_smem_opt_in<potrf_persistent_kernel>(PP_SMEM_BYTES);
+    if (ctas_per_sm[dev] == 0) {
+        int per = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, potrf_persistent_kernel, PP_THREADS,
+                                                      PP_SMEM_BYTES);
+        cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+        ctas_per_sm[dev] = per > 0 ? per : -1;
+    }
+    if (ctas_per_sm[dev] < 1) return -101;
+    const int64_t total = Winv ? (int64_t)S * nb * nb : (int64_t)S * ((int64_t)nb * (nb + 1) / 2);
+    int64_t grid = (int64_t)sms[dev] * ctas_per_sm[dev];
+    if (grid > total) grid = total;
+    cudaMemsetAsync(info, 0, sizeof(int) * S, cs);
+    cudaMemsetAsync(ints, 0, sizeof(int) * potrf_workspace_ints(n, S), cs);
+    PotrfPersistArgs a;
+    a.A = A;
+    a.n = n;
+    a.S = S;
+    a.nb = nb;
+    a.info = info;
+    a.rowdone = ints;
+    a.wdone = ints + (size_t)S * nb;
+    a.failed = a.wdone + (size_t)S * nb;
+    a.counters = a.failed + S;
+    a.Wd = Wd;
+    a.Wmat = Winv;
+    a.prof = g_potrf_prof;
+    void* args[] = {&a};
+    BQO_L;
+    cudaError_t e = cudaLaunchCooperativeKernel((void*)potrf_persistent_kernel, dim3((unsigned)grid),
+                                                dim3(PP_THREADS), args, PP_SMEM_BYTES, cs);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaGetLastError();
+}
+
+static int g_potrf_legacy = -1;
+extern "C" int bqo_potrf_set_multi_launch(int on) {
+    const int old = g_potrf_legacy > 0 ? 1 : 0;
+    g_potrf_legacy = on ? 1 : 0;
+    return old;
+}
+
+int bqo_internal_tri_inverse(const double* L, int n, int S, double* Wbuf, double* scratch,
+                              cudaStream_t cs);
+
+// Winv (optional, [S][n][n]): also W = L^-1 on the lower tiles -- by extra tasks of the persistent
+// kernel, or by the level kernels after the multi-launch path (scratch = the S n^2 doubles of T).
+static int potrf_launch(double* A, int n, int S, int* info, void* workspace, cudaStream_t cs,
+                        double* Winv = nullptr, double* Wscratch = nullptr) {
+    double* wd = (double*)workspace;
+    int* ints = (int*)(wd + potrf_workspace_doubles(n, S));
+    if (g_potrf_legacy < 0) {
+        const char* e = getenv("BQO_POTRF_LEGACY");
+        g_potrf_legacy = (e && e[0] == '1') ? 1 : 0;
+    }
+    const int legacy = g_potrf_legacy;
+    // 16-byte aligned rows (n even, base aligned) are what the persistent kernel's L2-only copies
+    // of finished tiles need
+    const bool aligned = (n % 2 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+    if (legacy || !aligned) {
+        int rc = potrf_launch_multi(A, n, S, info, wd, cs);
+        if (rc == 0 && Winv) rc = bqo_internal_tri_inverse(A, n, S, Winv, Wscratch, cs);
+        return rc;
+    }
+    return potrf_launch_persistent(A, n, S, info, wd, ints, Winv, cs);
+}
+
+// Tuning aid: the same factorisation with %globaltimer stamps of the critical-path tasks of matrix 0
+// written to prof[nb][2][8] (device, zero-initialised by the caller).  Not thread safe.
+extern "C" int bqo_potrf_profile(double* A, int32_t n, int32_t S, int32_t* info, void* workspace,
+                                 unsigned long long* prof, void* stream) {
+    g_potrf_prof = prof;
+    int rc = potrf_launch(A, n, S, info, workspace, (cudaStream_t)stream);
+    g_potrf_prof = nullptr;
+    return rc;
+}
+
+extern "C" int bqo_potrf_batched(double* A, int32_t n, int32_t S, int32_t* info, void* workspace,
+                                 void* stream) {
     BQO_CHECK_ARG(A != nullptr, 1);
     BQO_CHECK_ARG(n > 0, 2);
     BQO_CHECK_ARG(S > 0 && S <= 65535, 3);
     BQO_CHECK_ARG(info != nullptr, 4);
-    return potrf_launch(A, n, S, info, (cudaStream_t)stream);
+    BQO_CHECK_ARG(workspace != nullptr, 5);
+    return potrf_launch(A, n, S, info, workspace, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -645,8 +767,8 @@ static int potrs_launch(const double* L, int n, int S, double* Bt, int m, int id
     if ((int64_t)m * S <= TRSV_MAX_VECTORS && m <= 65535 && !identity_rhs &&
         trsv_smem_bytes(n) <= 200 * 1024) {
         const size_t sb = trsv_smem_bytes(n);
-        cudaFuncSetAttribute(trsv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
-        cudaFuncSetAttribute(trsv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
+        bqo_smem_opt_in<trsv_kernel<true>>(sb);
+        bqo_smem_opt_in<trsv_kernel<false>>(sb);
         dim3 grid(m, S);
         // blocks of TRSV_BLK rows: one CTA per vector solves the block, then the block is
         // eliminated from the remaining rows by (rows / 64) x m x S CTAs
@@ -670,14 +792,8 @@ static int potrs_launch(const double* L, int n, int S, double* Bt, int m, int id
         }
         return (int)cudaGetLastError();
     }
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(trsm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)SMEM_TRSM);
-        cudaFuncSetAttribute(trsm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)SMEM_TRSM);
-        attr_done = true;
-    }
+    bqo_smem_opt_in<trsm_kernel<true>>(SMEM_TRSM);
+    bqo_smem_opt_in<trsm_kernel<false>>(SMEM_TRSM);
     dim3 grid((m + NB - 1) / NB, S);
     BQO_L, trsm_kernel<true><<<grid, 128, SMEM_TRSM, cs>>>(L, n, Bt, m, identity_rhs);
     if (forward_only) return (int)cudaGetLastError();
@@ -818,35 +934,41 @@ __global__ void __launch_bounds__(128) inv_syrk_kernel(const double* __restrict_
     });
 }
 
-int bqo_internal_inverse_from_chol(const double* L, int n, int S, double* Inv, double* Wbuf,
-                                   cudaStream_t cs) {
+// W = L^-1 by recursive doubling (multi-launch path); `scratch`: S n^2 doubles (T of the levels).
+int bqo_internal_tri_inverse(const double* L, int n, int S, double* Wbuf, double* scratch,
+                             cudaStream_t cs) {
     const int nb = (n + NB - 1) / NB;
     const size_t smem_diag = 2 * (size_t)NB * LDT * sizeof(double);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(tri_inv_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)smem_diag);
-        attr_done = true;
-    }
-    cudaFuncSetAttribute(tri_inv_level_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)SMEM_SYRK);
-    cudaFuncSetAttribute(tri_inv_level_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)SMEM_SYRK);
-    cudaFuncSetAttribute(inv_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)SMEM_SYRK);
+    bqo_smem_opt_in<tri_inv_diag_kernel>(smem_diag);
+    bqo_smem_opt_in<tri_inv_level_kernel<1>>(SMEM_SYRK);
+    bqo_smem_opt_in<tri_inv_level_kernel<2>>(SMEM_SYRK);
     dim3 dg(nb, S);
     BQO_L, tri_inv_diag_kernel<<<dg, NB, smem_diag, cs>>>(L, n, Wbuf);
     for (int b = NB; b < n; b *= 2) {
         const int pairs = (n + 2 * b - 1) / (2 * b);
         if ((int64_t)pairs * S > 65535) return -3;
         dim3 lg(b / NB, b / NB, pairs * S);
-        // Inv doubles as the scratch T of the levels; the final product overwrites all of it
-        BQO_L, tri_inv_level_kernel<1><<<lg, 128, SMEM_SYRK, cs>>>(L, Wbuf, Inv, n, b, pairs);
-        BQO_L, tri_inv_level_kernel<2><<<lg, 128, SMEM_SYRK, cs>>>(L, Wbuf, Inv, n, b, pairs);
+        BQO_L, tri_inv_level_kernel<1><<<lg, 128, SMEM_SYRK, cs>>>(L, Wbuf, scratch, n, b, pairs);
+        BQO_L, tri_inv_level_kernel<2><<<lg, 128, SMEM_SYRK, cs>>>(L, Wbuf, scratch, n, b, pairs);
     }
+    return (int)cudaGetLastError();
+}
+
+// Inv = W^T W on the lower tiles.
+int bqo_internal_inv_syrk(const double* Wbuf, int n, int S, double* Inv, cudaStream_t cs) {
+    const int nb = (n + NB - 1) / NB;
+    bqo_smem_opt_in<inv_syrk_kernel>(SMEM_SYRK);
     dim3 sg(nb, nb, S);
     BQO_L, inv_syrk_kernel<<<sg, 128, SMEM_SYRK, cs>>>(Wbuf, n, Inv);
     return (int)cudaGetLastError();
+}
+
+int bqo_internal_inverse_from_chol(const double* L, int n, int S, double* Inv, double* Wbuf,
+                                   cudaStream_t cs) {
+    // Inv doubles as the scratch T of the levels; the final product overwrites all of it
+    int rc = bqo_internal_tri_inverse(L, n, S, Wbuf, Inv, cs);
+    if (rc) return rc;
+    return bqo_internal_inv_syrk(Wbuf, n, S, Inv, cs);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -874,72 +996,55 @@ __global__ void diag_stats_kernel(const double* __restrict__ A, int n, double* _
     }
 }
 
+// No allocation and no host synchronisation: Sigma is assembled into L, its diagonal statistics
+// are taken (they are needed only if a factorisation fails, but the factorisation overwrites the
+// diagonal), and all S matrices are factored.  `status` (device, 2 S doubles + S ints, see
+// bqo_chol_cov_status_bytes) receives mean(diag Sigma_s), a flag for a non-positive diagonal entry
+// and -- in `info` -- dpotrf's code per matrix.  The caller reads them together with whatever
+// result it needs anyway and, for the matrices that failed, drives the reference's jitter policy
+// (sbo/lib/la_functions.py:19-38) with bqo_chol_cov_retry.
 extern "C" int bqo_chol_cov_batched(const bqo_kernel_desc* desc, const double* hyp, int32_t S,
                                     const double* Xs, const int32_t* tid, int32_t n,
-                                    const double* noise_obs, int32_t max_tries, double* L,
-                                    int32_t* info_host, double* jitter_used_host, void* stream) {
+                                    const double* noise_obs, double* L, int32_t* info,
+                                    double* diag_mean, int32_t* diag_nonpos, double* Winv,
+                                    double* Winv_scratch, void* workspace, void* stream) {
     BQO_CHECK_ARG(desc != nullptr, 1);
     BQO_CHECK_ARG(S > 0 && S <= 65535, 3);
-    BQO_CHECK_ARG(L != nullptr, 9);
-    BQO_CHECK_ARG(info_host != nullptr, 10);
+    BQO_CHECK_ARG(L != nullptr, 8);
+    BQO_CHECK_ARG(info != nullptr, 9);
+    BQO_CHECK_ARG(diag_mean != nullptr, 10);
+    BQO_CHECK_ARG(diag_nonpos != nullptr, 11);
+    BQO_CHECK_ARG(workspace != nullptr, 14);
+    BQO_CHECK_ARG(Winv == nullptr || Winv_scratch != nullptr || n % 2 == 0, 13);
     cudaStream_t cs = (cudaStream_t)stream;
     int rc = bqo_kernel_assemble_batched(desc, hyp, S, Xs, tid, n, noise_obs, 1, nullptr, L, stream);
     if (rc) return rc;
-    int* info_d = nullptr;
-    double* mean_d = nullptr;
-    int* nonpos_d = nullptr;
-    cudaError_t e = cudaMallocAsync((void**)&info_d, sizeof(int) * S * 2 + sizeof(double) * S * 2, cs);
-    if (e != cudaSuccess) return (int)e;
-    nonpos_d = info_d + S;
-    mean_d = (double*)(info_d + 2 * S);
-    double* extra_d = mean_d + S;
-    // diagonal statistics of Sigma are needed only on failure, but they must be taken before the
-    // in-place factorisation destroys the diagonal.
-    BQO_L, diag_stats_kernel<<<S, 256, 0, cs>>>(L, n, mean_d, nonpos_d);
-    rc = potrf_launch(L, n, S, info_d, cs);
-    std::vector<int> info(S), nonpos(S);
-    std::vector<double> mean(S), jit(S, 0.0), extra(S, 0.0);
-    cudaMemcpyAsync(info.data(), info_d, sizeof(int) * S, cudaMemcpyDeviceToHost, cs);
-    cudaMemcpyAsync(nonpos.data(), nonpos_d, sizeof(int) * S, cudaMemcpyDeviceToHost, cs);
-    cudaMemcpyAsync(mean.data(), mean_d, sizeof(double) * S, cudaMemcpyDeviceToHost, cs);
-    cudaStreamSynchronize(cs);
-    for (int s = 0; s < S; ++s) {
-        info_host[s] = 0;
-        if (info[s] == 0) continue;
-        if (nonpos[s]) {  // "not positive definite matrix"
-            info_host[s] = -1;
-            continue;
-        }
-        double jitter = mean[s] * 1e-6;
-        int n_tries = 1;
-        bool ok = false;
-        // per failed matrix: re-assemble Sigma_s + jitter I into its slot and re-factor it
-        bqo_kernel_desc d1 = *desc;
-        int64_t st = bqo_hyper_stride_impl(d1);
-        while (n_tries <= max_tries && isfinite(jitter)) {
-            cudaMemcpyAsync(extra_d, &jitter, sizeof(double), cudaMemcpyHostToDevice, cs);
-            bqo_kernel_assemble_batched(desc, hyp + (int64_t)s * st, 1,
-                                        Xs + (int64_t)s * desc->dim_m * n, tid, n, noise_obs, 1,
-                                        extra_d, L + (int64_t)s * n * n, stream);
-            potrf_launch(L + (int64_t)s * n * n, n, 1, info_d, cs);
-            int one = 0;
-            cudaMemcpyAsync(&one, info_d, sizeof(int), cudaMemcpyDeviceToHost, cs);
-            cudaStreamSynchronize(cs);
-            if (one == 0) {
-                ok = true;
-                break;
-            }
-            jitter *= 10.0;
-            ++n_tries;
-        }
-        if (ok) jit[s] = jitter;
-        else info_host[s] = -2;
-    }
-    if (jitter_used_host)
-        for (int s = 0; s < S; ++s) jitter_used_host[s] = jit[s];
-    cudaFreeAsync(info_d, cs);
-    e = cudaGetLastError();
-    return rc ? rc : (int)e;
+    BQO_L, diag_stats_kernel<<<S, 256, 0, cs>>>(L, n, diag_mean, diag_nonpos);
+    return potrf_launch(L, n, S, info, workspace, cs, Winv, Winv_scratch);
+}
+
+// One step of the jitter policy for matrix s: Sigma_s + jitter I is re-assembled into its slot of
+// L and factored again; info_one (device, 1 int) receives the code.  `jitter_dev`: one double of
+// device scratch (the value is copied there).  The workspace of bqo_potrf_workspace_bytes(n, 1)
+// is enough.
+extern "C" int bqo_chol_cov_retry(const bqo_kernel_desc* desc, const double* hyp, int32_t s,
+                                  const double* Xs, const int32_t* tid, int32_t n,
+                                  const double* noise_obs, double jitter, double* jitter_dev,
+                                  double* L, int32_t* info_one, void* workspace, void* stream) {
+    BQO_CHECK_ARG(desc != nullptr, 1);
+    BQO_CHECK_ARG(s >= 0, 3);
+    BQO_CHECK_ARG(jitter_dev != nullptr, 9);
+    BQO_CHECK_ARG(L != nullptr, 10);
+    BQO_CHECK_ARG(info_one != nullptr, 11);
+    BQO_CHECK_ARG(workspace != nullptr, 12);
+    cudaStream_t cs = (cudaStream_t)stream;
+    const int64_t st = bqo_hyper_stride_impl(*desc);
+    cudaMemcpyAsync(jitter_dev, &jitter, sizeof(double), cudaMemcpyHostToDevice, cs);
+    int rc = bqo_kernel_assemble_batched(desc, hyp + (int64_t)s * st, 1,
+                                         Xs + (int64_t)s * desc->dim_m * n, tid, n, noise_obs, 1,
+                                         jitter_dev, L + (int64_t)s * n * n, stream);
+    if (rc) return rc;
+    return potrf_launch(L + (int64_t)s * n * n, n, 1, info_one, workspace, cs);
 }
 
 // ---------------------------------------------------------------------------------------------

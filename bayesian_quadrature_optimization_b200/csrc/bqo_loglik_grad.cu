@@ -9,10 +9,12 @@
 // fly in registers from the same pairwise distance (never stored), over the lower triangle of
 // tiles only.  Partial sums are written per CTA and added in a fixed order, so the result is
 // bit-reproducible.
-#include "bqo_common.cuh"
+#include "bqo_gemm.cuh"
 
 int bqo_internal_inverse_from_chol(const double* L, int n, int S, double* Inv, double* Wbuf,
                                    cudaStream_t cs);
+int bqo_internal_tri_inverse(const double* L, int n, int S, double* Wbuf, double* scratch,
+                             cudaStream_t cs);
 
 #define LG_MAX_ACC (BQO_MAX_DIM + 4)
 // accumulator slots: [0..dim_m) length scales, then
@@ -106,6 +108,109 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Sigma^-1 = W^T W and the contraction in ONE kernel: a CTA forms one 64 x 64 lower tile of
+// Sigma^-1 on DMMA (K range from the tile's first row: W = L^-1 vanishes above it) and contracts it,
+// still in registers, with M = alpha alpha^T - Sigma^-1 against every dK_j generated on the fly.
+// Sigma^-1 is never written to HBM (the separate contraction pass read 8 n^2 / 2 bytes per
+// hyper-sample back and took 1.0 of the gradient's 5.3 ms at n = 2048, S = 20).
+// The per-tile partial sums go to partial[s][slot][tile] and are added in a fixed order.
+#define LGF_SMEM_BYTES ((size_t)(2 * BQO_OPER_BUF_DOUBLES(BQO_GEMM_STAGES)) * sizeof(double))
+__global__ void __launch_bounds__(128)
+    inv_syrk_contract_kernel(bqo_kernel_desc d, const double* __restrict__ hyp, int64_t stride,
+                             const double* __restrict__ Xs, const int32_t* __restrict__ tid, int n,
+                             const double* __restrict__ W, const double* __restrict__ alpha,
+                             double* __restrict__ partial, double* __restrict__ Wtask, int ntiles) {
+    extern __shared__ __align__(16) double dyn_smem[];
+    double* Asm = dyn_smem;
+    double* Bsm = Asm + BQO_OPER_BUF_DOUBLES(BQO_GEMM_STAGES);
+    __shared__ double red[32];
+    const int s = blockIdx.z;
+    const int ba = blockIdx.y, bb = blockIdx.x;
+    if (bb > ba) return;
+    const double* Wm = W + (int64_t)s * n * n;
+    const int a0 = ba * BQO_TILE, b0 = bb * BQO_TILE;
+    const int ra = (n - a0 < BQO_TILE) ? n - a0 : BQO_TILE;
+    const int rb = (n - b0 < BQO_TILE) ? n - b0 : BQO_TILE;
+    BqoAcc acc;
+    acc.zero();
+    bqo_gemm_tile<false, false>(acc, Wm + (int64_t)a0 * n + a0, n, ra, Wm + (int64_t)a0 * n + b0, n,
+                                rb, n - a0, Asm, Bsm);
+    __syncthreads();
+    // coordinates, alpha and task ids of the tile's 64 rows (i) and 64 columns (j) -> shared memory
+    const int dm = d.dim_m;
+    const double* h = hyp + (int64_t)s * stride;
+    const double* xs = Xs + (int64_t)s * dm * n;
+    const double* al = alpha + (int64_t)s * n;
+    double* xi = Asm;                      // [dm][64]
+    double* xj = xi + dm * BQO_TILE;       // [dm][64]
+    double* ai = xj + dm * BQO_TILE;       // [64]
+    double* aj = ai + BQO_TILE;            // [64]
+    int* ti = (int*)(aj + BQO_TILE);       // [64]
+    int* tj = ti + BQO_TILE;               // [64]
+    const bool prod = d.kind == BQO_KIND_PRODUCT_TASKS;
+    for (int e = threadIdx.x; e < dm * BQO_TILE; e += 128) {
+        const int l = e / BQO_TILE, r = e % BQO_TILE;
+        xi[e] = (r < ra) ? xs[(int64_t)l * n + a0 + r] : 0.0;
+        xj[e] = (r < rb) ? xs[(int64_t)l * n + b0 + r] : 0.0;
+    }
+    for (int r = threadIdx.x; r < BQO_TILE; r += 128) {
+        ai[r] = (r < ra) ? al[a0 + r] : 0.0;
+        aj[r] = (r < rb) ? al[b0 + r] : 0.0;
+        ti[r] = (prod && r < ra) ? tid[a0 + r] : 0;
+        tj[r] = (prod && r < rb) ? tid[b0 + r] : 0;
+    }
+    __syncthreads();
+    const int nacc = dm + 4;
+    double sums[LG_MAX_ACC];
+    for (int q = 0; q < nacc; ++q) sums[q] = 0.0;
+    const bool general_tasks = prod && !d.same_corr;
+    const double wsym = (bb < ba) ? 2.0 : 1.0;   // strictly lower tiles stand for their mirror too
+    const double sigma2 = (d.kind == BQO_KIND_SCALED_MATERN52) ? h[BQO_H_SIGMA2] : 1.0;
+    bqo_acc_foreach(acc, [&](int r, int c, double& v) {
+        if (r >= ra || c >= rb) return;
+        const int i = a0 + r, j = b0 + c;
+        const double Mij = wsym * (ai[r] * aj[c] - v);
+        double df[BQO_MAX_DIM];
+        double r2 = 0.0;
+        for (int l = 0; l < dm; ++l) {
+            df[l] = xi[l * BQO_TILE + r] - xj[l * BQO_TILE + c];
+            r2 = fma(df[l], df[l], r2);
+        }
+        double km = 1.0, g = -BQO_FIVE_THIRDS;
+        if (i != j) {
+            double u2v[1], ev[1], uv[1];
+            u2v[0] = fma(r2, BQO_PRESCALE * BQO_PRESCALE, 1e-300);
+            bqo_matern52_q_v<1>(u2v, GlobalExpTab(), ev, uv);
+            const double lin = fma(uv[0], BQO_LN2_N, 1.0) * ev[0];  // (1 + sqrt5 r) e
+            km = fma(u2v[0] * ev[0], BQO_H_TO_K, lin);
+            g = -BQO_FIVE_THIRDS * lin;                             // k'(r) / r
+        }
+        double other = sigma2;
+        if (prod) other = bqo_task_cov(h, d.n_tasks, ti[r], tj[c]);
+        if (i != j) {
+            const double w = -Mij * g * other;
+            for (int l = 0; l < dm; ++l)
+                sums[l] = fma(w * df[l] * df[l], h[BQO_H_INVLS + l], sums[l]);
+        } else {
+            sums[LG_SLOT_TRACE(dm)] += Mij;
+        }
+        const double mk = Mij * km;
+        sums[LG_SLOT_KM(dm)] += mk;
+        if (prod) {
+            if (general_tasks) atomicAdd(Wtask + ((int64_t)s * d.n_tasks + ti[r]) * d.n_tasks + tj[c], mk);
+            else if (ti[r] == tj[c]) sums[LG_SLOT_SAME(dm)] += mk;
+            else sums[LG_SLOT_DIFF(dm)] += mk;
+        }
+    });
+    const int tile = ba * (ba + 1) / 2 + bb;
+    for (int q = 0; q < nacc; ++q) {
+        const double tot = bqo_block_sum(sums[q], red);
+        if (threadIdx.x == 0) partial[((int64_t)s * nacc + q) * ntiles + tile] = tot;
+    }
+}
+
 __global__ void loglik_grad_final_kernel(bqo_kernel_desc d, const double* __restrict__ hyp,
                                          int64_t stride, const double* __restrict__ partial,
                                          int nblk, const double* __restrict__ alpha, int n,
@@ -176,7 +281,8 @@ extern "C" int64_t bqo_loglik_grad_workspace_bytes(int32_t n, int32_t S) {
 extern "C" int bqo_loglik_grad_batched(const bqo_kernel_desc* desc, const double* hyp, int32_t S,
                                        const double* Xs, const int32_t* tid, int32_t n,
                                        const double* L, const double* alpha, const double* y,
-                                       double* grad, void* workspace, void* stream) {
+                                       const double* Winv, double* grad, void* workspace,
+                                       void* stream) {
     BQO_CHECK_ARG(desc != nullptr, 1);
     BQO_CHECK_ARG(hyp != nullptr, 2);
     BQO_CHECK_ARG(S > 0 && S <= 65535, 3);
@@ -184,8 +290,8 @@ extern "C" int bqo_loglik_grad_batched(const bqo_kernel_desc* desc, const double
     BQO_CHECK_ARG(n > 0, 6);
     BQO_CHECK_ARG(L != nullptr, 7);
     BQO_CHECK_ARG(alpha != nullptr, 8);
-    BQO_CHECK_ARG(grad != nullptr, 10);
-    BQO_CHECK_ARG(workspace != nullptr, 11);
+    BQO_CHECK_ARG(grad != nullptr, 11);
+    BQO_CHECK_ARG(workspace != nullptr, 12);
     BQO_CHECK_ARG(desc->n_tasks <= 128, 1);
     (void)y;
     cudaStream_t cs = (cudaStream_t)stream;
@@ -195,15 +301,33 @@ extern "C" int bqo_loglik_grad_batched(const bqo_kernel_desc* desc, const double
     double* Wbuf = Inv + (int64_t)S * n * n;
     double* partial = Wbuf + (int64_t)S * n * n;
     double* Wtask = partial + (int64_t)S * LG_MAX_ACC * nblk;
-    int rc = bqo_internal_inverse_from_chol(L, n, S, Inv, Wbuf, cs);
-    if (rc) return rc;
+    // W = L^-1 either comes with the factorisation (bqo_chol_cov_batched's Winv) or is built here
+    int rc = 0;
+    const double* Wuse = Winv;
+    if (!Wuse) {
+        rc = bqo_internal_tri_inverse(L, n, S, Wbuf, Inv, cs);
+        if (rc) return rc;
+        Wuse = Wbuf;
+    }
     if (desc->kind == BQO_KIND_PRODUCT_TASKS && !desc->same_corr)
         cudaMemsetAsync(Wtask, 0, sizeof(double) * S * desc->n_tasks * desc->n_tasks, cs);
-    dim3 grid(1, nb, S);
     const int64_t st = bqo_hyper_stride_impl(*desc);
     bqo_ensure_global_exp_table(cs);
-    BQO_L, loglik_grad_partial_kernel<<<grid, 256, 0, cs>>>(*desc, hyp, st, Xs, tid, n, Inv, alpha, partial,
-                                                     Wtask);
-    BQO_L, loglik_grad_final_kernel<<<S, 256, 0, cs>>>(*desc, hyp, st, partial, nb, alpha, n, Wtask, grad);
+    const int nb64 = (n + BQO_TILE - 1) / BQO_TILE;
+    const int ntiles = nb64 * (nb64 + 1) / 2;       // <= the (n/32)^2 slots of `partial`
+    {
+        static int granted[64] = {0};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 64 && !granted[dev]) {
+            cudaFuncSetAttribute(inv_syrk_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)LGF_SMEM_BYTES);
+            granted[dev] = 1;
+        }
+    }
+    dim3 grid(nb64, nb64, S);
+    BQO_L, inv_syrk_contract_kernel<<<grid, 128, LGF_SMEM_BYTES, cs>>>(*desc, hyp, st, Xs, tid, n, Wuse,
+                                                                alpha, partial, Wtask, ntiles);
+    BQO_L, loglik_grad_final_kernel<<<S, 256, 0, cs>>>(*desc, hyp, st, partial, ntiles, alpha, n, Wtask, grad);
     BQO_RETURN_LAST_ERROR();
 }

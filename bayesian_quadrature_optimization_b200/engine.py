@@ -85,6 +85,17 @@ class GPEngine(object):
         return HyperBatch(self, thetas)
 
 
+def potrf_batched(eng: GPEngine, A: torch.Tensor):
+    """In-place lower Cholesky of A[S][n][n] (bqo_potrf_batched with its scratch) -> info[S]."""
+    S, n = int(A.shape[0]), int(A.shape[1])
+    info = torch.zeros(S, dtype=I32, device=A.device)
+    work = torch.empty(int(eng.lib.bqo_potrf_workspace_bytes(n, S)) // 8 + 2, dtype=F64,
+                       device=A.device)
+    check(eng.lib.bqo_potrf_batched(ptr(A), n, S, ptr(info), ptr(work), _stream()),
+          "bqo_potrf_batched")
+    return info
+
+
 class HyperBatch(object):
     """S hyper-samples resident on the device with their prepared blocks and factors."""
 
@@ -101,9 +112,10 @@ class HyperBatch(object):
         check(lib.bqo_scale_points(C.byref(d), ptr(self.hyp), self.S, ptr(eng.X), eng.n, d.dim,
                                    ptr(self.Xs), ptr(self.tid), _stream()), "bqo_scale_points")
         self.L = None
+        self.Winv = None
         self.alpha = None
-        self.info = None
-        self.jitter = None
+        self._info = None
+        self._jitter = None
 
     # -- kernel matrices ------------------------------------------------------------------------
     def cov(self, add_noise=False):
@@ -148,24 +160,127 @@ class HyperBatch(object):
         return out
 
     # -- factorisation ----------------------------------------------------------------------------
-    def factorize(self, max_tries=7):
-        """Sigma_s = K_s + noise; L_s with the reference's jitter policy; alpha_s."""
+    def factorize(self, max_tries=7, with_inverse=False):
+        """Sigma_s = K_s + noise; L_s (first attempt of the reference's jitter policy); alpha_s.
+        Nothing is copied to the host here: `info` / `jitter` resolve lazily (one device-to-host
+        read) and continue the policy for the matrices that failed.
+        with_inverse: the same launch also leaves W_s = L_s^-1 (the log-likelihood gradient forms
+        Sigma^-1 = W^T W from it), as extra tasks that fill the SMs the factorisation leaves idle."""
         if self.L is not None:
             return self
         eng = self.eng
-        self.L = eng.empty(self.S, eng.n, eng.n)
-        info = (C.c_int32 * self.S)()
-        jit = (C.c_double * self.S)()
+        S = self.S
+        self.L = eng.empty(S, eng.n, eng.n)
+        self.Winv = eng.empty(S, eng.n, eng.n) if with_inverse else None
+        wscratch = eng.empty(S, eng.n, eng.n) if (with_inverse and eng.n % 2 == 1) else None
+        self._max_tries = int(max_tries)
+        self._info_dev = torch.zeros(S, dtype=I32, device=eng.device)
+        self._diag_mean = eng.empty(S)
+        self._diag_nonpos = torch.zeros(S, dtype=I32, device=eng.device)
+        nbytes = int(eng.lib.bqo_potrf_workspace_bytes(eng.n, S))
+        work = torch.empty(nbytes // 8 + 2, dtype=F64, device=eng.device)
         check(eng.lib.bqo_chol_cov_batched(
-            C.byref(eng.desc), ptr(self.hyp), self.S, ptr(self.Xs), ptr(self.tid), eng.n,
-            ptr(eng.noise_obs), int(max_tries), ptr(self.L), info, jit, _stream()),
+            C.byref(eng.desc), ptr(self.hyp), S, ptr(self.Xs), ptr(self.tid), eng.n,
+            ptr(eng.noise_obs), ptr(self.L), ptr(self._info_dev), ptr(self._diag_mean),
+            ptr(self._diag_nonpos), ptr(self.Winv), ptr(wscratch), ptr(work), _stream()),
             "bqo_chol_cov_batched")
-        self.info = np.array(list(info), dtype=np.int32)
-        self.jitter = np.array(list(jit), dtype=np.float64)
-        self.alpha = eng.empty(self.S, eng.n)
+        self._info = self._jitter = None
+        self._alpha()
+        return self
+
+    def _alpha(self):
+        eng = self.eng
+        if self.alpha is None:
+            self.alpha = eng.empty(self.S, eng.n)
         check(eng.lib.bqo_alpha_batched(ptr(self.hyp), eng.hyp_stride, ptr(self.L), eng.n, self.S,
                                         ptr(eng.y), ptr(self.alpha), _stream()), "bqo_alpha_batched")
-        return self
+
+    def _resolve(self, info_host=None):
+        """Host copy of the factorisation codes; runs the rest of the reference's jitter policy
+        (sbo/lib/la_functions.py:19-38: "not positive definite matrix" when a diagonal entry is
+        <= 0, else Sigma + jitter I with jitter = mean(diag) 1e-6 10^t, t < max_tries) for the
+        matrices whose first attempt failed.  -> info: 0 ok, -1, -2 as in the two LinAlgErrors."""
+        if self._info is not None:
+            return
+        eng = self.eng
+        S = self.S
+        if info_host is None:
+            info_host = self._info_dev.cpu().numpy()
+        info = np.zeros(S, dtype=np.int32)
+        jitter = np.zeros(S, dtype=np.float64)
+        bad = np.nonzero(info_host)[0]
+        if len(bad) > 0:
+            if np.any(info_host[bad] == -3):
+                raise _cabi.BqoLibraryError("persistent Cholesky: scheduling wait limit reached")
+            mean = self._diag_mean.cpu().numpy()
+            nonpos = self._diag_nonpos.cpu().numpy()
+            work1 = torch.empty(int(eng.lib.bqo_potrf_workspace_bytes(eng.n, 1)) // 8 + 2, dtype=F64,
+                                device=eng.device)
+            jd = eng.empty(1)
+            one = torch.zeros(1, dtype=I32, device=eng.device)
+            for s in bad:
+                if nonpos[s]:
+                    info[s] = -1
+                    continue
+                jit = mean[s] * 1e-6
+                ok = False
+                for _ in range(self._max_tries):
+                    if not np.isfinite(jit):
+                        break
+                    check(eng.lib.bqo_chol_cov_retry(
+                        C.byref(eng.desc), ptr(self.hyp), int(s), ptr(self.Xs), ptr(self.tid), eng.n,
+                        ptr(eng.noise_obs), float(jit), ptr(jd), ptr(self.L), ptr(one), ptr(work1),
+                        _stream()), "bqo_chol_cov_retry")
+                    if int(one.item()) == 0:
+                        ok = True
+                        break
+                    jit *= 10.0
+                if ok:
+                    jitter[s] = jit
+                else:
+                    info[s] = -2
+            self._alpha()
+            self.Winv = None  # refactored matrices: the gradient rebuilds L^-1 from L
+        self._info, self._jitter = info, jitter
+
+    @property
+    def info(self):
+        if self.L is None:
+            return None
+        self._resolve()
+        return self._info
+
+    @info.setter
+    def info(self, value):
+        self._info = value
+
+    @property
+    def jitter(self):
+        if self.L is None:
+            return None
+        self._resolve()
+        return self._jitter
+
+    @jitter.setter
+    def jitter(self, value):
+        self._jitter = value
+
+    def log_likelihood_host(self):
+        """np.array(S) of log-likelihoods with -inf where the factorisation failed: the values and
+        the factorisation codes come back in ONE device-to-host copy (the slice sampler's probes)."""
+        self.factorize()
+        llh = self.log_likelihood()
+        if self._info is None:
+            both = torch.cat([llh, self._info_dev.to(F64)]).cpu().numpy()
+            codes = both[self.S:].astype(np.int32)
+            if not np.any(codes):
+                self._resolve(info_host=codes)
+                return both[:self.S]
+            self._resolve(info_host=codes)
+            llh = self.log_likelihood()
+        out = llh.cpu().numpy()
+        out[self._info != 0] = -np.inf
+        return out
 
     def appended(self, eng2: GPEngine) -> "HyperBatch":
         """The same hyper-samples on `eng2`, whose training set is this engine's plus ONE point
@@ -194,11 +309,11 @@ class HyperBatch(object):
         if bool(info.any().item()):
             return hb2.factorize()
         hb2.L = L_new
+        hb2.Winv = None
+        hb2._max_tries = self._max_tries
         hb2.info = np.zeros(S, dtype=np.int32)
         hb2.jitter = self.jitter.copy()
-        hb2.alpha = eng2.empty(S, n + 1)
-        check(eng.lib.bqo_alpha_batched(ptr(hb2.hyp), eng2.hyp_stride, ptr(hb2.L), n + 1, S,
-                                        ptr(eng2.y), ptr(hb2.alpha), _stream()), "bqo_alpha_batched")
+        hb2._alpha()
         return hb2
 
     def solve(self, Bt):
@@ -221,14 +336,16 @@ class HyperBatch(object):
 
     def grad_log_likelihood(self):
         eng = self.eng
-        self.factorize()
+        self.factorize(with_inverse=True)
+        _ = self.info  # (resolves a failed first attempt before L^-1 is used)
         nbytes = int(eng.lib.bqo_loglik_grad_workspace_bytes(eng.n, self.S))
         work = torch.empty(nbytes // 8 + 1, dtype=F64, device=eng.device)
         grad = eng.empty(self.S, 2 + eng.desc.n_params)
         check(eng.lib.bqo_loglik_grad_batched(
             C.byref(eng.desc), ptr(self.hyp), self.S, ptr(self.Xs), ptr(self.tid), eng.n,
-            ptr(self.L), ptr(self.alpha), ptr(eng.y), ptr(grad), ptr(work), _stream()),
-            "bqo_loglik_grad_batched")
+            ptr(self.L), ptr(self.alpha), ptr(eng.y), ptr(self.Winv), ptr(grad), ptr(work),
+            _stream()), "bqo_loglik_grad_batched")
+        self.Winv = None  # S n^2 doubles: not kept alive in the caller's factor cache
         return grad
 
     # -- posterior / EI ------------------------------------------------------------------------------

@@ -457,7 +457,7 @@ class GPFittingGaussian(object):
     def grad_log_likelihood(self, var_noise, mean, parameters_kernel):
         """:876-897 -> np.array(2 + p): [d var_noise, d mean, d kernel params]."""
         hb = self._hb1(var_noise, mean, parameters_kernel)
-        hb.factorize(max_tries=7)
+        hb.factorize(max_tries=7, with_inverse=True)
         self._raise_info(int(hb.info[0]))
         return hb.grad_log_likelihood().cpu().numpy()[0]
 
@@ -470,13 +470,11 @@ class GPFittingGaussian(object):
         factorisation failed (objective_llh convention, :946-960)."""
         hb = self.hyper_batch(thetas)
         hb.factorize(max_tries=7)
-        llh = hb.log_likelihood().cpu().numpy()
-        llh[hb.info != 0] = -np.inf
-        return llh
+        return hb.log_likelihood_host()
 
     def grad_log_likelihood_batch(self, thetas):
         hb = self.hyper_batch(thetas)
-        hb.factorize(max_tries=7)
+        hb.factorize(max_tries=7, with_inverse=True)
         return hb.grad_log_likelihood().cpu().numpy()
 
     def _cholesky_solve_vectors_for_posterior(self, var_noise, mean, parameters_kernel,

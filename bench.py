@@ -525,7 +525,7 @@ def run_gpu(args):
         hb = eng.hypers(wl["thetas"])
         torch.cuda.synchronize()
         ev0.record()
-        hb.factorize()
+        hb.factorize(with_inverse=True)   # log-likelihood AND gradient are asked for
         llh = hb.log_likelihood()
         gll = hb.grad_log_likelihood()
         ev1.record()

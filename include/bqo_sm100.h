@@ -14,7 +14,7 @@
  *     side); FP64 unless stated; row-major; nothing is allocated internally except where a
  *     `*_workspace_bytes` query says how much scratch the caller must pass;
  *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on that stream
- *     unless documented otherwise (only `bqo_chol_cov_batched` and the probes synchronise);
+ *     unless documented otherwise (only the roofline probes synchronise);
  *   - return value: 0 = ok, <0 = bad argument (-(1-based argument index)), >0 = CUDA error
  *     code (cudaError_t) from the launch;
  *   - hyper-sample vector layout (sbo/models/gp_fitting_gaussian.py:637-655):
@@ -120,20 +120,46 @@ int bqo_cross_cov_hessian_batched(const bqo_kernel_desc* desc, const double* hyp
 /* In-place lower Cholesky of S row-major n x n matrices (lower triangle read; strict upper
  * triangle zeroed like scipy dpotrf clean=1, sbo/lib/la_functions.py:17).
  * info[s] = 0 ok, k>0: leading minor k not positive definite. */
-int bqo_potrf_batched(double* A, int32_t n, int32_t S, int32_t* info, void* stream);
+int bqo_potrf_batched(double* A, int32_t n, int32_t S, int32_t* info, void* workspace,
+                      void* stream);
+/* Scratch of bqo_potrf_batched / bqo_chol_cov_batched / bqo_chol_cov_retry for S matrices of
+ * order n (inverses of the 64 x 64 diagonal blocks and the progress counters of the persistent
+ * kernel).  The content need not be initialised and is not needed after the call. */
+int64_t bqo_potrf_workspace_bytes(int32_t n, int32_t S);
+/* 1: factor with the multi-launch right-looking path of round 1 instead of the persistent kernel
+ * (tests compare the two; also selected by the environment variable BQO_POTRF_LEGACY=1, and always
+ * used for odd n).  Returns the previous setting. */
+int bqo_potrf_set_multi_launch(int on);
+/* Tuning aid (no reference counterpart): bqo_potrf_batched that also writes %globaltimer stamps of
+ * the critical-path tasks of matrix 0 to prof[ceil(n/64)][2][8] (uint64, device, zeroed by the
+ * caller): [j][0][.] diagonal task of column j, [j][1][.] tile (j+1, j). */
+int bqo_potrf_profile(double* A, int32_t n, int32_t S, int32_t* info, void* workspace,
+                      unsigned long long* prof, void* stream);
 /* Solve L L^T x = b for m right-hand sides per matrix; Bt[s][r][i] holds right-hand side r
  * contiguously (RHS-major), overwritten by the solution (cho_solve, sbo/lib/la_functions.py:41-50). */
 int bqo_potrs_batched(const double* L, int32_t n, int32_t S, double* Bt, int32_t m,
                       void* stream);
-/* Sigma_s = K_s + noise, L_s = chol(Sigma_s) with the reference's jitter escalation
- * (cholesky(cov, max_tries), sbo/lib/la_functions.py:8-38, called with max_tries=7 from
- * sbo/models/gp_fitting_gaussian.py:764).  Synchronises the stream to read info.
- * info[s]: 0 ok; -1 "not positive definite matrix" (a diagonal entry <= 0);
- * -2 "not positive definite, even with jitter".  jitter_used[s] = jitter finally added. */
+/* Sigma_s = K_s + noise, L_s = chol(Sigma_s): the first attempt of
+ * cholesky(cov, max_tries) (sbo/lib/la_functions.py:8-38, called from
+ * sbo/models/gp_fitting_gaussian.py:764), for all S hyper-samples, WITHOUT synchronising.
+ * Device outputs: info[s] = dpotrf's code (0 ok, k > 0: leading minor k not positive definite),
+ * diag_mean[s] = mean(diag Sigma_s) and diag_nonpos[s] = 1 when a diagonal entry is <= 0 (the
+ * two inputs of the jitter policy).  When info[s] != 0 the caller continues the policy with
+ * bqo_chol_cov_retry: "not positive definite matrix" if diag_nonpos, else jitter =
+ * diag_mean * 1e-6 * 10^t for t = 0 .. max_tries - 1 (la_functions.py:19-38).
+ * Winv (optional, [S][n][n]): the same launch also leaves W_s = L_s^-1 on the lower 64 x 64 tiles
+ * (what the log-likelihood gradient needs to form Sigma^-1 = W^T W; pass it on to
+ * bqo_loglik_grad_batched).  Winv_scratch: S n^2 doubles, needed only for odd n. */
 int bqo_chol_cov_batched(const bqo_kernel_desc* desc, const double* hyp, int32_t S,
                          const double* Xs, const int32_t* tid, int32_t n, const double* noise_obs,
-                         int32_t max_tries, double* L, int32_t* info_host,
-                         double* jitter_used_host, void* stream);
+                         double* L, int32_t* info, double* diag_mean, int32_t* diag_nonpos,
+                         double* Winv, double* Winv_scratch, void* workspace, void* stream);
+/* One retry of the policy for hyper-sample s: L_s = chol(Sigma_s + jitter I); info_one (device,
+ * one int) receives the code; jitter_dev: one double of device scratch. */
+int bqo_chol_cov_retry(const bqo_kernel_desc* desc, const double* hyp, int32_t s, const double* Xs,
+                       const int32_t* tid, int32_t n, const double* noise_obs, double jitter,
+                       double* jitter_dev, double* L, int32_t* info_one, void* workspace,
+                       void* stream);
 /* Append one training point to S factors in O(n^2) each (the "updated cache in a smart way" TODO of
  * add_points_evaluations, sbo/models/gp_fitting_gaussian.py:492-511, which refactorises instead).
  * knew[s][0..n) = Sigma'_s(new, old points), knew[s][n] = Sigma'_s(new, new) including noise (and the
@@ -153,11 +179,12 @@ int64_t bqo_loglik_grad_workspace_bytes(int32_t n, int32_t S);
 /* grad[s][0]=d/d var_noise, [1]=d/d mean, [2+j]=d/d kernel param j
  * (grad_log_likelihood, sbo/models/gp_fitting_gaussian.py:832-897, 1654-1697; a13).
  * Computed as 0.5 <alpha alpha^T - Sigma^{-1}, dK_j>_F with Sigma^{-1} formed once from L and
- * dK_j generated on the fly (never written to HBM). */
+ * dK_j generated on the fly (never written to HBM).  Winv: L^-1 from bqo_chol_cov_batched, or NULL
+ * (it is then built here from L). */
 int bqo_loglik_grad_batched(const bqo_kernel_desc* desc, const double* hyp, int32_t S,
                             const double* Xs, const int32_t* tid, int32_t n, const double* L,
-                            const double* alpha, const double* y, double* grad, void* workspace,
-                            void* stream);
+                            const double* alpha, const double* y, const double* Winv, double* grad,
+                            void* workspace, void* stream);
 
 /* ---- GP posterior and EI (a18, a19, a39) ------------------------------------------------ */
 /* For each hyper-sample s and query point q (P raw [m][dim]):

@@ -253,3 +253,54 @@ def test_bench_accounting_helpers():
     m = bench.issue_model(evals, ms, {"sm_mhz": mhz}, 34.6)
     assert abs(m["model_cycles_over_elapsed_cycles"] - 1.0) < 1e-12
     assert 0.0 < m["executed_frac_of_dfma_issue_rate"] < 1.0
+
+
+def _pp_decode(tsk, S, nb, with_w):
+    """Python restatement of pp_decode (csrc/bqo_potrf_persistent.cuh): task index ->
+    (kind, matrix, tile row, tile column); kind 0 = factor tile, 1 = inverse tile."""
+    if tsk < 3 * S:
+        w = tsk // S
+        return (0, tsk % S, 0 if w == 0 else 1, 1 if w == 2 else 0)
+    rem = tsk - 3 * S
+    for jj in range(0, nb - 1):
+        c1 = S * (nb - jj - 2)
+        if rem < c1:
+            return (0, rem % S, jj + 2 + rem // S, jj)
+        rem -= c1
+        c2 = 2 * S if jj + 2 <= nb - 1 else 0
+        if rem < c2:
+            return (0, rem % S, jj + 2, jj + 1 if rem < S else jj + 2)
+        rem -= c2
+        c3 = S * jj if with_w else 0
+        if rem < c3:
+            return (1, rem % S, jj, rem // S)
+        rem -= c3
+    return (1, rem % S, nb - 1, rem // S)
+
+
+@pytest.mark.parametrize("nb,S", [(1, 1), (1, 3), (2, 2), (3, 1), (5, 3), (8, 2), (32, 1)])
+@pytest.mark.parametrize("with_w", [False, True])
+def test_persistent_cholesky_task_order_is_topological(nb, S, with_w):
+    """The persistent kernel hands tasks out in list order and a task waits for its inputs: no
+    deadlock needs every input of a task to sit EARLIER in the list, and every tile exactly once."""
+    total = S * nb * nb if with_w else S * nb * (nb + 1) // 2
+    seen = {}
+    for t in range(total):
+        kind, s, i, j = _pp_decode(t, S, nb, with_w)
+        assert 0 <= j <= i < nb and 0 <= s < S
+        assert (kind, s, i, j) not in seen
+        if kind == 0:
+            for k in range(j):          # left-looking product: rows i and j up to column j
+                assert (0, s, i, k) in seen and (0, s, j, k) in seen
+            if i > j:
+                assert (0, s, j, j) in seen            # inverse of the diagonal block
+        else:
+            assert i > j and (0, s, i, i) in seen      # W(i,i) comes from the diagonal task
+            for k in range(j + 1, i):
+                assert (1, s, k, j) in seen            # W(k,j) above it in the same column
+            for k in range(j, i):
+                assert (0, s, i, k) in seen            # row i of L
+        seen[(kind, s, i, j)] = t
+    n_factor = sum(1 for k in seen if k[0] == 0)
+    assert n_factor == S * nb * (nb + 1) // 2
+    assert len(seen) - n_factor == (S * nb * (nb - 1) // 2 if with_w else 0)

@@ -266,15 +266,15 @@ def test_cholesky_solve_random_sizes():
     eng = E.GPEngine(_cabi.KIND_MATERN52, 1)
     # m * S <= 512 takes the vector-solve kernels, above that the DMMA tile solve: both at ragged
     # sizes, odd n (8-byte cp.async staging) and even n (16-byte staging)
+    # even n: the persistent kernel (one launch); odd n: the multi-launch path
     for n, S, m in [(1, 2, 1), (63, 2, 3), (64, 1, 65), (65, 3, 7), (300, 2, 130), (517, 2, 5),
                     (65, 3, 200), (300, 2, 300), (517, 2, 261), (130, 9, 64), (257, 1, 513),
-                    (64, 2, 300), (1, 3, 200)]:
+                    (64, 2, 300), (1, 3, 200), (2, 1, 1), (66, 5, 2), (128, 3, 4), (190, 1, 1),
+                    (448, 7, 3), (1024, 2, 2), (1090, 3, 1)]:
         A = rng.normal(0, 1, (S, n, n + 5))
         A = A @ A.transpose(0, 2, 1) + 1e-3 * np.eye(n)
         Ad = eng.to_device(A.copy())
-        info = torch.zeros(S, dtype=torch.int32, device=eng.device)
-        _cabi.check(eng.lib.bqo_potrf_batched(_cabi.ptr(Ad), n, S, _cabi.ptr(info),
-                                              torch.cuda.current_stream().cuda_stream), "potrf")
+        info = E.potrf_batched(eng, Ad)
         assert not info.cpu().numpy().any()
         L = np.stack([np.linalg.cholesky(a) for a in A])
         assert_close(Ad.cpu().numpy(), L, rtol=1e-9, atol=1e-11, what="potrf n=%d" % n)
@@ -319,10 +319,45 @@ def test_cholesky_not_positive_definite_and_jitter():
         assert_close(hb.L.cpu().numpy()[0], want, rtol=1e-6, atol=1e-9, what="jittered chol")
     # a matrix with a non-positive diagonal entry reports the reference's first error
     A = eng.to_device(np.array([[[1.0, 2.0], [2.0, -1.0]]]))
-    info = torch.zeros(1, dtype=torch.int32, device=eng.device)
-    _cabi.check(eng.lib.bqo_potrf_batched(_cabi.ptr(A), 2, 1, _cabi.ptr(info),
-                                          torch.cuda.current_stream().cuda_stream), "potrf")
-    assert info.cpu().numpy()[0] == 2
+    assert E.potrf_batched(eng, A).cpu().numpy()[0] == 2
+
+
+def test_persistent_cholesky_against_multi_launch_and_failures():
+    """The persistent kernel against the multi-launch factorisation (same matrices), dpotrf's
+    failure code in the middle of a large matrix, and a failing matrix next to healthy ones in
+    the same batch (its tasks stop, the others finish)."""
+    import torch
+    from bayesian_quadrature_optimization_b200 import engine as E, _cabi
+    rng = np.random.RandomState(3)
+    eng = E.GPEngine(_cabi.KIND_MATERN52, 1)
+    for n, S in [(640, 4), (2048, 3), (130, 20)]:
+        A = rng.normal(0, 1, (S, n, n + 8))
+        A = A @ A.transpose(0, 2, 1) + 1e-2 * np.eye(n)
+        a1, a2 = eng.to_device(A.copy()), eng.to_device(A.copy())
+        assert not E.potrf_batched(eng, a1).cpu().numpy().any()
+        old = eng.lib.bqo_potrf_set_multi_launch(1)
+        try:
+            assert not E.potrf_batched(eng, a2).cpu().numpy().any()
+        finally:
+            eng.lib.bqo_potrf_set_multi_launch(old)
+        ref = torch.linalg.cholesky(eng.to_device(A))
+        scale = ref.abs().max().item()
+        assert (a1 - ref).abs().max().item() < 1e-11 * scale
+        assert (a2 - ref).abs().max().item() < 1e-11 * scale
+        assert a1.triu(1).abs().max().item() == 0.0
+    # leading minor 301 of matrix 1 is not positive definite; matrices 0 and 2 are fine
+    n, S = 512, 3
+    A = rng.normal(0, 1, (S, n, n + 8))
+    A = A @ A.transpose(0, 2, 1) + 1e-2 * np.eye(n)
+    Lref = np.linalg.cholesky(A[1])
+    # make the pivot at index 300 negative: subtract more than its Schur complement
+    A[1, 300, 300] -= 2.0 * Lref[300, 300] ** 2
+    Ad = eng.to_device(A.copy())
+    info = E.potrf_batched(eng, Ad).cpu().numpy()
+    assert info[0] == 0 and info[2] == 0 and info[1] == 301
+    for s in (0, 2):
+        assert_close(Ad[s].cpu().numpy(), np.linalg.cholesky(A[s]), rtol=1e-9, atol=1e-10,
+                     what="healthy matrix next to a failing one")
 
 
 def test_large_size_properties():
