@@ -447,6 +447,9 @@ class SBO(object):
                 start = st_ei
         start = np.asarray(start, dtype=float).reshape(-1, len(self.bounds_opt))
 
+        if n_samples_parameters == 0 and not monte_carlo:
+            return self._optimize_discretised(start)
+
         # ---- batched Adam over all restarts --------------------------------------------------------
         parameters = gp.samples_parameters[-n_parameters:] if n_parameters > 0 else \
             [gp.get_value_parameters_model]
@@ -517,6 +520,44 @@ class SBO(object):
                 npt[i] += np.random.uniform(-lb, ub)
         result = {'solution': solution, 'optimal_value': float(output['evaluations'][ind_max]),
                   'gradient': gradient}
+        self.optimization_results.append(result)
+        return result
+
+    def _optimize_discretised(self, start):
+        """The branch `n_samples_parameters == 0 and not monte_carlo` of SBO.optimize (:1800-1821):
+        the discretised SBO (closed-form knowledge gradient over `discretization_domain`, model
+        parameters at their current values) is maximised from every start point with L-BFGS-B,
+        maxiter = 10 (Optimization(LBFGS_NAME, wrapper_objective_voi, bounds, wrapper_gradient_voi,
+        minimize=False, maxiter=10), sbo/lib/optimization.py:87-155); scipy drives, every value and
+        gradient comes from the device (kg_kernel, gradient_vector_b).  Returns the best restart
+        with the reference's result keys."""
+        from scipy.optimize import fmin_l_bfgs_b
+        if self.discretization is None:
+            raise ValueError("the discretised SBO needs a discretization_domain")
+        bounds = [tuple(bound) for bound in self.bounds_opt]
+        results = []
+        for x0 in start:
+            opt = fmin_l_bfgs_b(
+                lambda x: -1.0 * self.evaluate(x.reshape((1, len(x)))), np.array(x0, dtype=float),
+                fprime=lambda x: -1.0 * self.evaluate_gradient(x.reshape((1, len(x)))),
+                bounds=bounds, maxiter=10)
+            results.append({'solution': opt[0], 'optimal_value': -1.0 * opt[1],
+                            'gradient': -1.0 * opt[2]['grad'], 'warnflag': opt[2]['warnflag'],
+                            'task': opt[2]['task'], 'nit': opt[2]['nit'],
+                            'funcalls': opt[2]['funcalls']})
+        ind_max = int(np.argmax([r['optimal_value'] for r in results]))
+        result = results[ind_max]
+        if np.any(np.isnan(result['gradient'])):
+            # :1915-1946: perturb the solution when its gradient is unavailable
+            bq = self.bq
+            finite = not bq.task_continue and bq.separate_tasks
+            point = result['solution'][:-1] if finite else result['solution']
+            size = np.sqrt(np.sum(point ** 2)) * 1e-6
+            for i in range(len(point)):
+                lb = min(size, point[i] - bounds[i][0])
+                ub = min(size, bounds[i][1] - point[i])
+                point[i] += np.random.uniform(-lb, ub)
+            result['gradient'] = 'unavailable'
         self.optimization_results.append(result)
         return result
 

@@ -49,8 +49,10 @@ class BayesianQuadrature(object):
             self.weights = np.array(self.parameters_distribution['weights'], dtype=float)
             self.n_tasks = len(self.weights)
             self.task_continue = True
-            if self.parameters_distribution.get('n_samples'):
-                raise NotImplementedError("sub-sampled finite expectations are not accelerated")
+        self.full_weights = self.weights
+        if distribution in (UNIFORM_FINITE, WEIGHTED_UNIFORM_FINITE) and \
+                self.parameters_distribution.get('n_samples'):
+            self.resample_tasks(self.parameters_distribution.get('n_samples'))
         elif distribution in (GAMMA, EXPONENTIAL):
             pass
         else:
@@ -99,6 +101,19 @@ class BayesianQuadrature(object):
         dim_w = len(self.w_domain)
         self.w_sets = np.stack([gamma.rvs(a, scale=scale, size=(n_samples, dim_w))
                                 for _ in range(n_w_sets)])
+        self._bq_cache = OrderedDict()
+
+    def resample_tasks(self, n_samples):
+        """Sub-sampled finite expectation (`n_samples` of parameters_distribution; uniform_finite,
+        sbo/lib/expectations.py:37-42): n_samples tasks are drawn with replacement with the task
+        probabilities, np.random.choice(T, n_samples, replace=True, p=weights), and the
+        expectation becomes their plain average -- i.e. quadrature weights count / n_samples.  The
+        reference redraws inside every call; here the draw is made once per object (and again on
+        demand), like the W samples of the continuous case."""
+        p = None if self.full_weights is None else self.full_weights / np.sum(self.full_weights)
+        index = np.random.choice(self.n_tasks, int(n_samples), replace=True, p=p)
+        self.task_sample = index
+        self.weights = np.bincount(index, minlength=self.n_tasks).astype(float) / float(n_samples)
         self._bq_cache = OrderedDict()
 
     def set_w_sets(self, w_sets):

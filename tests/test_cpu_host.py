@@ -304,3 +304,42 @@ def test_persistent_cholesky_task_order_is_topological(nb, S, with_w):
     n_factor = sum(1 for k in seen if k[0] == 0)
     assert n_factor == S * nb * (nb + 1) // 2
     assert len(seen) - n_factor == (S * nb * (nb - 1) // 2 if with_w else 0)
+
+
+def test_simplex_start_points_match_the_reference(golden):
+    """DomainService.get_points_domain with a simplex domain (sbo/services/domain.py:115-170)."""
+    from bayesian_quadrature_optimization_b200.services.domain import DomainService
+    g = golden("host_misc")
+    bounds = [list(b) for b in g["simplex_bounds"]]
+    np.random.seed(17)
+    pts = np.array(DomainService.get_points_domain(7, bounds, type_bounds=6 * [0],
+                                                   simplex_domain=int(g["simplex_domain"])))
+    assert np.array_equal(pts, g["simplex_points"])
+    assert np.all(pts[:, 2:].sum(1) <= int(g["simplex_domain"]))
+
+
+def test_subsampled_finite_expectation_matches_the_reference(golden):
+    """`n_samples` of parameters_distribution (uniform_finite, sbo/lib/expectations.py:37-42): the
+    tasks drawn for a seed and the quadrature weights they induce, weighted and uniform."""
+    from bayesian_quadrature_optimization_b200.models.gp_fitting_gaussian import GPFittingGaussian
+    from bayesian_quadrature_optimization_b200.numerical_tools.bayesian_quadrature import \
+        BayesianQuadrature
+    from bayesian_quadrature_optimization_b200.lib import constant as K
+    g = golden("host_misc")
+    T = len(g["weights"])
+    pts = np.array([[0.1 * i, i % T] for i in range(2 * T)], dtype=float)
+    td = {"points": pts.tolist(), "evaluations": list(np.arange(2 * T, dtype=float)), "var_noise": []}
+    gp = GPFittingGaussian([K.PRODUCT_KERNELS_SEPARABLE, K.MATERN52_NAME, K.TASKS_KERNEL_NAME], td,
+                           [2, 1, T], bounds_domain=[[0, 2], list(range(T))], type_bounds=[0, 1],
+                           define_samplers=False)
+    np.random.seed(23)
+    bq = BayesianQuadrature(gp, [0], K.WEIGHTED_UNIFORM_FINITE, parameters_distribution={
+        "weights": g["weights"], "domain_random": np.arange(T).reshape(T, 1), "n_samples": 11})
+    assert np.array_equal(bq.task_sample, g["sub_weighted_index"])
+    # E f = sum_t w_t f(t): the reference's sub-sampled mean of f(x, t) = table[t] * x at x = 2
+    assert abs(np.dot(bq.weights, g["table"]) * 2.0 - float(g["sub_weighted"].reshape(-1)[0])) < 1e-14
+    np.random.seed(29)
+    bq = BayesianQuadrature(gp, [0], K.UNIFORM_FINITE, parameters_distribution={
+        K.TASKS: T, "n_samples": 9})
+    assert np.array_equal(bq.task_sample, g["sub_uniform_index"])
+    assert abs(np.dot(bq.weights, g["table"]) * 2.0 - float(g["sub_uniform"].reshape(-1)[0])) < 1e-14

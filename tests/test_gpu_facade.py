@@ -637,3 +637,35 @@ def test_model_with_several_chains_samples_and_runs_bgo():
               n_restarts_mean=4, n_best_restarts_mean=2, n_samples_parameters_mean=2, maxepoch_mean=3,
               default_n_samples_parameters=3, default_n_samples=3, n_chains=2)
     assert out["optimal_solution"].shape == (1,) and 0.0 <= out["optimal_solution"][0] <= 1.0
+
+
+@pytest.mark.parametrize("name", ["product_uniform", "product_weighted"])
+def test_sbo_optimize_discretised_branch(golden, name):
+    """SBO.optimize(monte_carlo=False, n_samples_parameters=0) (sbo/acquisition_functions/sbo.py:
+    1800-1821): L-BFGS-B (maxiter 10) on the discretised knowledge gradient from every start.  The
+    same scipy call on the CPU oracle from the same start points gives the same optimum."""
+    from scipy.optimize import fmin_l_bfgs_b
+    from bayesian_quadrature_optimization_b200.acquisition_functions.sbo import SBO
+    g = golden(name)
+    gp, bq = _models(g)
+    spec, ogp, obq = oracle_from_golden(g)
+    disc = g["discretization"]
+    sbo = SBO(bq, disc)
+    th = gp.get_value_parameters_model
+    np.random.seed(3)
+    starts = sbo._restart_points(2)
+    np.random.seed(3)
+    res = sbo.optimize(monte_carlo=False, n_samples_parameters=0, n_restarts=2, start_ei=False)
+    assert set(res) >= {"solution", "optimal_value", "gradient"}
+    bounds_x = [(disc[:, l].min(), disc[:, l].max()) for l in range(disc.shape[1])]
+    osbo = orc.OracleSBO(obq, bounds_x, discretization=disc)
+    bounds = [tuple(b) for b in sbo.bounds_opt]
+    best = -np.inf
+    for x0 in starts:
+        opt = fmin_l_bfgs_b(lambda x: -osbo.evaluate(x.reshape(1, -1), th[0], th[1], th[2:]), x0,
+                            fprime=lambda x: -osbo.evaluate_gradient(x.reshape(1, -1), th[0], th[1], th[2:]),
+                            bounds=bounds, maxiter=10)
+        best = max(best, -opt[1])
+    assert_close(res["optimal_value"], best, rtol=1e-5, atol=1e-9, what="discretised SBO optimum")
+    # the returned value is the discretised SBO at the returned solution
+    assert_close(sbo.evaluate(res["solution"].reshape(1, -1)), res["optimal_value"], rtol=1e-12)
