@@ -104,6 +104,7 @@ SIGNATURES = {
     "bqo_chol_cov_retry": (C.c_int, [_KD, _P, _I, _P, _P, _I, _P, _D, _P, _P, _P, _P, _P]),
     "bqo_chol_append_batched": (C.c_int, [_P, _I, _I, _P, _P, _P, _P, _P]),
     "bqo_alpha_batched": (C.c_int, [_P, _L, _P, _I, _I, _P, _P, _P]),
+    "bqo_alpha_from_inverse_batched": (C.c_int, [_P, _L, _P, _I, _I, _P, _P, _P, _P]),
     "bqo_loglik_batched": (C.c_int, [_P, _L, _P, _P, _P, _I, _I, _P, _P]),
     "bqo_loglik_grad_workspace_bytes": (_L, [_I, _I]),
     "bqo_loglik_grad_batched": (C.c_int, [_KD, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P]),

@@ -15,6 +15,7 @@ int bqo_internal_inverse_from_chol(const double* L, int n, int S, double* Inv, d
                                    cudaStream_t cs);
 int bqo_internal_tri_inverse(const double* L, int n, int S, double* Wbuf, double* scratch,
                              cudaStream_t cs);
+int bqo_internal_inv_syrk(const double* Wbuf, int n, int S, double* Inv, cudaStream_t cs);
 
 #define LG_MAX_ACC (BQO_MAX_DIM + 4)
 // accumulator slots: [0..dim_m) length scales, then
@@ -109,6 +110,88 @@ __global__ void __launch_bounds__(256)
 }
 
 
+
+// Contraction of one 64 x 64 tile of Sigma^-1 (in the accumulator registers) with M = alpha alpha^T
+// - Sigma^-1 against every dK_j.  DMT = dim_m at compile time (0: run-time value, local-memory
+// arrays): with a run-time loop bound the per-pair arrays live in local memory and the epilogue
+// costs as much as the tile product itself.
+struct LgTile {
+    const double *xi, *xj, *ai, *aj;
+    const int *ti, *tj;
+    int a0, b0, ra, rb, s;
+    double wsym;
+};
+
+template <int DMT>
+__device__ __forceinline__ void lg_contract_tile(BqoAcc& acc, const bqo_kernel_desc& d,
+                                                 const double* __restrict__ h, const LgTile& tl,
+                                                 double* __restrict__ Wtask, double* __restrict__ out,
+                                                 int ntiles, double* red) {
+    constexpr int DMA = (DMT > 0) ? DMT : BQO_MAX_DIM;
+    const int dm = (DMT > 0) ? DMT : d.dim_m;
+    const bool prod = d.kind == BQO_KIND_PRODUCT_TASKS;
+    const bool general_tasks = prod && !d.same_corr;
+    const double sigma2 = (d.kind == BQO_KIND_SCALED_MATERN52) ? h[BQO_H_SIGMA2] : 1.0;
+    double invls[DMA], sums[DMA], s_km = 0.0, s_same = 0.0, s_diff = 0.0, s_trace = 0.0;
+#pragma unroll
+    for (int l = 0; l < DMA; ++l) {
+        invls[l] = (l < dm) ? h[BQO_H_INVLS + l] : 0.0;
+        sums[l] = 0.0;
+    }
+    bqo_acc_foreach(acc, [&](int r, int c, double& v) {
+        if (r >= tl.ra || c >= tl.rb) return;
+        const int i = tl.a0 + r, j = tl.b0 + c;
+        const double Mij = tl.wsym * (tl.ai[r] * tl.aj[c] - v);
+        double df[DMA];
+        double r2 = 0.0;
+#pragma unroll
+        for (int l = 0; l < DMA; ++l) {
+            df[l] = (l < dm) ? tl.xi[l * BQO_TILE + r] - tl.xj[l * BQO_TILE + c] : 0.0;
+            r2 = fma(df[l], df[l], r2);
+        }
+        double km = 1.0, g = -BQO_FIVE_THIRDS;
+        if (i != j) {
+            double u2v[1], ev[1], uv[1];
+            u2v[0] = fma(r2, BQO_PRESCALE * BQO_PRESCALE, 1e-300);
+            bqo_matern52_q_v<1>(u2v, GlobalExpTab(), ev, uv);
+            const double lin = fma(uv[0], BQO_LN2_N, 1.0) * ev[0];  // (1 + sqrt5 r) e
+            km = fma(u2v[0] * ev[0], BQO_H_TO_K, lin);
+            g = -BQO_FIVE_THIRDS * lin;                             // k'(r) / r
+        }
+        double other = sigma2;
+        if (prod) other = bqo_task_cov(h, d.n_tasks, tl.ti[r], tl.tj[c]);
+        if (i != j) {
+            const double w = -Mij * g * other;
+#pragma unroll
+            for (int l = 0; l < DMA; ++l) sums[l] = fma(w * df[l] * df[l], invls[l], sums[l]);
+        } else {
+            s_trace += Mij;
+        }
+        const double mk = Mij * km;
+        s_km += mk;
+        if (prod) {
+            if (general_tasks)
+                atomicAdd(Wtask + ((int64_t)tl.s * d.n_tasks + tl.ti[r]) * d.n_tasks + tl.tj[c], mk);
+            else if (tl.ti[r] == tl.tj[c]) s_same += mk;
+            else s_diff += mk;
+        }
+    });
+    // slots: [0..dm) length scales, then LG_SLOT_KM, LG_SLOT_SAME, LG_SLOT_DIFF, LG_SLOT_TRACE
+#pragma unroll
+    for (int l = 0; l < DMA; ++l) {
+        if (l < dm) {
+            const double tot = bqo_block_sum(sums[l], red);
+            if (threadIdx.x == 0) out[(int64_t)l * ntiles] = tot;
+        }
+    }
+    const double extra[4] = {s_km, s_same, s_diff, s_trace};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const double tot = bqo_block_sum(extra[q], red);
+        if (threadIdx.x == 0) out[(int64_t)(dm + q) * ntiles] = tot;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Sigma^-1 = W^T W and the contraction in ONE kernel: a CTA forms one 64 x 64 lower tile of
 // Sigma^-1 on DMMA (K range from the tile's first row: W = L^-1 vanishes above it) and contracts it,
@@ -162,52 +245,22 @@ __global__ void __launch_bounds__(128)
         tj[r] = (prod && r < rb) ? tid[b0 + r] : 0;
     }
     __syncthreads();
-    const int nacc = dm + 4;
-    double sums[LG_MAX_ACC];
-    for (int q = 0; q < nacc; ++q) sums[q] = 0.0;
-    const bool general_tasks = prod && !d.same_corr;
     const double wsym = (bb < ba) ? 2.0 : 1.0;   // strictly lower tiles stand for their mirror too
-    const double sigma2 = (d.kind == BQO_KIND_SCALED_MATERN52) ? h[BQO_H_SIGMA2] : 1.0;
-    bqo_acc_foreach(acc, [&](int r, int c, double& v) {
-        if (r >= ra || c >= rb) return;
-        const int i = a0 + r, j = b0 + c;
-        const double Mij = wsym * (ai[r] * aj[c] - v);
-        double df[BQO_MAX_DIM];
-        double r2 = 0.0;
-        for (int l = 0; l < dm; ++l) {
-            df[l] = xi[l * BQO_TILE + r] - xj[l * BQO_TILE + c];
-            r2 = fma(df[l], df[l], r2);
-        }
-        double km = 1.0, g = -BQO_FIVE_THIRDS;
-        if (i != j) {
-            double u2v[1], ev[1], uv[1];
-            u2v[0] = fma(r2, BQO_PRESCALE * BQO_PRESCALE, 1e-300);
-            bqo_matern52_q_v<1>(u2v, GlobalExpTab(), ev, uv);
-            const double lin = fma(uv[0], BQO_LN2_N, 1.0) * ev[0];  // (1 + sqrt5 r) e
-            km = fma(u2v[0] * ev[0], BQO_H_TO_K, lin);
-            g = -BQO_FIVE_THIRDS * lin;                             // k'(r) / r
-        }
-        double other = sigma2;
-        if (prod) other = bqo_task_cov(h, d.n_tasks, ti[r], tj[c]);
-        if (i != j) {
-            const double w = -Mij * g * other;
-            for (int l = 0; l < dm; ++l)
-                sums[l] = fma(w * df[l] * df[l], h[BQO_H_INVLS + l], sums[l]);
-        } else {
-            sums[LG_SLOT_TRACE(dm)] += Mij;
-        }
-        const double mk = Mij * km;
-        sums[LG_SLOT_KM(dm)] += mk;
-        if (prod) {
-            if (general_tasks) atomicAdd(Wtask + ((int64_t)s * d.n_tasks + ti[r]) * d.n_tasks + tj[c], mk);
-            else if (ti[r] == tj[c]) sums[LG_SLOT_SAME(dm)] += mk;
-            else sums[LG_SLOT_DIFF(dm)] += mk;
-        }
-    });
     const int tile = ba * (ba + 1) / 2 + bb;
-    for (int q = 0; q < nacc; ++q) {
-        const double tot = bqo_block_sum(sums[q], red);
-        if (threadIdx.x == 0) partial[((int64_t)s * nacc + q) * ntiles + tile] = tot;
+    LgTile tl;
+    tl.xi = xi; tl.xj = xj; tl.ai = ai; tl.aj = aj; tl.ti = ti; tl.tj = tj;
+    tl.a0 = a0; tl.b0 = b0; tl.ra = ra; tl.rb = rb; tl.wsym = wsym; tl.s = s;
+    double* out = partial + (int64_t)s * (dm + 4) * ntiles + tile;
+    switch (dm) {
+        case 1: lg_contract_tile<1>(acc, d, h, tl, Wtask, out, ntiles, red); break;
+        case 2: lg_contract_tile<2>(acc, d, h, tl, Wtask, out, ntiles, red); break;
+        case 3: lg_contract_tile<3>(acc, d, h, tl, Wtask, out, ntiles, red); break;
+        case 4: lg_contract_tile<4>(acc, d, h, tl, Wtask, out, ntiles, red); break;
+        case 5: lg_contract_tile<5>(acc, d, h, tl, Wtask, out, ntiles, red); break;
+        case 6: lg_contract_tile<6>(acc, d, h, tl, Wtask, out, ntiles, red); break;
+        case 7: lg_contract_tile<7>(acc, d, h, tl, Wtask, out, ntiles, red); break;
+        case 8: lg_contract_tile<8>(acc, d, h, tl, Wtask, out, ntiles, red); break;
+        default: break;   // dim_m > 8 takes the two-kernel path (bqo_loglik_grad_batched)
     }
 }
 
@@ -313,6 +366,16 @@ extern "C" int bqo_loglik_grad_batched(const bqo_kernel_desc* desc, const double
         cudaMemsetAsync(Wtask, 0, sizeof(double) * S * desc->n_tasks * desc->n_tasks, cs);
     const int64_t st = bqo_hyper_stride_impl(*desc);
     bqo_ensure_global_exp_table(cs);
+    if (desc->dim_m > 8) {
+        // generic path: Sigma^-1 to memory, then the contraction over 32 x 32 tiles
+        rc = bqo_internal_inv_syrk(Wuse, n, S, Inv, cs);
+        if (rc) return rc;
+        dim3 grid(1, nb, S);
+        BQO_L, loglik_grad_partial_kernel<<<grid, 256, 0, cs>>>(*desc, hyp, st, Xs, tid, n, Inv, alpha,
+                                                         partial, Wtask);
+        BQO_L, loglik_grad_final_kernel<<<S, 256, 0, cs>>>(*desc, hyp, st, partial, nb, alpha, n, Wtask, grad);
+        BQO_RETURN_LAST_ERROR();
+    }
     const int nb64 = (n + BQO_TILE - 1) / BQO_TILE;
     const int ntiles = nb64 * (nb64 + 1) / 2;       // <= the (n/32)^2 slots of `partial`
     {

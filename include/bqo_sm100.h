@@ -171,6 +171,11 @@ int bqo_chol_append_batched(const double* L_old, int32_t n, int32_t S, const dou
 /* alpha[s] = Sigma_s^{-1} (y - mean_s)  (sbo/models/gp_fitting_gaussian.py:1241-1244). */
 int bqo_alpha_batched(const double* hyp, int64_t hyp_stride, const double* L, int32_t n, int32_t S,
                       const double* y, double* alpha, void* stream);
+/* The same alpha from W_s = L_s^-1 (the Winv of bqo_chol_cov_batched): alpha = W^T (W (y - mean)),
+ * two bandwidth-bound passes instead of two triangular solves.  work: S * n doubles. */
+int bqo_alpha_from_inverse_batched(const double* hyp, int64_t hyp_stride, const double* Winv,
+                                   int32_t n, int32_t S, const double* y, double* alpha,
+                                   double* work, void* stream);
 /* llh[s] = -sum_i log L_ii - 0.5 (y-mean)^T alpha   (log_likelihood, :772-798; a12). */
 int bqo_loglik_batched(const double* hyp, int64_t hyp_stride, const double* L, const double* alpha,
                        const double* y, int32_t n, int32_t S, double* llh, void* stream);

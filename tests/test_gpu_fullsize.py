@@ -416,6 +416,12 @@ def test_c3_grad_loglik_against_oracle_n2048():
     assert_close(got, want, rtol=1e-9, atol=1e-9 * scale, what="grad llh n=2048")
     assert_close(hb.log_likelihood().cpu().numpy()[0], ogp.log_likelihood(th[0], th[1], th[2:]),
                  rtol=1e-11, what="llh n=2048")
+    # inverse produced by the factorisation launch, alpha from it, fused Sigma^-1 contraction
+    hb = eng.hypers(thetas).factorize(with_inverse=True)
+    assert_close(hb.grad_log_likelihood().cpu().numpy()[0], want, rtol=1e-9, atol=1e-9 * scale,
+                 what="grad llh n=2048 (fused)")
+    assert_close(hb.log_likelihood().cpu().numpy()[0], ogp.log_likelihood(th[0], th[1], th[2:]),
+                 rtol=1e-10, what="llh n=2048 (alpha from W)")
 
 
 def test_c3_whole_pipeline_against_oracle_pipeline_n2048():

@@ -57,6 +57,23 @@ def test_cholesky_loglik_and_gradient(golden, name):
                  what="grad llh")
 
 
+@pytest.mark.parametrize("name", GP_CASES)
+def test_loglik_and_gradient_with_inverse_from_the_factorisation(golden, name):
+    """factorize(with_inverse=True): L^-1 from extra tasks of the persistent kernel (even n) or the
+    level kernels (odd n), alpha = W^T W r, Sigma^-1 formed and contracted in one kernel -- against
+    the reference fixtures, and against the path that solves with L."""
+    g = golden(name)
+    eng = _engine(g)
+    hb = eng.hypers(g["thetas"]).factorize(with_inverse=True)
+    assert hb.Winv is not None and np.all(hb.info == 0)
+    assert_close(hb.log_likelihood().cpu().numpy(), g["llh"], rtol=1e-10, what="llh (alpha from W)")
+    assert_close(hb.grad_log_likelihood().cpu().numpy(), g["grad_llh"], rtol=1e-8, atol=1e-9,
+                 what="grad llh (fused)")
+    hb2 = eng.hypers(g["thetas"]).factorize()
+    assert_close(hb.alpha.cpu().numpy(), hb2.alpha.cpu().numpy(), rtol=1e-7,
+                 atol=1e-9 * float(hb2.alpha.abs().max()), what="alpha from W vs solves")
+
+
 @pytest.mark.parametrize("n", [1, 63, 64, 65, 130, 257, 300, 517])
 def test_loglik_gradient_ragged_sizes(n):
     """Sizes that are not multiples of the 64-wide tiles (and of the doubling blocks of the
@@ -76,6 +93,12 @@ def test_loglik_gradient_ragged_sizes(n):
     want = np.stack([ogp.grad_log_likelihood(t[0], t[1], t[2:]) for t in thetas])
     assert_close(hb.grad_log_likelihood().cpu().numpy(), want, rtol=1e-8, atol=1e-9,
                  what="grad llh n=%d" % n)
+    # the same with L^-1 produced by the factorisation launch
+    hb = eng.hypers(thetas).factorize(with_inverse=True)
+    assert_close(hb.grad_log_likelihood().cpu().numpy(), want, rtol=1e-8, atol=1e-9,
+                 what="grad llh (inverse from the factorisation) n=%d" % n)
+    want_llh = [ogp.log_likelihood(t[0], t[1], t[2:]) for t in thetas]
+    assert_close(hb.log_likelihood().cpu().numpy(), want_llh, rtol=1e-10, what="llh n=%d" % n)
 
 
 @pytest.mark.parametrize("name", GP_CASES)
