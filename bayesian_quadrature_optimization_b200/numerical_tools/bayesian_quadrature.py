@@ -49,15 +49,12 @@ class BayesianQuadrature(object):
             self.weights = np.array(self.parameters_distribution['weights'], dtype=float)
             self.n_tasks = len(self.weights)
             self.task_continue = True
-        self.full_weights = self.weights
-        if distribution in (UNIFORM_FINITE, WEIGHTED_UNIFORM_FINITE) and \
-                self.parameters_distribution.get('n_samples'):
-            self.resample_tasks(self.parameters_distribution.get('n_samples'))
-        elif distribution in (GAMMA, EXPONENTIAL):
-            pass
-        else:
+        elif distribution not in (GAMMA, EXPONENTIAL):
             raise NameError("distribution %s is not on the accelerated path" % distribution)
         finite = distribution in (UNIFORM_FINITE, WEIGHTED_UNIFORM_FINITE)
+        self.full_weights = self.weights
+        if finite and self.parameters_distribution.get('n_samples'):
+            self.resample_tasks(self.parameters_distribution.get('n_samples'))
         if finite != (self.gp._kind == _cabi.KIND_PRODUCT_TASKS):
             raise ValueError("finite W needs the Matern52 x Tasks product kernel and vice versa")
 

@@ -343,3 +343,32 @@ def test_subsampled_finite_expectation_matches_the_reference(golden):
         K.TASKS: T, "n_samples": 9})
     assert np.array_equal(bq.task_sample, g["sub_uniform_index"])
     assert abs(np.dot(bq.weights, g["table"]) * 2.0 - float(g["sub_uniform"].reshape(-1)[0])) < 1e-14
+
+
+def test_quadrature_models_build_on_the_host_for_every_distribution():
+    """BayesianQuadrature's constructor is host-only work: every supported distribution builds
+    without a device, anything else raises NameError like the reference's dictionary lookup."""
+    from bayesian_quadrature_optimization_b200.models.gp_fitting_gaussian import GPFittingGaussian
+    from bayesian_quadrature_optimization_b200.numerical_tools.bayesian_quadrature import \
+        BayesianQuadrature
+    from bayesian_quadrature_optimization_b200.lib import constant as K
+    T = 3
+    pts = np.array([[0.1 * i, i % T] for i in range(9)], dtype=float)
+    td = {"points": pts.tolist(), "evaluations": list(np.arange(9.0)), "var_noise": []}
+    gp = GPFittingGaussian([K.PRODUCT_KERNELS_SEPARABLE, K.MATERN52_NAME, K.TASKS_KERNEL_NAME], td,
+                           [2, 1, T], bounds_domain=[[0, 1], list(range(T))], type_bounds=[0, 1],
+                           define_samplers=False)
+    bq = BayesianQuadrature(gp, [0], K.UNIFORM_FINITE, parameters_distribution={K.TASKS: T})
+    assert bq.n_tasks == T and bq.weights is None and bq.separate_tasks
+    bq = BayesianQuadrature(gp, [0], K.WEIGHTED_UNIFORM_FINITE, parameters_distribution={
+        "weights": [0.2, 0.3, 0.5], "domain_random": np.arange(T).reshape(T, 1)})
+    assert bq.task_continue and np.allclose(bq.weights, [0.2, 0.3, 0.5])
+    with pytest.raises(NameError):
+        BayesianQuadrature(gp, [0], "beta", parameters_distribution={})
+    td2 = {"points": np.random.RandomState(0).uniform(0, 1, (6, 3)).tolist(),
+           "evaluations": list(np.arange(6.0)), "var_noise": []}
+    gp2 = GPFittingGaussian([K.SCALED_KERNEL, K.MATERN52_NAME], td2, [3],
+                            bounds_domain=[[0, 1]] * 3, define_samplers=False)
+    np.random.seed(1)
+    bq2 = BayesianQuadrature(gp2, [0, 1], K.GAMMA, parameters_distribution={"a": [2.0], "scale": [1.0]})
+    assert bq2.w_sets.shape == (1, 10, 1) and bq2.w_double_sets.shape == (2, 100, 1)
