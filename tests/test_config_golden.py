@@ -117,7 +117,10 @@ def test_gpu_classes_against_reference_at_config(golden, name):
         tol = _rtol(g, spec, s)
         chol, _ = gp._chol_cov_including_noise(vn, pk)
         assert_close(chol, g["chol"][s], rtol=max(1e-10, tol), atol=1e-13, what="chol")
-        assert_close(gp.log_likelihood(vn, mu, pk), g["llh"][s], rtol=1e-11, what="llh")
+        # the quadratic term of the log-likelihood passes through Sigma^-1: cond(Sigma) eps
+        # (1e-11 at the well-conditioned vector, 1.3e-9 observed at cond = 1e9 with the blocked
+        # factorisation, whose panel solves multiply by the inverted 64 x 64 diagonal blocks)
+        assert_close(gp.log_likelihood(vn, mu, pk), g["llh"][s], rtol=max(1e-11, tol), what="llh")
         assert_close(gp.grad_log_likelihood(vn, mu, pk), g["grad_llh"][s], rtol=max(1e-8, tol),
                      atol=1e-8, what="grad llh")
         post = gp.compute_posterior_parameters(g["query"], vn, mu, pk)
