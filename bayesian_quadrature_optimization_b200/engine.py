@@ -78,8 +78,37 @@ class GPEngine(object):
         self.n = int(self.X.shape[0])
         self.noise_obs = None if var_noise_obs is None else self.to_device(var_noise_obs).reshape(-1)
 
+    # Guard bands (debugging aid; compute-sanitizer is not available on the B200 pool): with
+    # GPEngine.guard_doubles > 0 every buffer handed to the library sits between two bands of a
+    # known bit pattern, and check_guards() reports any band a kernel wrote into.
+    guard_doubles = 0
+    _guards = []
+    _GUARD_VALUE = -6.02214076e23
+
     def empty(self, *shape, dtype=F64):
-        return torch.empty(*shape, dtype=dtype, device=self.device)
+        g = GPEngine.guard_doubles
+        if g <= 0 or dtype != F64:
+            return torch.empty(*shape, dtype=dtype, device=self.device)
+        if len(shape) == 1 and isinstance(shape[0], (tuple, list, torch.Size)):
+            shape = tuple(shape[0])
+        numel = 1
+        for d in shape:
+            numel *= int(d)
+        raw = torch.full((numel + 2 * g,), GPEngine._GUARD_VALUE, dtype=F64, device=self.device)
+        GPEngine._guards.append((raw, g, numel, tuple(int(d) for d in shape)))
+        return raw[g:g + numel].view(*shape)
+
+    @staticmethod
+    def check_guards(clear=True):
+        """Number of guard bands that no longer hold the pattern (0 = no out-of-bounds write)."""
+        bad = []
+        for raw, g, numel, shape in GPEngine._guards:
+            lo, hi = raw[:g], raw[g + numel:]
+            if not (bool((lo == GPEngine._GUARD_VALUE).all()) and bool((hi == GPEngine._GUARD_VALUE).all())):
+                bad.append(shape)
+        if clear:
+            GPEngine._guards = []
+        return bad
 
     def hypers(self, thetas) -> "HyperBatch":
         return HyperBatch(self, thetas)

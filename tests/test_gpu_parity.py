@@ -606,3 +606,25 @@ def test_stage_c_other_dimensions(dx, dw):
     gb = obq.gradient_vector_b(cands[1:2], xq, th[0], th[1], th[2:], w=wset)
     assert_close(gvb.cpu().numpy()[1 * S + 1][:, :gb.shape[1]], gb[:, :gvb.shape[2]], rtol=1e-6,
                  atol=1e-9, what="gvb dx=%d dw=%d" % (dx, dw))
+
+
+def test_no_kernel_writes_outside_its_buffers():
+    """compute-sanitizer is closed on the B200 pool, so out-of-bounds WRITES are looked for with
+    guard bands: every FP64 buffer the engine hands to the library sits between two bands of a
+    known pattern (GPEngine.guard_doubles); one pass through every kernel family at ragged sizes
+    (n = 200, 131, 64, 1; gamma-W and finite-W models) must leave all bands intact."""
+    import runpy
+    import os
+    from bayesian_quadrature_optimization_b200 import engine as E
+    from tests.conftest import ROOT
+    E.GPEngine.guard_doubles = 512
+    E.GPEngine._guards = []
+    try:
+        runpy.run_path(os.path.join(ROOT, "tests", "microbench", "sanitizer_smoke.py"), run_name="smoke")
+        n_buffers = len(E.GPEngine._guards)
+        bad = E.GPEngine.check_guards()
+    finally:
+        E.GPEngine.guard_doubles = 0
+        E.GPEngine._guards = []
+    assert n_buffers > 100
+    assert bad == [], "out-of-bounds writes next to buffers of shape %s" % (bad,)
