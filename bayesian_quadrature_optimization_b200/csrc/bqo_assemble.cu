@@ -127,7 +127,11 @@ template <int DM>
 __global__ void assemble_kernel(bqo_kernel_desc d, const double* __restrict__ hyp, int64_t stride,
                                 const double* __restrict__ Xs, const int32_t* __restrict__ tid,
                                 int n, const double* __restrict__ noise_obs, int add_noise,
-                                const double* __restrict__ extra_diag, double* __restrict__ K) {
+                                const double* __restrict__ extra_diag, double* __restrict__ K,
+                                int lower_only) {
+    // lower_only (the factorisation's input): only the 64 x 64 tiles on or below the diagonal are
+    // produced -- the Cholesky kernels read nothing else and zero the strict upper triangle
+    if (lower_only && (blockIdx.x >> 1) > (blockIdx.y >> 1)) return;
     int j = blockIdx.x * 32 + threadIdx.x;
     int i0 = blockIdx.y * 32 + threadIdx.y * 4;
     int s = blockIdx.z;
@@ -172,10 +176,23 @@ __global__ void assemble_kernel(bqo_kernel_desc d, const double* __restrict__ hy
     }
 }
 
+int bqo_internal_assemble(const bqo_kernel_desc* desc, const double* hyp, int32_t S,
+                          const double* Xs, const int32_t* tid, int32_t n, const double* noise_obs,
+                          int32_t add_noise, const double* extra_diag, double* K, int lower_only,
+                          void* stream);
+
 extern "C" int bqo_kernel_assemble_batched(const bqo_kernel_desc* desc, const double* hyp,
                                            int32_t S, const double* Xs, const int32_t* tid,
                                            int32_t n, const double* noise_obs, int32_t add_noise,
                                            const double* extra_diag, double* K, void* stream) {
+    return bqo_internal_assemble(desc, hyp, S, Xs, tid, n, noise_obs, add_noise, extra_diag, K, 0,
+                                 stream);
+}
+
+int bqo_internal_assemble(const bqo_kernel_desc* desc, const double* hyp, int32_t S,
+                          const double* Xs, const int32_t* tid, int32_t n, const double* noise_obs,
+                          int32_t add_noise, const double* extra_diag, double* K, int lower_only,
+                          void* stream) {
     BQO_CHECK_ARG(check_desc(desc), 1);
     BQO_CHECK_ARG(hyp != nullptr, 2);
     BQO_CHECK_ARG(S > 0, 3);
@@ -190,7 +207,7 @@ extern "C" int bqo_kernel_assemble_batched(const bqo_kernel_desc* desc, const do
     bqo_ensure_global_exp_table(cs);
 #define LAUNCH_ASM(DMV)                                                                          \
     BQO_L, assemble_kernel<DMV><<<grid, block, 0, cs>>>(*desc, hyp, st, Xs, tid, n, noise_obs,          \
-                                                 add_noise, extra_diag, K)
+                                                 add_noise, extra_diag, K, lower_only)
     switch (desc->dim_m) {
         case 1: LAUNCH_ASM(1); break;
         case 2: LAUNCH_ASM(2); break;

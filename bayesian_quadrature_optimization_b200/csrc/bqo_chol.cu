@@ -386,6 +386,11 @@ static int potrf_launch_persistent(double* A, int n, int S, int* info, double* W
     return (int)cudaGetLastError();
 }
 
+int bqo_internal_assemble(const bqo_kernel_desc* desc, const double* hyp, int32_t S,
+                          const double* Xs, const int32_t* tid, int32_t n, const double* noise_obs,
+                          int32_t add_noise, const double* extra_diag, double* K, int lower_only,
+                          void* stream);
+
 static int g_potrf_legacy = -1;
 extern "C" int bqo_potrf_set_multi_launch(int on) {
     const int old = g_potrf_legacy > 0 ? 1 : 0;
@@ -1017,7 +1022,7 @@ extern "C" int bqo_chol_cov_batched(const bqo_kernel_desc* desc, const double* h
     BQO_CHECK_ARG(workspace != nullptr, 14);
     BQO_CHECK_ARG(Winv == nullptr || Winv_scratch != nullptr || n % 2 == 0, 13);
     cudaStream_t cs = (cudaStream_t)stream;
-    int rc = bqo_kernel_assemble_batched(desc, hyp, S, Xs, tid, n, noise_obs, 1, nullptr, L, stream);
+    int rc = bqo_internal_assemble(desc, hyp, S, Xs, tid, n, noise_obs, 1, nullptr, L, 1, stream);
     if (rc) return rc;
     BQO_L, diag_stats_kernel<<<S, 256, 0, cs>>>(L, n, diag_mean, diag_nonpos);
     return potrf_launch(L, n, S, info, workspace, cs, Winv, Winv_scratch);
@@ -1040,9 +1045,9 @@ extern "C" int bqo_chol_cov_retry(const bqo_kernel_desc* desc, const double* hyp
     cudaStream_t cs = (cudaStream_t)stream;
     const int64_t st = bqo_hyper_stride_impl(*desc);
     cudaMemcpyAsync(jitter_dev, &jitter, sizeof(double), cudaMemcpyHostToDevice, cs);
-    int rc = bqo_kernel_assemble_batched(desc, hyp + (int64_t)s * st, 1,
-                                         Xs + (int64_t)s * desc->dim_m * n, tid, n, noise_obs, 1,
-                                         jitter_dev, L + (int64_t)s * n * n, stream);
+    int rc = bqo_internal_assemble(desc, hyp + (int64_t)s * st, 1, Xs + (int64_t)s * desc->dim_m * n,
+                                   tid, n, noise_obs, 1, jitter_dev, L + (int64_t)s * n * n, 1,
+                                   stream);
     if (rc) return rc;
     return potrf_launch(L + (int64_t)s * n * n, n, 1, info_one, workspace, cs);
 }

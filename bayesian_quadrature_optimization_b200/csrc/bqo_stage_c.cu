@@ -660,7 +660,16 @@ __global__ void __launch_bounds__(IM_WARPS * 32, 1)
                           double* __restrict__ out_arg, unsigned long long* __restrict__ n_evals) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int zc_per_unit = (opt.n_z + opt.z_per_cta - 1) / opt.z_per_cta;
-    const int unit = blockIdx.x / zc_per_unit;
+    // Without staging (n too large for shared memory) the operands of a unit stream from L2, and
+    // those shared by a hyper-sample (scaled points, alpha, the W-distance table: 3 MB at
+    // n = 8192) should be shared by the CTAs that run together: blocks walk the units
+    // hyper-sample-major (unit = c * S_u + k: block b -> c = b % C, k = b / C), not candidate-major
+    // (at S = 64 the candidate-major order touches 64 x 3 MB at once and falls out of the L2).
+    int unit = blockIdx.x / zc_per_unit;
+    if (!STAGE && pb.C > 0 && pb.n_units % pb.C == 0) {
+        const int s_units = pb.n_units / pb.C;
+        unit = (unit % pb.C) * s_units + unit / pb.C;
+    }
     const int zc = blockIdx.x % zc_per_unit;
     const int z0 = zc * opt.z_per_cta;
     const int nz = (opt.n_z - z0 < opt.z_per_cta) ? opt.n_z - z0 : opt.z_per_cta;
