@@ -127,11 +127,13 @@ __device__ __forceinline__ double bqo_matern52_dr(double r, double r2) {
 // The one constant that is not an FP64 immediate lives in constant memory so that DFMA/DMUL read
 // it as a c[bank][off] operand; as literals ptxas re-materialised each 64-bit constant with two
 // UMOVs inside the loop (27% of all issued instructions in the first profile).
-static __constant__ double BQO_FC[4] = {
+static __constant__ double BQO_FC[6] = {
     -BQO_LN2_N,                                      // 0: -c = -ln2/N
     -3.0 / BQO_LN2_N,                                // 1: b2 }  6 exp(-c d) / (-c^3) =
     6.0 / (BQO_LN2_N * BQO_LN2_N),                   // 2: b1 }    ((d + b2) d + b1) d + b0
     -6.0 / (BQO_LN2_N * BQO_LN2_N * BQO_LN2_N),      // 3: b0 }  (degree 3, N = 2048)
+    BQO_LN2_N,                                       // 4: c        } per-training-point constants of
+    BQO_H_TO_K,                                      // 5: c^2 / 3  } the stage-C loop (same values)
 };
 // Degree-3 variant that skips the multiplication by -c: the polynomial is taken in d = u - m
 // itself, monic, with its three coefficients as uniform-register operands (one LDCU each per
@@ -148,9 +150,18 @@ static __constant__ double BQO_FC[4] = {
 #define BQO_TAB_FOLD (1.0 / BQO_EXP_FOLD)
 #endif
 
+// Table entry j: T[j] = 2^(-j/N) * fold, with j * 2^(20 - BITS) ADDED to its high word.  The
+// evaluation turns the entry of m = q N + j into 2^-q T[j] with one IMAD on the high word,
+// hi - m * 2^(20 - BITS) = hi(T[j]) - q * 2^20 (the exponent field), and needs no mask to split
+// q from j: the j part of the product cancels the bias stored here (32-bit wrap-around arithmetic
+// on both sides).  The biased entry is not a meaningful double until that IMAD has been applied.
+__device__ __forceinline__ double bqo_exp_table_entry(int j) {
+    const double v = exp2(-(double)j / (double)BQO_EXP_TABLE) * BQO_TAB_FOLD;
+    return __hiloint2double(__double2hiint(v) + (j << (20 - BQO_EXP_BITS)), __double2loint(v));
+}
+
 __device__ __forceinline__ void bqo_exp_table_init(double* tab) {
-    for (int j = threadIdx.x; j < BQO_EXP_TABLE; j += blockDim.x)
-        tab[j] = exp2(-(double)j / (double)BQO_EXP_TABLE) * BQO_TAB_FOLD;
+    for (int j = threadIdx.x; j < BQO_EXP_TABLE; j += blockDim.x) tab[j] = bqo_exp_table_entry(j);
 }
 
 // NV independent evaluations in lock step (a single evaluation is one long dependent chain).
@@ -164,9 +175,9 @@ __device__ __forceinline__ void bqo_exp_table_init(double* tab) {
 // FP64 instructions per evaluation (N = 2048): sqrt 5, reduction 3, polynomial 3, table multiply 1.
 // CLAMP = false: the caller guarantees u2 <= 2^(2 (BITS + 9)) (bqo_wdist_precompute bounds its table
 // and the x part is clamped once per training point), so the per-evaluation clamp is dropped.
-template <int NV, class Tab, bool CLAMP = true>
+template <int NV, class Tab, bool CLAMP = true, bool LOSRC = false>
 __device__ __forceinline__ void bqo_matern52_q_v(const double (&u2)[NV], Tab tab, double (&e)[NV],
-                                                 double (&t1)[NV]) {
+                                                 double (&t1)[NV], const double* losrc = nullptr) {
     double g[NV], h[NV], w[NV], kf[NV], fr[NV], p[NV];
     unsigned n[NV];
     const double magic = 4503599627370496.0;  // 2^52: low word of (magic + u) = round(u) >= 0
@@ -174,9 +185,14 @@ __device__ __forceinline__ void bqo_matern52_q_v(const double (&u2)[NV], Tab tab
     for (int q = 0; q < NV; ++q) {
         double y;
         asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(u2[q]));
+        // LOSRC: the seed's low word is taken from `losrc` (any value the caller has in a dying
+        // register pair) instead of being zeroed -- one MOV less per evaluation.  The seed is
+        // then off by up to 2^-20 instead of 2^-22; after the Goldschmidt step and the Newton
+        // correction that is 1e-18 relative, far below half an ulp.
+        if (LOSRC) y = __hiloint2double(__double2hiint(y), __double2loint(losrc[q]));
         g[q] = u2[q] * y;
 #if BQO_HALF_INT
-        h[q] = __hiloint2double(__double2hiint(y) - 0x00100000, 0);  // y/2 on the integer pipe
+        h[q] = __hiloint2double(__double2hiint(y) - 0x00100000, LOSRC ? __double2loint(y) : 0);  // y/2 on the integer pipe
 #else
         h[q] = 0.5 * y;
 #endif
@@ -251,14 +267,13 @@ __device__ __forceinline__ void bqo_matern52_q_v(const double (&u2)[NV], Tab tab
 #endif
 #pragma unroll
     for (int q = 0; q < NV; ++q) {
-        double ev = p[q] * tab(n[q]);
-        // 2^-(m div N) into the exponent field: hi -= (m - m mod N) * 2^20 / N
+        const double tv = tab(n[q]);
+        // 2^-(m div N) into the exponent field of the table entry (see bqo_exp_table_entry)
         int hi;
         asm("mad.lo.s32 %0, %1, %3, %2;"
             : "=r"(hi)
-            : "r"((int)(n[q] & ~(unsigned)(BQO_EXP_TABLE - 1))), "r"(__double2hiint(ev)),
-              "n"(-(1 << (20 - BQO_EXP_BITS))));
-        e[q] = __hiloint2double(hi, __double2loint(ev));
+            : "r"((int)n[q]), "r"(__double2hiint(tv)), "n"(-(1 << (20 - BQO_EXP_BITS))));
+        e[q] = p[q] * __hiloint2double(hi, __double2loint(tv));
         t1[q] = g[q];
     }
 }
@@ -270,7 +285,7 @@ static __device__ double bqo_g_exp_tab[BQO_EXP_TABLE];
 
 static __global__ void bqo_exp_table_global_init_kernel() {
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < BQO_EXP_TABLE; j += gridDim.x * blockDim.x)
-        bqo_g_exp_tab[j] = exp2(-(double)j / (double)BQO_EXP_TABLE) * BQO_TAB_FOLD;
+        bqo_g_exp_tab[j] = bqo_exp_table_entry(j);
 }
 
 struct GlobalExpTab {

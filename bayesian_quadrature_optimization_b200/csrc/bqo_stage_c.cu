@@ -230,6 +230,9 @@ __device__ __forceinline__ EvalPtrs eval_ptrs_from(const UnitCtx<DX, DW>& u) {
 #ifndef EVAL_NV
 #define EVAL_NV 2
 #endif
+#ifndef BQO_LOSRC
+#define BQO_LOSRC true
+#endif
 
 // Warp-cooperative evaluation of a, b and their x-gradients at the raw point x.
 // Works in coordinates multiplied by K = sqrt5 N / ln2 (u2 = K^2 r^2, see bqo_matern52_q_v):
@@ -283,10 +286,13 @@ __device__ __forceinline__ void eval_ab_warp(const EvalPtrs& p, const UnitCtx<DX
             Dx = __hiloint2double((int)min((unsigned)__double2hiint(Dx), (unsigned)BQO_U2_PART_HI),
                                   __double2loint(Dx));
             auto step_nv = [&](int m) {
-                double q2v[EVAL_NV], ev[EVAL_NV], t1v[EVAL_NV];
+                double q2v[EVAL_NV], ev[EVAL_NV], t1v[EVAL_NV], wv[EVAL_NV];
 #pragma unroll
-                for (int q = 0; q < EVAL_NV; ++q) q2v[q] = Dx + __ldg(wj + (m + q) * 32);
-                bqo_matern52_q_v<EVAL_NV, SmemExpTab, false>(q2v, SmemExpTab(), ev, t1v);
+                for (int q = 0; q < EVAL_NV; ++q) {
+                    wv[q] = __ldg(wj + (m + q) * 32);
+                    q2v[q] = Dx + wv[q];
+                }
+                bqo_matern52_q_v<EVAL_NV, SmemExpTab, false, BQO_LOSRC>(q2v, SmemExpTab(), ev, t1v, wv);
 #pragma unroll
                 for (int q = 0; q < EVAL_NV; ++q) {
                     E0 += ev[q];
@@ -378,8 +384,9 @@ __device__ __forceinline__ void eval_ab_warp(const EvalPtrs& p, const UnitCtx<DX
             E1 = t1v[0] * ev[0];
             H = q2v[0] * ev[0];
         }
-        const double G = fma(E1, BQO_LN2_N, E0);  // sum_m (1 + sqrt5 r_m) e_m
-        const double ksum = fma(H, BQO_H_TO_K, G);
+        // c and c^2/3 as constant-bank operands: as literals they cost two UMOVs each per point
+        const double G = fma(E1, BQO_FC[4], E0);  // sum_m (1 + sqrt5 r_m) e_m
+        const double ksum = fma(H, BQO_FC[5], G);
         const double wa = REC ? p.xs[(size_t)j * RECLD + DX] : p.wa[j];
         const double wb = REC ? p.xs[(size_t)j * RECLD + DX + 1] : p.wb[j];
         if (CMB) {

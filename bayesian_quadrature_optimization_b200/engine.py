@@ -214,6 +214,8 @@ class HyperBatch(object):
             ptr(self._diag_nonpos), ptr(self.Winv), ptr(wscratch), ptr(work), _stream()),
             "bqo_chol_cov_batched")
         self._info = self._jitter = None
+        self._ill = None
+        self._alpha_refined = False
         self._alpha()
         return self
 
@@ -276,6 +278,8 @@ class HyperBatch(object):
                 else:
                     info[s] = -2
             self.Winv = None  # refactored matrices: the gradient rebuilds L^-1 from L
+            self._ill = None
+            self._alpha_refined = False
             self._alpha()
         self._info, self._jitter = info, jitter
 
@@ -352,14 +356,79 @@ class HyperBatch(object):
         hb2._alpha()
         return hb2
 
+    # -- solves ----------------------------------------------------------------------------------
+    # The blocked factorisation and the blocked triangular solves multiply by the explicitly
+    # inverted 64 x 64 diagonal blocks, so their backward error grows with the condition number of
+    # those blocks (LAPACK's substitution does not).  Harmless up to cond(Sigma) ~ 1e6; at the
+    # reference's own test vector (theta = [1, 5, 50, 9.6, -3, -0.1], cond = 7e9) b(x), which
+    # cancels to 1e-13 of its terms, moved by 2e-5.  Hyper-samples whose factor says
+    # cond(Sigma) >= (max L_ii / min L_ii)^2 >= REFINE_COND therefore get classical iterative
+    # refinement against the re-assembled Sigma (x += Sigma^-1 (b - Sigma x), FP64 residual):
+    # it restores the accuracy of a backward-stable solve and costs nothing elsewhere.
+    REFINE_COND = 1e6
+    REFINE_STEPS = 2
+
+    def ill_conditioned(self):
+        """Indices of the hyper-samples that get refined solves (one small device-to-host read per
+        factorisation; not on the slice sampler's log-likelihood path)."""
+        self.factorize()
+        ill = self.__dict__.get("_ill")
+        if ill is None:
+            dg = torch.diagonal(self.L, dim1=1, dim2=2)
+            ratio = (dg.amax(dim=1) / dg.amin(dim=1)).cpu().numpy()
+            ok = self.info == 0
+            with np.errstate(invalid="ignore"):
+                ill = np.nonzero(ok & (ratio * ratio >= self.REFINE_COND))[0]
+            self._ill = ill
+        return ill
+
+    def _cov_one(self, s):
+        """Sigma_s (noise and the factorisation's jitter on the diagonal): [n][n]."""
+        eng = self.eng
+        K = eng.empty(1, eng.n, eng.n)
+        check(eng.lib.bqo_kernel_assemble_batched(
+            C.byref(eng.desc), ptr(self.hyp[s:s + 1]), 1, ptr(self.Xs[s:s + 1]), ptr(self.tid), eng.n,
+            ptr(eng.noise_obs), 1, None, ptr(K), _stream()), "bqo_kernel_assemble_batched")
+        K = K[0]
+        if self.jitter[s] > 0:
+            K.diagonal().add_(float(self.jitter[s]))
+        return K
+
+    def _refine(self, s, rhs, x):
+        """x[m][n] <- x + Sigma_s^-1 (rhs - x Sigma_s), REFINE_STEPS times (rows are vectors)."""
+        eng = self.eng
+        Sig = self._cov_one(s)
+        m = int(x.shape[0])
+        for _ in range(self.REFINE_STEPS):
+            r = (rhs - torch.matmul(x, Sig)).contiguous()
+            check(eng.lib.bqo_potrs_batched(ptr(self.L[s]), eng.n, 1, ptr(r), m, _stream()),
+                  "bqo_potrs_batched")
+            x.add_(r)
+
     def solve(self, Bt):
         """Sigma_s^-1 applied to Bt[S][m][n] in place."""
         eng = self.eng
         self.factorize()
         m = int(Bt.shape[1])
+        ill = self.ill_conditioned()
+        rhs = {int(s): Bt[s].clone() for s in ill}
         check(eng.lib.bqo_potrs_batched(ptr(self.L), eng.n, self.S, ptr(Bt), m, _stream()),
               "bqo_potrs_batched")
+        for s, b0 in rhs.items():
+            self._refine(s, b0, Bt[s])
         return Bt
+
+    def refined_alpha(self):
+        """alpha with the refinement applied where `ill_conditioned` says so (in place, once)."""
+        self.factorize()
+        if not self.__dict__.get("_alpha_refined"):
+            eng = self.eng
+            for s in self.ill_conditioned():
+                s = int(s)
+                rhs = (eng.y - self.theta[s, 1]).reshape(1, eng.n)
+                self._refine(s, rhs, self.alpha[s].reshape(1, eng.n))
+            self._alpha_refined = True
+        return self.alpha
 
     def log_likelihood(self):
         eng = self.eng
@@ -398,6 +467,7 @@ class HyperBatch(object):
     def posterior(self, P, var=True, grad=False):
         eng = self.eng
         self.factorize()
+        self.refined_alpha()
         d = eng.desc
         P = eng.to_device(P).reshape(-1, d.dim)
         m = int(P.shape[0])
@@ -457,6 +527,7 @@ class BQEngine(object):
                                                       ptr(self.weights), ptr(self.qt), _stream()),
                   "bqo_task_quadrature_weights")
         self.alpha_q = eng.empty(hb.S, eng.n)
+        hb.refined_alpha()
         check(eng.lib.bqo_weight_alpha(C.byref(d), ptr(hb.alpha), ptr(self.qt), ptr(hb.tid), hb.S,
                                        eng.n, ptr(self.alpha_q), _stream()), "bqo_weight_alpha")
         if self.dw > 0:
@@ -607,9 +678,7 @@ class BQEngine(object):
         check(eng.lib.bqo_cross_cov_batched(
             C.byref(d), ptr(hb.hyp), hb.S, ptr(hb.Xs), ptr(hb.tid), eng.n, ptr(ub.cand), Cn, 1,
             ptr(ub.G), None, _stream()), "bqo_cross_cov_batched")
-        ub.R = ub.G.clone()
-        check(eng.lib.bqo_potrs_batched(ptr(hb.L), eng.n, hb.S, ptr(ub.R), Cn * rows, _stream()),
-              "bqo_potrs_batched")
+        ub.R = hb.solve(ub.G.clone())
         ub.den = eng.empty(hb.S, Cn)
         ub.beta4 = eng.empty(hb.S, Cn, d.dim_m)
         check(eng.lib.bqo_candidate_setup_batched(

@@ -25,10 +25,14 @@ __global__ void k(double* out, const double* in, int iters) {
             if (MODE == 3) x[c] = x[c] * y[c];                    // DMUL
             if (MODE == 4) x[c] = x[c] + y[c];                    // DADD
             if (MODE == 5 || MODE == 6 || MODE == 7) x[c] = fma(x[c], x[c], z[c]);
+            // accumulator forms: does the operand-reuse cache hide the third register read?
+            if (MODE == 8) x[c] = fma(y[c], z[0], x[c]);        // one multiplicand shared by all chains
+            if (MODE == 9) x[c] = fma(y[c], z[c >> 1], x[c]);   // shared by pairs (E1 += u e; H += u2 e)
+            if (MODE == 10) x[c] = fma(y[c], z[c], x[c]);       // accumulator, three distinct registers
         }
         // MODE 5/6/7: CH two-register DFMAs followed by CH/2CH/4CH independent integer ops: does a
         // non-FP64 instruction issue "for free" in the second cycle of an FP64 instruction?
-        if (MODE >= 5) {
+        if (MODE >= 5 && MODE <= 7) {
             const int reps = (MODE == 5) ? 1 : (MODE == 6 ? 2 : 4);
 #pragma unroll
             for (int r = 0; r < reps; ++r)
@@ -100,6 +104,10 @@ int main() {
     run<8, 2>(16, out, in, sms);
     run<8, 3>(16, out, in, sms);
     run<8, 4>(16, out, in, sms);
+    printf("accumulator forms at 16 warps/SM x 8 chains (8: one shared multiplicand, 9: shared by pairs, 10: all distinct):\n");
+    run<8, 8>(16, out, in, sms);
+    run<8, 9>(16, out, in, sms);
+    run<8, 10>(16, out, in, sms);
     printf("mixing: 8 two-register DFMAs + {2,4,8 x (SHF,LOP3,IADD)} integer ops per chain, 16 warps/SM\n");
     run<8, 1>(16, out, in, sms);
     run<8, 5>(16, out, in, sms);

@@ -186,3 +186,39 @@ def test_gpu_chosen_task_index_is_the_reference_one(golden, name):
         assert int(task) == int(g["chosen_task"][i])
         assert_close(value, g["chosen_task_value"][i], rtol=max(1e-8, tol), atol=1e-300,
                      what="chosen task value")
+
+
+@pytest.mark.gpu
+def test_gpu_refined_solves_at_the_ill_conditioned_vector(golden):
+    """C1's first theta (the reference's own test vector) has cond(Sigma) = 7e9.  The engine's
+    blocked solves multiply by inverted diagonal blocks, so there it refines against the
+    re-assembled Sigma (HyperBatch.solve): the result must be as close to a longdouble-refined
+    solution as LAPACK's backward-stable solve is (the reference's path), not cond * 1e-12 away."""
+    import scipy.linalg as sl
+    import torch
+    g = golden("config_c1")
+    spec, _, _ = oracle_from_golden(g)
+    gp, bq, _ = _models(g)
+    th = g["thetas"][0]
+    cov = spec.cov(th[2:], g["points"]) + th[0] * np.eye(len(g["evaluations"]))
+    assert np.linalg.cond(cov) > 1e9
+    hb = gp.hyper_batch(np.asarray([th]))
+    assert list(hb.ill_conditioned()) == [0]
+    rng = np.random.RandomState(5)
+    rhs = np.vstack([g["gamma"][0, 0], rng.randn(3, cov.shape[0])])
+    x = hb.solve(hb.eng.to_device(rhs[None]).clone())[0].cpu().numpy()
+    L = np.linalg.cholesky(cov)
+    covl = cov.astype(np.longdouble)
+    for i in range(rhs.shape[0]):
+        ref64 = sl.cho_solve((L, True), rhs[i])
+        xl = ref64.astype(np.longdouble)
+        for _ in range(6):
+            r = rhs[i].astype(np.longdouble) - covl @ xl
+            xl = xl + sl.cho_solve((L, True), np.asarray(r, dtype=float)).astype(np.longdouble)
+        scale = float(np.max(np.abs(xl)))
+        err_dev = float(np.max(np.abs(x[i] - xl))) / scale
+        err_lapack = float(np.max(np.abs(ref64 - xl))) / scale
+        assert err_dev <= max(4.0 * err_lapack, 1e-9), (i, err_dev, err_lapack)
+    # the well-conditioned second vector is not touched by the refinement
+    hb2 = gp.hyper_batch(np.asarray([g["thetas"][1]]))
+    assert len(hb2.ill_conditioned()) == 0
