@@ -43,6 +43,7 @@ N_CAND_TOTAL = 10000
 CAND_PER_STEP = int(os.environ.get("BQO_CAND_PER_STEP", "111"))
 N_RESTARTS_MC, MAXITER_MC, FACTR_MC = 5, 10, 1e12  # bgo() defaults, sbo/services/bgo.py:43-44
 Z_PER_CTA = int(os.environ.get("BQO_Z_PER_CTA", "100"))
+ZS_SEED = 3
 
 
 def make_workload(seed_shift=0):
@@ -56,12 +57,17 @@ def make_workload(seed_shift=0):
     base = np.array([1e-4, 0.0] + DX * [0.3] + DW * [2.0] + [1.0])
     thetas = base[None, :] * (1.0 + 0.05 * r2.normal(0, 1, (N_HYPER, base.size)))
     thetas[:, 1] = 0.05 * r2.normal(0, 1, N_HYPER)
-    zs = np.random.RandomState(3).normal(0, 1, N_Z)
+    # Z samples and start points exactly as the public API draws them after np.random.seed(ZS_SEED)
+    # (SBO.generate_samples_starting_points_evaluate_mc: Z first, then one uniform vector per
+    # coordinate, services/domain.py): the end-to-end leg re-seeds before every step, so both legs
+    # maximise from the same starts against the same Z
+    r3 = np.random.RandomState(ZS_SEED)
+    zs = r3.normal(0, 1, N_Z)
+    starts = np.array([r3.uniform(0, 1, N_RESTARTS_MC + 1) for _ in range(DX)]).T.copy()
     wsets = np.random.RandomState(4).gamma(2.0, 1.0, (N_WSETS, M_W, DW))
     r5 = np.random.RandomState(5 + seed_shift)
     cands = np.concatenate([r5.uniform(0, 1, (N_CAND_TOTAL, DX)),
                             r5.gamma(2.0, 1.0, (N_CAND_TOTAL, DW))], 1)
-    starts = np.random.RandomState(6).uniform(0, 1, (N_RESTARTS_MC + 1, DX))
     return dict(pts=pts, y=y, thetas=thetas, zs=zs, wsets=wsets, cands=cands, starts=starts,
                 lower=np.zeros(DX), upper=np.ones(DX))
 
@@ -76,15 +82,17 @@ def f_eval_flops():
 def issue_model(evals_per_launch, kernel_ms, clocks, dfma_peak_tflops=None):
     """What the kernel EXECUTES, next to the algorithmic count above: SASS instruction counts of the
     inner loop (one warp iteration = one training point x 10 W samples for the 32 evaluations held
-    by the lanes; profiles/r01_inner_maximize_final.md) priced with
+    by the lanes; profiles/r02_inner_maximize.md) priced with
     the measured issue costs (FP64 2 cycles, 3 with three register sources, others 1), against
     the cycles the launch took at the sampled SM clock."""
-    fp64, fp64_3src, other = 182.0, 35.3, 131.7
+    fp64, fp64_3src, other = 182.0, 35.3, 111.7
     cyc = 2.0 * fp64 + fp64_3src + other
     out = {"fp64_instr_per_point": fp64, "other_instr_per_point": other,
            "issue_cycles_per_point": cyc, "fp64_3src_instr_per_point": fp64_3src,
-           "source": "executed-instruction counts of the ncu capture in "
-           "profiles/r01_inner_maximize_final.md; 148 SMs x 4 sub-partitions"}
+           "source": "executed-instruction counts of the ncu captures in "
+           "profiles/r02_inner_maximize.md (293.7 warp instructions per point, 182 of them FP64; "
+           "the three-source share from profiles/r01_inner_maximize_final.md); "
+           "148 SMs x 4 sub-partitions"}
     mhz = (clocks or {}).get("sm_mhz")
     if mhz:
         need = evals_per_launch / 32.0 * N_TRAIN * cyc / (148 * 4)
@@ -364,6 +372,9 @@ def workload_config():
                        "once with the engine, outside the timed steps like the factors); roofline "
                        "flops keep SURVEY 8d's count, which includes that part",
         "z_per_cta": Z_PER_CTA,
+        "e2e_inputs": "the same candidate batches, Z samples and start points as the device-resident "
+                      "steps: the API draws Z and the starts itself, np.random is re-seeded (%d) "
+                      "before every end-to-end step and the workload uses those draws" % ZS_SEED,
     }
 
 
@@ -647,6 +658,7 @@ def run_gpu(args):
         host_cands = wl["cands"]
 
         def e2e_step(i):
+            np.random.seed(ZS_SEED)   # the API draws Z and the starts itself: same draws as wl
             lo = rank * per_rank + (i * CAND_PER_STEP) % max(1, per_rank - CAND_PER_STEP)
             r = sbo.evaluate_mc_bayesian_candidate_points_no_restarts(
                 host_cands[lo:lo + CAND_PER_STEP], N_HYPER, N_Z, n_restarts=N_RESTARTS_MC,
@@ -661,7 +673,7 @@ def run_gpu(args):
         w0 = time.perf_counter()
         n_e2e = max(1, args.steps)
         for i in range(n_e2e):
-            r = e2e_step(10 + i)
+            r = e2e_step(args.warmup + i)   # the candidate batches of the device-resident steps
         torch.cuda.synchronize()
         dt = time.perf_counter() - w0
         if world > 1:
