@@ -119,60 +119,121 @@ extern "C" int bqo_scale_points(const bqo_kernel_desc* desc, const double* hyp, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// K[s][i][j].  32x32 tiles, 4 rows per thread; column reads of the SoA Xs are coalesced, row
-// reads broadcast.  The Matern factor goes through the fast evaluation (HBM-write bound at
-// n = 2048: 671 MB per 20 hyper-samples; with libm exp/sqrt the kernel was instruction bound at
-// 1.6 TB/s); the diagonal is exactly 1 like the reference's k(x, x).
-template <int DM>
-__global__ void assemble_kernel(bqo_kernel_desc d, const double* __restrict__ hyp, int64_t stride,
-                                const double* __restrict__ Xs, const int32_t* __restrict__ tid,
-                                int n, const double* __restrict__ noise_obs, int add_noise,
-                                const double* __restrict__ extra_diag, double* __restrict__ K,
-                                int lower_only) {
-    // lower_only (the factorisation's input): only the 64 x 64 tiles on or below the diagonal are
-    // produced -- the Cholesky kernels read nothing else and zero the strict upper triangle
-    if (lower_only && (blockIdx.x >> 1) > (blockIdx.y >> 1)) return;
-    int j = blockIdx.x * 32 + threadIdx.x;
-    int i0 = blockIdx.y * 32 + threadIdx.y * 4;
-    int s = blockIdx.z;
-    if (j >= n) return;
+// K[s][i][j] in 64 x 64 tiles, one CTA of 8 warps per tile ON OR BELOW the diagonal (the matrix is
+// symmetric bit for bit: (x_i - x_j)^2 and the task covariance do not depend on the order).
+//   * the 64 row points sit in shared memory (broadcast loads), each lane keeps its two column
+//     points in registers and pushes the two kernel values of a row through the fast Matern
+//     evaluation together (independent chains);
+//   * a warp writes two 256-byte row segments per row; for the full matrix (`lower_only` = 0) the
+//     tile also goes to shared memory and is written once more transposed, as the mirror tile.
+// The kernel is FP64-issue bound, not HBM bound: ~30 FP64 + ~15 other instructions per element
+// (the 32 x 32 version it replaces executed 33 + 101: six global loads with 64-bit address
+// arithmetic per element, and computed both halves of the matrix).  The diagonal is exactly 1
+// like the reference's k(x, x).
+#define ASM_T 64
+template <int DM, bool TASKS>
+__global__ void __launch_bounds__(256)
+assemble_kernel(bqo_kernel_desc d, const double* __restrict__ hyp, int64_t stride,
+                const double* __restrict__ Xs, const int32_t* __restrict__ tid, int n,
+                const double* __restrict__ noise_obs, int add_noise,
+                const double* __restrict__ extra_diag, double* __restrict__ K, int lower_only) {
+    constexpr int DMS = (DM > 0) ? DM : BQO_MAX_DIM;
+    __shared__ double s_row[ASM_T][DMS];
+    __shared__ int s_tid[ASM_T];
+    __shared__ double s_tile[ASM_T][ASM_T + 1];
+    // packed enumeration of the lower-triangular tiles: blockIdx.x = ti (ti + 1) / 2 + tj
+    const int t = blockIdx.x;
+    int ti = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+    while (ti * (ti + 1) / 2 > t) --ti;
+    const int tj = t - ti * (ti + 1) / 2;
+    const int s = blockIdx.y;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const double* h = hyp + (int64_t)s * stride;
     const double* xs = Xs + (int64_t)s * d.dim_m * n;
     const int dm = (DM > 0) ? DM : d.dim_m;
-    double xj[(DM > 0) ? DM : BQO_MAX_DIM];
+    constexpr bool tasks = TASKS;   // d.kind == BQO_KIND_PRODUCT_TASKS, resolved at compile time
+    for (int e = threadIdx.x; e < ASM_T * dm; e += blockDim.x) {
+        const int l = e / ASM_T, r = e - l * ASM_T;
+        const int gi = ti * ASM_T + r;
+        s_row[r][l] = (gi < n) ? xs[(int64_t)l * n + gi] : 0.0;
+    }
+    if (tasks && threadIdx.x < ASM_T) {
+        const int gi = ti * ASM_T + threadIdx.x;
+        s_tid[threadIdx.x] = (gi < n) ? tid[gi] : 0;
+    }
+    const int j0 = tj * ASM_T + lane, j1 = j0 + 32;
+    double xj0[DMS], xj1[DMS];
 #pragma unroll
-    for (int l = 0; l < dm; ++l) xj[l] = xs[(int64_t)l * n + j];
-    const double sigma2 = h[BQO_H_SIGMA2];
-    const int tj = (d.kind == BQO_KIND_PRODUCT_TASKS) ? tid[j] : 0;
+    for (int l = 0; l < DMS; ++l) {
+        xj0[l] = (l < dm && j0 < n) ? xs[(int64_t)l * n + j0] : 0.0;
+        xj1[l] = (l < dm && j1 < n) ? xs[(int64_t)l * n + j1] : 0.0;
+    }
+    const int tj0 = (tasks && j0 < n) ? tid[j0] : 0, tj1 = (tasks && j1 < n) ? tid[j1] : 0;
+    // ScaledKernel's sigma^2 as a plain factor (1 for the other kinds): no select per element
+    const double kscale = (d.kind == BQO_KIND_SCALED_MATERN52) ? h[BQO_H_SIGMA2] : 1.0;
+    const bool mirror = !lower_only && ti != tj;
     double* Ks = K + (int64_t)s * n * n;
+    __syncthreads();
+    const int r0 = w * (ASM_T / 8);
+    double* out = Ks + (int64_t)(ti * ASM_T + r0) * n + j0;   // this warp's first row, column j0
+    const bool in0 = j0 < n, in1 = j1 < n;
+    for (int ii = 0; ii < ASM_T / 8; ++ii, out += n) {
+        const int r = r0 + ii;
+        const int i = ti * ASM_T + r;
+        if (i >= n) break;  // warp-uniform
+        double u2v[2] = {0.0, 0.0}, ev[2], uv[2], k[2];
 #pragma unroll
-    for (int ii = 0; ii < 4; ++ii) {
-        int i = i0 + ii;
-        if (i >= n) break;
-        double r2 = 0.0;
-#pragma unroll
-        for (int l = 0; l < dm; ++l) {
-            double df = xs[(int64_t)l * n + i] - xj[l];
-            r2 = fma(df, df, r2);
-        }
-        double k = 1.0;
-        if (i != j) {
-            double u2v[1], ev[1], uv[1];
-            u2v[0] = fma(r2, BQO_PRESCALE * BQO_PRESCALE, 1e-300);
-            bqo_matern52_q_v<1>(u2v, GlobalExpTab(), ev, uv);
-            // k = (1 + u c + u2 c^2/3) e with c = ln2/N
-            k = fma(u2v[0], BQO_H_TO_K, fma(uv[0], BQO_LN2_N, 1.0)) * ev[0];
-        }
-        if (d.kind == BQO_KIND_SCALED_MATERN52) k *= sigma2;
-        if (d.kind == BQO_KIND_PRODUCT_TASKS) k *= bqo_task_cov(h, d.n_tasks, tid[i], tj);
-        if (i == j) {
-            if (add_noise) {
-                if (noise_obs) k += noise_obs[i];
-                k += h[BQO_H_VARNOISE];
+        for (int l = 0; l < DMS; ++l) {
+            if (l < dm) {
+                const double xi = s_row[r][l];
+                const double d0 = xi - xj0[l], d1 = xi - xj1[l];
+                u2v[0] = fma(d0, d0, u2v[0]);
+                u2v[1] = fma(d1, d1, u2v[1]);
             }
-            if (extra_diag) k += extra_diag[s];
         }
-        Ks[(int64_t)i * n + j] = k;
+        u2v[0] = fma(u2v[0], BQO_PRESCALE * BQO_PRESCALE, 1e-300);
+        u2v[1] = fma(u2v[1], BQO_PRESCALE * BQO_PRESCALE, 1e-300);
+        bqo_matern52_q_v<2>(u2v, GlobalExpTab(), ev, uv);
+        // k = (1 + u c + u2 c^2/3) e with c = ln2/N
+        k[0] = fma(u2v[0], BQO_H_TO_K, fma(uv[0], BQO_LN2_N, 1.0)) * ev[0] * kscale;
+        k[1] = fma(u2v[1], BQO_H_TO_K, fma(uv[1], BQO_LN2_N, 1.0)) * ev[1] * kscale;
+        if (tasks) {
+            const int tr = s_tid[r];
+            k[0] *= bqo_task_cov(h, d.n_tasks, tr, tj0);
+            k[1] *= bqo_task_cov(h, d.n_tasks, tr, tj1);
+        }
+        if (ti == tj && (r == lane || r == lane + 32)) {
+            // the diagonal entry of this row (one lane of a diagonal tile): k(x, x) = 1 exactly
+            double kd = kscale;
+            if (tasks) kd *= bqo_task_cov(h, d.n_tasks, s_tid[r], s_tid[r]);
+            if (add_noise) {
+                if (noise_obs) kd += noise_obs[i];
+                kd += h[BQO_H_VARNOISE];
+            }
+            if (extra_diag) kd += extra_diag[s];
+            if (r == lane) k[0] = kd; else k[1] = kd;
+        }
+        if (in0) out[0] = k[0];
+        if (in1) out[32] = k[1];
+        if (mirror) {
+            s_tile[r][lane] = k[0];
+            s_tile[r][lane + 32] = k[1];
+        }
+    }
+    if (mirror) {
+        __syncthreads();
+        for (int cc = 0; cc < ASM_T / 8; ++cc) {
+            const int c = w * (ASM_T / 8) + cc;
+            const int gj = tj * ASM_T + c;
+            if (gj >= n) break;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int r = lane + 32 * hh;
+                const int gi = ti * ASM_T + r;
+                if (gi < n) Ks[(int64_t)gj * n + gi] = s_tile[r][c];
+            }
+        }
     }
 }
 
@@ -200,14 +261,21 @@ int bqo_internal_assemble(const bqo_kernel_desc* desc, const double* hyp, int32_
     BQO_CHECK_ARG(desc->kind != BQO_KIND_PRODUCT_TASKS || tid != nullptr, 5);
     BQO_CHECK_ARG(n > 0, 6);
     BQO_CHECK_ARG(K != nullptr, 10);
-    dim3 block(32, 8);
-    dim3 grid((n + 31) / 32, (n + 31) / 32, S);
+    const int nt = (n + ASM_T - 1) / ASM_T;
+    dim3 block(256);
+    dim3 grid(nt * (nt + 1) / 2, S);
     int64_t st = bqo_hyper_stride_impl(*desc);
     cudaStream_t cs = (cudaStream_t)stream;
     bqo_ensure_global_exp_table(cs);
 #define LAUNCH_ASM(DMV)                                                                          \
-    BQO_L, assemble_kernel<DMV><<<grid, block, 0, cs>>>(*desc, hyp, st, Xs, tid, n, noise_obs,          \
-                                                 add_noise, extra_diag, K, lower_only)
+    do {                                                                                         \
+        if (desc->kind == BQO_KIND_PRODUCT_TASKS)                                                \
+            BQO_L, assemble_kernel<DMV, true><<<grid, block, 0, cs>>>(                           \
+                *desc, hyp, st, Xs, tid, n, noise_obs, add_noise, extra_diag, K, lower_only);    \
+        else                                                                                     \
+            BQO_L, assemble_kernel<DMV, false><<<grid, block, 0, cs>>>(                          \
+                *desc, hyp, st, Xs, tid, n, noise_obs, add_noise, extra_diag, K, lower_only);    \
+    } while (0)
     switch (desc->dim_m) {
         case 1: LAUNCH_ASM(1); break;
         case 2: LAUNCH_ASM(2); break;

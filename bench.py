@@ -57,19 +57,21 @@ def make_workload(seed_shift=0):
     base = np.array([1e-4, 0.0] + DX * [0.3] + DW * [2.0] + [1.0])
     thetas = base[None, :] * (1.0 + 0.05 * r2.normal(0, 1, (N_HYPER, base.size)))
     thetas[:, 1] = 0.05 * r2.normal(0, 1, N_HYPER)
-    # Z samples and start points exactly as the public API draws them after np.random.seed(ZS_SEED)
+    # Z samples and `starts_api` exactly as the public API draws them after np.random.seed(ZS_SEED)
     # (SBO.generate_samples_starting_points_evaluate_mc: Z first, then one uniform vector per
-    # coordinate, services/domain.py): the end-to-end leg re-seeds before every step, so both legs
-    # maximise from the same starts against the same Z
+    # coordinate, services/domain.py): the end-to-end leg re-seeds before every step
     r3 = np.random.RandomState(ZS_SEED)
     zs = r3.normal(0, 1, N_Z)
-    starts = np.array([r3.uniform(0, 1, N_RESTARTS_MC + 1) for _ in range(DX)]).T.copy()
+    starts_api = np.array([r3.uniform(0, 1, N_RESTARTS_MC + 1) for _ in range(DX)]).T.copy()
+    # the device-resident leg keeps round 1's start points, so that `value` stays comparable
+    # between rounds; `e2e.device_resident_same_inputs` times it on the API's draws as well
+    starts = np.random.RandomState(6).uniform(0, 1, (N_RESTARTS_MC + 1, DX))
     wsets = np.random.RandomState(4).gamma(2.0, 1.0, (N_WSETS, M_W, DW))
     r5 = np.random.RandomState(5 + seed_shift)
     cands = np.concatenate([r5.uniform(0, 1, (N_CAND_TOTAL, DX)),
                             r5.gamma(2.0, 1.0, (N_CAND_TOTAL, DW))], 1)
     return dict(pts=pts, y=y, thetas=thetas, zs=zs, wsets=wsets, cands=cands, starts=starts,
-                lower=np.zeros(DX), upper=np.ones(DX))
+                starts_api=starts_api, lower=np.zeros(DX), upper=np.ones(DX))
 
 
 def f_eval_flops():
@@ -372,9 +374,11 @@ def workload_config():
                        "once with the engine, outside the timed steps like the factors); roofline "
                        "flops keep SURVEY 8d's count, which includes that part",
         "z_per_cta": Z_PER_CTA,
-        "e2e_inputs": "the same candidate batches, Z samples and start points as the device-resident "
-                      "steps: the API draws Z and the starts itself, np.random is re-seeded (%d) "
-                      "before every end-to-end step and the workload uses those draws" % ZS_SEED,
+        "e2e_inputs": "same candidate batches and Z samples as the device-resident steps; the API "
+                      "draws Z and its start points itself (np.random re-seeded with %d before every "
+                      "end-to-end step), so its start points differ from the fixed ones of `value`: "
+                      "e2e.device_resident_same_inputs is the device-resident step on the API's own "
+                      "draws" % ZS_SEED,
     }
 
 
@@ -684,6 +688,28 @@ def run_gpu(args):
         d2h = CAND_PER_STEP * 8 + CAND_PER_STEP * (DX + DW) * 8
         e2e = {"value": world * units_per_step * n_e2e / dt, "unit": "units/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_e2e}
+        # the device-resident step on exactly the inputs the API drew (same Z, the API's start
+        # points, same candidate batches): what the end-to-end number is to be compared with
+        starts_dev = starts
+        starts = eng.to_device(wl["starts_api"])
+        step(args.warmup, False)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        cnt2 = [step(args.warmup + i, True) for i in range(n_e2e)]
+        s1.record()
+        torch.cuda.synchronize()
+        ms2 = s0.elapsed_time(s1)
+        if world > 1:
+            t = torch.tensor([ms2], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms2 = float(t.item())
+        starts = starts_dev
+        e2e["device_resident_same_inputs"] = world * units_per_step * n_e2e / (ms2 * 1e-3)
+        e2e["evals_per_unit_per_z_same_inputs"] = float(
+            sum(int(c.sum().item()) for c in cnt2)) / n_e2e / (units_per_step * N_Z)
 
     c5 = None
     if not args.profile and not args.no_c5:
