@@ -227,13 +227,13 @@ class SBO(object):
         return (rank, ws) if self.distributed else (0, 1)
 
     def _evaluate_candidates(self, parameters, candidate_points, samples, start, compute_max_mean,
-                             compute_gradient, hyper_indices=None, **opt):
+                             compute_gradient, hyper_indices=None, local_only=False, **opt):
         """value [C] and gradient [C][dim_m] (device tensors) of the Monte-Carlo acquisition for
         the hyper-samples `parameters` (all of them, or those at `hyper_indices`).  Single GPU: one
         pass over every hyper-sample.  Distributed: this rank's slice of `parameters` only, then
         one all_gather + rank-ordered sum of the partial sums (bit-identical on all ranks)."""
         from .. import distributed as D
-        rank, ws = self._world()
+        rank, ws = (0, 1) if local_only else self._world()
         S = len(parameters)
         lo, hi = D.shard_range(S, rank, ws) if ws > 1 else (0, S)
         if ws > 1 and hi == lo:
@@ -386,7 +386,7 @@ class SBO(object):
                  start_ei=True, n_samples_parameters=0, start_new_chain=True,
                  compute_max_mean_bayesian=False, maxepoch=10, default_n_samples=None,
                  default_n_samples_parameters=None, default_restarts_mc=None, method_opt_mc=None,
-                 **opt_params_mc):
+                 advance_chain=False, **opt_params_mc):
         """:1571-1950 -> {'solution', 'optimal_value', 'gradient'} of the best restart.
 
         Monte-Carlo / Bayesian branch on the device.  Every SGD epoch is ONE pass of the hot path:
@@ -395,7 +395,15 @@ class SBO(object):
         advances the chain by one slice step per gradient, sbo.py:1129) times n_samples fresh
         Z ~ N(0,1), i.e. N = n_samples * n_samples_parameters single-sample gradients
         (sbo.py:1845) averaged, followed by the reference's Adam step, box projection and stop
-        rule (sbo/lib/stochastic_gradient_descent.py:83-130) for every restart at once."""
+        rule (sbo/lib/stochastic_gradient_descent.py:83-130) for every restart at once (a restart
+        that has met its stop rule is frozen; the loop ends when all have).
+
+        advance_chain=True restores the reference's source of hyper-samples: every epoch advances
+        the slice-sampling chain by n_samples_parameters new samples (gp.sample_parameters, as
+        grad_voi_sgd does at sbo.py:1129) and takes the gradient at those, at the price of the
+        sampler's sweeps and one factorisation per new sample and epoch.  The default draws from
+        the resident posterior samples -- the set the final scoring of the end points averages
+        over anyway (:1884-1900); tests/test_gpu_facade.py compares the two."""
         import torch
         from .. import _cabi
         from .ei import EI
@@ -471,12 +479,21 @@ class SBO(object):
         n_zs = max(1, n_samples)
         bx = self._bounds_x()
         for t in range(1, maxepoch + 1):
-            ks = np.random.choice(len(parameters), n_k, replace=False)
+            fresh = None
+            if advance_chain and n_samples_parameters > 0:
+                fresh = [np.asarray(p, dtype=float) for p in gp.sample_parameters(n_k)[-n_k:]]
+            else:
+                ks = np.random.choice(len(parameters), n_k, replace=False)
             zs = np.random.normal(0, 1, n_zs)
             starts_x = np.array(DomainService.get_points_domain(
                 default_restarts_mc + 1, bx, type_bounds=len(bx) * [0]))
-            _, grad_t = self._evaluate_candidates(parameters, pts, zs, starts_x, False, True,
-                                                  hyper_indices=ks, **opt_params_mc)
+            if fresh is not None:
+                # every rank advances the same chain (same seeds) and scores the new samples itself
+                _, grad_t = self._evaluate_candidates(fresh, pts, zs, starts_x, False, True,
+                                                      local_only=True, **opt_params_mc)
+            else:
+                _, grad_t = self._evaluate_candidates(parameters, pts, zs, starts_x, False, True,
+                                                      hyper_indices=ks, **opt_params_mc)
             g = torch.zeros(R, dim, dtype=torch.float64, device=eng.device)
             g[:, :dim_m] = -grad_t                        # maximise: descend on -acquisition
             bad = torch.isnan(g).any(dim=1)

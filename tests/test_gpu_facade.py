@@ -669,3 +669,34 @@ def test_sbo_optimize_discretised_branch(golden, name):
     assert_close(res["optimal_value"], best, rtol=1e-5, atol=1e-9, what="discretised SBO optimum")
     # the returned value is the discretised SBO at the returned solution
     assert_close(sbo.evaluate(res["solution"].reshape(1, -1)), res["optimal_value"], rtol=1e-12)
+
+
+def test_sbo_optimize_resident_samples_against_advancing_chain():
+    """VERDICT r1 weak point 12: the SGD of SBO.optimize draws its hyper-samples from the resident
+    posterior samples; advance_chain=True is the reference's source (one new slice sample per
+    gradient, sbo.py:1129).  Same seeds and starts, one common scorer: the default must not be worse
+    (profiles/r02_sgd_hyper_source.md has the 32-seed run)."""
+    import sys
+    sys.path.insert(0, "tests/microbench")
+    import sgd_hyper_source as m
+    td, T = m.problem()
+    gp, bq, sbo = m.model(td, T, 11)
+    gp.sample_parameters(8, random_seed=5)
+    n0 = len(gp.samples_parameters)
+    res = sbo.optimize(random_seed=3, monte_carlo=True, n_samples=2, n_restarts_mc=3, n_restarts=4,
+                       n_samples_parameters=2, start_new_chain=False, maxepoch=4,
+                       default_n_samples=6, default_n_samples_parameters=8, start_ei=False,
+                       factr=1e12, maxiter=10, advance_chain=True)
+    grown = len(gp.samples_parameters) - n0
+    assert grown >= 2 and grown % 2 == 0 and grown <= 2 * 4      # two new samples per epoch run
+    x = res["solution"]
+    assert 0.0 <= x[0] <= 1.0 and 0.0 <= x[1] <= 1.0 and int(x[2]) in range(T)
+    out = m.main(seeds=tuple(range(1, 9)), maxepoch=10)
+    a = np.array([r["resident"]["score"] for r in out["rows"]])
+    b = np.array([r["chain"]["score"] for r in out["rows"]])
+    for r in out["rows"]:
+        for k in ("resident", "chain"):
+            xs = r[k]["x"]
+            assert 0.0 <= xs[0] <= 1.0 and 0.0 <= xs[1] <= 1.0 and int(xs[2]) in range(T)
+    se = (a - b).std(ddof=1) / np.sqrt(len(a))
+    assert a.mean() >= b.mean() - 2.0 * se, (a.mean(), b.mean(), se)
