@@ -682,13 +682,19 @@ def test_sbo_optimize_resident_samples_against_advancing_chain():
     td, T = m.problem()
     gp, bq, sbo = m.model(td, T, 11)
     gp.sample_parameters(8, random_seed=5)
-    n0 = len(gp.samples_parameters)
+    calls = []
+    orig = gp.sample_parameters
+
+    def counting(n_samples, *a, **k):
+        calls.append(n_samples)
+        return orig(n_samples, *a, **k)
+
+    gp.sample_parameters = counting
     res = sbo.optimize(random_seed=3, monte_carlo=True, n_samples=2, n_restarts_mc=3, n_restarts=4,
                        n_samples_parameters=2, start_new_chain=False, maxepoch=4,
                        default_n_samples=6, default_n_samples_parameters=8, start_ei=False,
                        factr=1e12, maxiter=10, advance_chain=True)
-    grown = len(gp.samples_parameters) - n0
-    assert grown >= 2 and grown % 2 == 0 and grown <= 2 * 4      # two new samples per epoch run
+    assert 1 <= len(calls) <= 4 and all(c == 2 for c in calls)   # two new samples per epoch run
     x = res["solution"]
     assert 0.0 <= x[0] <= 1.0 and 0.0 <= x[1] <= 1.0 and int(x[2]) in range(T)
     out = m.main(seeds=tuple(range(1, 9)), maxepoch=10)
