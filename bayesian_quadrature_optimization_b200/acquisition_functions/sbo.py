@@ -359,9 +359,12 @@ class SBO(object):
         tasks when W is finite.  Same numpy RNG calls as the reference."""
         bq = self.bq
         bounds = bq.bounds
-        new_points = np.array(DomainService.get_points_domain(100, bounds, type_bounds=bq.type_bounds))
-        current = np.array(bq.gp.data['points'])
         finite = bq.separate_tasks and not bq.task_continue
+        # :1737-1740: the simplex constraint (citi_bike_mt) applies to the non-finite branch only
+        new_points = np.array(DomainService.get_points_domain(
+            100, bounds, type_bounds=bq.type_bounds,
+            simplex_domain=None if finite else bq.simplex_domain))
+        current = np.array(bq.gp.data['points'])
         if finite:
             current = current[:, 0:-1]
         d = new_points[:, None, :] - current[None, :, :new_points.shape[1]]
@@ -516,6 +519,13 @@ class SBO(object):
                 _cabi.ptr(pts), _cabi.ptr(g.contiguous()), _cabi.ptr(m0), _cabi.ptr(v0),
                 _cabi.ptr(active), _cabi.ptr(lo_d), _cabi.ptr(up_d), R, dim, t, 0.1, 0.9, 0.999, 1e-8,
                 torch.cuda.current_stream().cuda_stream), "bqo_adam_step_batched")
+            if bq.simplex_domain is not None and dim > 2:
+                # stochastic_gradient_descent.py:112-114: points whose coordinates from the third
+                # on sum to more than the simplex bound are scaled back onto it
+                tail = pts[:, 2:]
+                tot = tail.sum(dim=1, keepdim=True)
+                over = tot > float(bq.simplex_domain)
+                pts[:, 2:] = torch.where(over, tail * (float(bq.simplex_domain) / tot), tail)
             if int(active.sum().item()) == 0:
                 break
         candidate_points = pts.cpu().numpy()

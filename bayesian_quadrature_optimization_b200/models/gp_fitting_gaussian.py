@@ -698,15 +698,15 @@ class GPFittingGaussian(object):
             self.samples_parameters += kept
             return kept
         if self.n_chains > 1 and float(n_samples).is_integer() and n_samples >= self.n_chains:
-            # every chain starts at the current state, decorrelates over its first (thinning + 1)
-            # sweeps and keeps ceil(n / chains) points; seeds come from the global stream so that
+            # every chain starts at the current state, runs (thinning + 1) sweeps before its first
+            # kept point and keeps ceil(n / chains) points; seeds come from the global stream so that
             # np.random.seed still fixes the run
             per = -(-int(n_samples) // self.n_chains)
             seed = int(np.random.randint(0, 2 ** 31 - 1 - self.n_chains))
             n_before = len(self.samples_parameters)
             kept = self.sample_parameters_chains(per, self.n_chains, random_seed=seed,
                                                  start_points=[start_point] * self.n_chains,
-                                                 burn_in_sweeps=0)[:int(n_samples)]
+                                                 burn_in_sweeps=self.thinning + 1)[:int(n_samples)]
             self.samples_parameters = self.samples_parameters[:n_before] + kept
             return kept
         n_sweeps = int(n_samples * (self.thinning + 1))
