@@ -49,14 +49,20 @@ __device__ __forceinline__ double pp_rsqrt(double d) {
 // (first version: 8-wide blocks, 24 barriers, thread-per-element loops: 51 us per block measured
 // with bqo_potrf_profile; this one: 8 us.)
 //
-// A 32 x 32 block is factored by ONE warp with one matrix row per lane in registers: per pivot a
-// shuffle broadcasts the diagonal entry, 1/sqrt comes from MUFU.RSQ64H + two Newton steps, the
-// column is scaled and 31 - p shuffle + DFMA pairs apply it to the trailing columns (no
-// predication: the strict upper triangle collects garbage that nothing reads).  The same warp then
-// inverts the factor, lane c solving L w = e_c by forward substitution with the rows of L again
-// broadcast by shuffles (four partial sums per entry to shorten the dependent chain).
+// A 32 x 32 block is factored by ONE warp with one matrix row per lane in registers.  Per pivot
+// the lanes put their entry of the scaled column into a 32-double shared-memory line and read it
+// back with broadcast 128-bit loads (two entries per load): 31 - p DFMAs apply it to the trailing
+// columns (no predication: the strict upper triangle collects garbage that nothing reads).  The
+// same warp then inverts the factor, lane c solving L w = e_c by forward substitution with the
+// rows of L read from the stored factor by broadcast loads (four partial sums per entry to
+// shorten the dependent chain).
+// The code is straight-line and runs once per diagonal task, so it is bound by instruction fetch:
+// the first version broadcast with __shfl_sync (2 SHFL + WARPSYNC + ENDCOLLECTIVE + moves per
+// double, 6400 instructions per 32 x 32 block, 11 us); broadcasting through shared memory needs
+// half a load per entry.
+// `col`: 2 x 32 doubles of scratch (16-byte aligned), double-buffered by pivot parity.
 // Returns 0 or base + (1-based index of the first non-positive pivot); warp-uniform.
-__device__ __noinline__ int pp_chol_inv_32_warp(double* T, double* Wm, int base) {
+__device__ __noinline__ int pp_chol_inv_32_warp(double* T, double* Wm, double* col, int base) {
     const int lane = threadIdx.x & 31;
     const unsigned full = 0xffffffffu;
     double a[32];
@@ -65,7 +71,10 @@ __device__ __noinline__ int pp_chol_inv_32_warp(double* T, double* Wm, int base)
     int bad = 0;
 #pragma unroll
     for (int p = 0; p < 32; ++p) {
-        const double d = __shfl_sync(full, a[p], p);
+        double* cb = col + (p & 1) * 32;
+        if (lane == p) cb[p] = a[p];
+        __syncwarp(full);
+        const double d = cb[p];
         if (!(d > 0.0) && bad == 0) bad = base + p + 1;   // also NaN
         const double rs = pp_rsqrt(d > 0.0 ? d : 1.0);
         double lp = a[p] * rs;                              // L[lane][p] for lane > p
@@ -74,10 +83,17 @@ __device__ __noinline__ int pp_chol_inv_32_warp(double* T, double* Wm, int base)
             lp = fma(fma(-g, g, d), 0.5 * rs, g);
         }
         a[p] = lp;
+        if (p < 31) {
+            // lane > p publishes L[lane][p]; lane p's slot still holds d, which nothing reads again
+            if (lane > p) cb[lane] = lp;
+            __syncwarp(full);
+            if ((p & 1) == 0) a[p + 1] = fma(-lp, cb[p + 1], a[p + 1]);   // odd q = p + 1 first
 #pragma unroll
-        for (int q = p + 1; q < 32; ++q) {
-            const double lq = __shfl_sync(full, lp, q);    // L[q][p]
-            a[q] = fma(-lp, lq, a[q]);
+            for (int q = (p + 2) & ~1; q < 32; q += 2) {
+                const double2 l2 = *reinterpret_cast<const double2*>(cb + q);   // L[q][p], L[q+1][p]
+                a[q] = fma(-lp, l2.x, a[q]);
+                a[q + 1] = fma(-lp, l2.y, a[q + 1]);
+            }
         }
     }
     if (bad) return bad;
@@ -88,18 +104,21 @@ __device__ __noinline__ int pp_chol_inv_32_warp(double* T, double* Wm, int base)
 #pragma unroll
     for (int q = 0; q < 32; ++q)
         if (q == lane) dg = a[q];
-    const double rdg = 1.0 / dg;
+    col[lane] = 1.0 / dg;                                   // 1 / L[i][i], read back by broadcast
+    __syncwarp(full);
     double x[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
         double acc[4] = {(i == lane) ? 1.0 : 0.0, 0.0, 0.0, 0.0};
+        const double* Li = T + i * PP_LD;                   // row i of L (16-byte aligned)
 #pragma unroll
-        for (int k = 0; k < i; ++k) {
-            const double lik = __shfl_sync(full, a[k], i);  // L[i][k]
-            acc[k & 3] = fma(-lik, x[k], acc[k & 3]);       // x[k] = 0 for k < lane
+        for (int k = 0; k + 1 < i; k += 2) {
+            const double2 l2 = *reinterpret_cast<const double2*>(Li + k);   // L[i][k], L[i][k+1]
+            acc[k & 3] = fma(-l2.x, x[k], acc[k & 3]);      // x[k] = 0 for k < lane
+            acc[(k + 1) & 3] = fma(-l2.y, x[k + 1], acc[(k + 1) & 3]);
         }
-        const double rdi = __shfl_sync(full, rdg, i);
-        x[i] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) * rdi;
+        if (i & 1) acc[(i - 1) & 3] = fma(-Li[i - 1], x[i - 1], acc[(i - 1) & 3]);
+        x[i] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) * col[i];
         Wm[i * PP_LD + lane] = x[i];                        // W[i][c], zero above the diagonal
     }
     return 0;
@@ -151,6 +170,7 @@ __device__ __forceinline__ void pp_acc32_foreach(double (&acc)[2][2][2], int r0,
 //                   L22 = chol(A22), W22 = L22^-1          warp 0   | P = L21 W11   warps 1-3
 //                   W21 = -W22 P                            DMMA, 4 warps
 __device__ int pp_potrf_inv_64(double* T, double* Wm, int* flag_sm) {
+    __shared__ __align__(16) double pp_col[64];
     const int t = threadIdx.x, warp = t >> 5;
     double* T21 = T + 32 * PP_LD;
     double* T22 = T21 + 32;
@@ -158,7 +178,7 @@ __device__ int pp_potrf_inv_64(double* T, double* Wm, int* flag_sm) {
     double* W22 = W21 + 32;
     for (int e = t; e < 32 * 32; e += PP_THREADS) Wm[(e >> 5) * PP_LD + 32 + (e & 31)] = 0.0;
     if (warp == 0) {
-        const int bad = pp_chol_inv_32_warp(T, Wm, 0);
+        const int bad = pp_chol_inv_32_warp(T, Wm, pp_col, 0);
         if ((t & 31) == 0) *flag_sm = bad;
     }
     __syncthreads();
@@ -176,7 +196,7 @@ __device__ int pp_potrf_inv_64(double* T, double* Wm, int* flag_sm) {
     }
     __syncthreads();
     if (warp == 0) {
-        const int bad = pp_chol_inv_32_warp(T22, W22, 32);
+        const int bad = pp_chol_inv_32_warp(T22, W22, pp_col, 32);
         if ((t & 31) == 0) *flag_sm = bad;
     } else {
         // P = L21 W11 (into W21's place), the four 16 x 16 blocks over warps 1..3
