@@ -269,9 +269,10 @@ __device__ __forceinline__ unsigned long long pp_now() {
 
 // Task order (a topological order of the dependency graph; priority = position):
 //   diag(0); tile(1,0); diag(1);                                     all matrices interleaved
-//   step j = 0 .. nb-2:  tiles (i >= j+2, j)                          the bulk of column j
+//   step j = 0 .. nb-2:  tile (j+2, j)                                the chain's input from column j
 //                        tile (j+2, j+1), diag (j+2)                  the critical chain, issued one
 //                                                                     step AHEAD of its column's bulk
+//                        tiles (i >= j+3, j)                          the bulk of column j
 //                        W(j, j'), j' < j                             (inverse requested) background
 //   W(nb-1, .)                                                        (inverse requested)
 // The chain tasks are grabbed early and wait (at most 2 S CTAs do), so the bulk and the inverse
@@ -288,15 +289,16 @@ __device__ __forceinline__ void pp_decode(int tsk, int S, int nb, bool with_w, i
     }
     int rem = tsk - 3 * S;
     for (int jj = 0; jj <= nb - 2; ++jj) {
-        const int c1 = S * (nb - jj - 2);
-        if (rem < c1) {
-            s = rem % S;
-            i = jj + 2 + rem / S;
+        const bool chain = jj + 2 <= nb - 1;
+        const int c1a = chain ? S : 0;               // tile (jj+2, jj): the chain's own input
+        if (rem < c1a) {
+            s = rem;
+            i = jj + 2;
             j = jj;
             return;
         }
-        rem -= c1;
-        const int c2 = (jj + 2 <= nb - 1) ? 2 * S : 0;
+        rem -= c1a;
+        const int c2 = chain ? 2 * S : 0;
         if (rem < c2) {
             s = rem % S;
             i = jj + 2;
@@ -304,6 +306,14 @@ __device__ __forceinline__ void pp_decode(int tsk, int S, int nb, bool with_w, i
             return;
         }
         rem -= c2;
+        const int c1b = chain ? S * (nb - jj - 3) : 0;   // the rest of column jj
+        if (rem < c1b) {
+            s = rem % S;
+            i = jj + 3 + rem / S;
+            j = jj;
+            return;
+        }
+        rem -= c1b;
         const int c3 = with_w ? S * jj : 0;
         if (rem < c3) {
             kind = 1;

@@ -263,14 +263,19 @@ def _pp_decode(tsk, S, nb, with_w):
         return (0, tsk % S, 0 if w == 0 else 1, 1 if w == 2 else 0)
     rem = tsk - 3 * S
     for jj in range(0, nb - 1):
-        c1 = S * (nb - jj - 2)
-        if rem < c1:
-            return (0, rem % S, jj + 2 + rem // S, jj)
-        rem -= c1
-        c2 = 2 * S if jj + 2 <= nb - 1 else 0
+        chain = jj + 2 <= nb - 1
+        c1a = S if chain else 0
+        if rem < c1a:
+            return (0, rem, jj + 2, jj)
+        rem -= c1a
+        c2 = 2 * S if chain else 0
         if rem < c2:
             return (0, rem % S, jj + 2, jj + 1 if rem < S else jj + 2)
         rem -= c2
+        c1b = S * (nb - jj - 3) if chain else 0
+        if rem < c1b:
+            return (0, rem % S, jj + 3 + rem // S, jj)
+        rem -= c1b
         c3 = S * jj if with_w else 0
         if rem < c3:
             return (1, rem % S, jj, rem // S)
