@@ -87,7 +87,8 @@ SIGNATURES = {
     "bqo_set_device": (C.c_int, [C.c_int]),
     "bqo_launch_count": (_L, []),
     "bqo_hyper_stride": (_L, [_KD]),
-    "bqo_fp64_peak_probe": (C.c_int, [C.c_int, C.c_int, C.POINTER(_D), C.POINTER(_D)]),
+    "bqo_fp64_peak_probe_workspace_bytes": (C.c_int64, []),
+    "bqo_fp64_peak_probe": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.POINTER(_D), C.POINTER(_D)]),
     "bqo_hbm_copy_probe": (C.c_int, [_P, _P, _L, C.c_int, C.POINTER(_D)]),
     "bqo_hyper_prepare": (C.c_int, [_KD, _P, _I, _P, _P]),
     "bqo_scale_points": (C.c_int, [_KD, _P, _I, _P, _I, _I, _P, _P, _P]),

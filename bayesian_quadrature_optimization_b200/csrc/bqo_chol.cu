@@ -16,19 +16,6 @@
 #define NB BQO_TILE
 #define LDT (NB + 1)
 
-// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute of one kernel: set it once
-// per (kernel, device) and again only when a larger size is asked for.
-template <auto Kernel>
-static void bqo_smem_opt_in(size_t bytes) {
-    static int granted[64] = {0};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || granted[dev] < (int)bytes) {
-        cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        if (dev >= 0 && dev < 64) granted[dev] = (int)bytes;
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 // 1/sqrt(d) to full precision: MUFU.RSQ64H seed (2^-22) and two Newton steps.
 __device__ __forceinline__ double bqo_rsqrt_full(double d) {

@@ -304,6 +304,19 @@ static inline void bqo_ensure_global_exp_table(cudaStream_t cs) {
     done[dev] = true;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute of one kernel: set it once
+// per (kernel, device) and again only when a larger size is asked for.
+template <auto Kernel>
+static void bqo_smem_opt_in(size_t bytes) {
+    static int granted[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || granted[dev] < (int)bytes) {
+        cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (dev >= 0 && dev < 64) granted[dev] = (int)bytes;
+    }
+}
+
 __device__ __forceinline__ double bqo_warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -378,16 +378,7 @@ extern "C" int bqo_loglik_grad_batched(const bqo_kernel_desc* desc, const double
     }
     const int nb64 = (n + BQO_TILE - 1) / BQO_TILE;
     const int ntiles = nb64 * (nb64 + 1) / 2;       // <= the (n/32)^2 slots of `partial`
-    {
-        static int granted[64] = {0};
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (dev >= 0 && dev < 64 && !granted[dev]) {
-            cudaFuncSetAttribute(inv_syrk_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)LGF_SMEM_BYTES);
-            granted[dev] = 1;
-        }
-    }
+    bqo_smem_opt_in<inv_syrk_contract_kernel>(LGF_SMEM_BYTES);
     dim3 grid(nb64, nb64, S);
     BQO_L, inv_syrk_contract_kernel<<<grid, 128, LGF_SMEM_BYTES, cs>>>(*desc, hyp, st, Xs, tid, n, Wuse,
                                                                 alpha, partial, Wtask, ntiles);

@@ -362,17 +362,24 @@ __global__ void dmma_probe_kernel(double* out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
-extern "C" int bqo_fp64_peak_probe(int kind, int iters, double* ms_out, double* flops_out) {
+extern "C" int64_t bqo_fp64_peak_probe_workspace_bytes(void) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return (int64_t)sizeof(double) * sms * 4 * 256;
+}
+
+extern "C" int bqo_fp64_peak_probe(int kind, int iters, void* workspace, double* ms_out,
+                                   double* flops_out) {
     BQO_CHECK_ARG(kind == 0 || kind == 1, 1);
     BQO_CHECK_ARG(iters > 0, 2);
-    BQO_CHECK_ARG(ms_out != nullptr && flops_out != nullptr, 3);
+    BQO_CHECK_ARG(workspace != nullptr, 3);
+    BQO_CHECK_ARG(ms_out != nullptr && flops_out != nullptr, 4);
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int blocks = sms * 4, threads = 256;
-    double* out = nullptr;
-    cudaError_t e = cudaMalloc((void**)&out, sizeof(double) * blocks * threads);
-    if (e != cudaSuccess) return (int)e;
+    double* out = (double*)workspace;   // caller-owned: the library allocates nothing
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
@@ -392,7 +399,6 @@ extern "C" int bqo_fp64_peak_probe(int kind, int iters, double* ms_out, double* 
     else *flops_out = 2.0 * 8.0 * 8.0 * 4.0 * 8.0 * (double)iters * blocks * (threads / 32);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    cudaFree(out);
     return (int)cudaGetLastError();
 }
 

@@ -1063,8 +1063,7 @@ extern "C" int bqo_inner_maximize_batched(const bqo_stage_c* pb, const bqo_inner
     if (n_evals) cudaMemsetAsync(n_evals, 0, sizeof(unsigned long long) * pb->n_units, cs);
 #define LAUNCH_IM_K(DXV, DWV, STG, MTV, WDV, SB)                                                 \
     do {                                                                                         \
-        cudaFuncSetAttribute(inner_maximize_kernel<DXV, DWV, STG, MTV, WDV>,                     \
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SB));            \
+        bqo_smem_opt_in<inner_maximize_kernel<DXV, DWV, STG, MTV, WDV>>(SB);                     \
         BQO_L, inner_maximize_kernel<DXV, DWV, STG, MTV, WDV><<<grid, IM_WARPS * 32, (SB), cs>>>(       \
             *pb, *opt, z, starts, out_max, out_arg, n_evals);                                    \
     } while (0)
@@ -1351,8 +1350,7 @@ extern "C" int bqo_grad_vector_b_batched(const bqo_stage_c* pb, const double* pt
 #define LAUNCH_GVBS(DXV, DWV)                                                                    \
     do {                                                                                         \
         if (DWV > 0) {                                                                           \
-            cudaFuncSetAttribute(grad_vector_b_staged_kernel<DXV, (DWV > 0 ? DWV : 1)>,          \
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);          \
+            bqo_smem_opt_in<grad_vector_b_staged_kernel<DXV, (DWV > 0 ? DWV : 1)>>(sb);          \
             BQO_L, grad_vector_b_staged_kernel<DXV, (DWV > 0 ? DWV : 1)>                                \
                 <<<pb->n_units, IM_WARPS * 32, sb, cs>>>(*pb, pts, npts, out, is_nan);           \
         }                                                                                        \

@@ -512,9 +512,10 @@ def run_gpu(args):
     # FP64 peak of this GPU, measured now (MEASURED_PEAKS.json has no FP64 entry)
     lib = eng.lib
     ms, fl = C.c_double(), C.c_double()
-    _cabi.check(lib.bqo_fp64_peak_probe(0, 100000, C.byref(ms), C.byref(fl)), "probe")
+    probe_ws = torch.empty(int(lib.bqo_fp64_peak_probe_workspace_bytes()), dtype=torch.uint8, device=dev)
+    _cabi.check(lib.bqo_fp64_peak_probe(0, 100000, probe_ws.data_ptr(), C.byref(ms), C.byref(fl)), "probe")
     dfma_peak = fl.value / (ms.value * 1e-3) / 1e12
-    _cabi.check(lib.bqo_fp64_peak_probe(1, 100000, C.byref(ms), C.byref(fl)), "probe")
+    _cabi.check(lib.bqo_fp64_peak_probe(1, 100000, probe_ws.data_ptr(), C.byref(ms), C.byref(fl)), "probe")
     dmma_peak = fl.value / (ms.value * 1e-3) / 1e12
     # independent anchor for the FP64 tensor peak: cuBLAS DGEMM 4096^3 through torch.matmul
     ga = torch.randn(4096, 4096, dtype=torch.float64, device=dev)

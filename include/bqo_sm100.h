@@ -64,8 +64,10 @@ int64_t bqo_hyper_stride(const bqo_kernel_desc* desc);
 
 /* FP64 roofline probes (no reference counterpart; SURVEY 8d asks for a measured FP64 peak).
  * kind 0: dependent-chain-free DFMA loop, kind 1: DMMA m8n8k4 loop.  Synchronous.
- * Writes elapsed milliseconds and the FP64 flops executed. */
-int bqo_fp64_peak_probe(int kind, int iters, double* ms_out, double* flops_out);
+ * Writes elapsed milliseconds and the FP64 flops executed.  `workspace`: device scratch of
+ * bqo_fp64_peak_probe_workspace_bytes() bytes (the library allocates nothing itself). */
+int64_t bqo_fp64_peak_probe_workspace_bytes(void);
+int bqo_fp64_peak_probe(int kind, int iters, void* workspace, double* ms_out, double* flops_out);
 /* HBM copy probe: copies `bytes` bytes device to device `reps` times, returns the best ms. */
 int bqo_hbm_copy_probe(void* dst, const void* src, int64_t bytes, int reps, double* best_ms_out);
 

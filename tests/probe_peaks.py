@@ -11,10 +11,11 @@ lib = _cabi.load()
 torch.cuda.set_device(0)
 lib.bqo_set_device(0)
 out = {}
+ws = torch.empty(int(lib.bqo_fp64_peak_probe_workspace_bytes()), dtype=torch.uint8, device="cuda")
 for kind, name in [(0, "dfma"), (1, "dmma")]:
     ms, fl = C.c_double(), C.c_double()
     for iters in (20000, 200000):
-        rc = lib.bqo_fp64_peak_probe(kind, iters, C.byref(ms), C.byref(fl))
+        rc = lib.bqo_fp64_peak_probe(kind, iters, ws.data_ptr(), C.byref(ms), C.byref(fl))
         assert rc == 0, rc
         out["%s_tflops_%d" % (name, iters)] = fl.value / (ms.value * 1e-3) / 1e12
 a = torch.empty(1 << 28, dtype=torch.float64, device="cuda")
