@@ -20,14 +20,20 @@ gp = GPFittingGaussian([SCALED_KERNEL, MATERN52_NAME], td, [bench.DX + bench.DW]
 rng = np.random.RandomState(0)
 base = wl["thetas"][0]
 for S in (1, 2, 4, 8, 20):
-    ts = []
-    for rep in range(6):
-        th = base[None, :] * (1.0 + 0.02 * rng.normal(0, 1, (S, base.size)))
-        th[:, 1] = 0.0
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        gp.log_likelihood_batch(th)
-        torch.cuda.synchronize()
-        ts.append(time.perf_counter() - t0)
-    print("S=%2d: %.2f ms per call (min of 5 after warm-up; all: %s)"
-          % (S, 1e3 * min(ts[1:]), " ".join("%.1f" % (1e3 * t) for t in ts)))
+    for inv in (False, True):
+        # inv: alpha from L^-1 produced by extra tasks of the factorisation launch (two mat-vecs)
+        # instead of two triangular vector solves
+        ts = []
+        for rep in range(6):
+            th = base[None, :] * (1.0 + 0.02 * rng.normal(0, 1, (S, base.size)))
+            th[:, 1] = 0.0
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            hb = gp.hyper_batch(th)
+            hb.factorize(max_tries=7, with_inverse=inv)
+            hb.log_likelihood_host()
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        print("S=%2d, alpha from %s: %.2f ms per call (min of 5 after warm-up; all: %s)"
+              % (S, "L^-1 " if inv else "solves", 1e3 * min(ts[1:]),
+                 " ".join("%.1f" % (1e3 * t) for t in ts)))
