@@ -447,11 +447,21 @@ class GPFittingGaussian(object):
         self._raise_info(int(hb.info[0]))
         return hb.L.cpu().numpy()[0], cov
 
+    @staticmethod
+    def _factorize_for_likelihood(hb):
+        """Few large matrices (the slice sampler's probes): alpha from L^-1, which extra tasks of
+        the factorisation launch produce on otherwise idle SMs, beats two chains of vector solves
+        (1.72 -> 1.45 ms for one n = 2048 matrix, profiles/r02_stage_a.md).  The caller drops
+        hb.Winv once alpha is there."""
+        small = hb.S <= 4 and hb.eng.n >= 1024 and hb.eng.n % 2 == 0
+        return hb.factorize(max_tries=7, with_inverse=small)
+
     def log_likelihood(self, var_noise, mean, parameters_kernel):
         """:772-798 -> float."""
         hb = self._hb1(var_noise, mean, parameters_kernel)
-        hb.factorize(max_tries=7)
+        self._factorize_for_likelihood(hb)
         self._raise_info(int(hb.info[0]))
+        hb.Winv = None
         return float(hb.log_likelihood().cpu().numpy()[0])
 
     def grad_log_likelihood(self, var_noise, mean, parameters_kernel):
@@ -469,8 +479,10 @@ class GPFittingGaussian(object):
         """Batched extension: log-likelihood of S hyper-samples -> np.array(S); -inf where the
         factorisation failed (objective_llh convention, :946-960)."""
         hb = self.hyper_batch(thetas)
-        hb.factorize(max_tries=7)
-        return hb.log_likelihood_host()
+        self._factorize_for_likelihood(hb)
+        out = hb.log_likelihood_host()
+        hb.Winv = None
+        return out
 
     def grad_log_likelihood_batch(self, thetas):
         hb = self.hyper_batch(thetas)
