@@ -81,9 +81,12 @@ __device__ __forceinline__ double bqo_matern52_dr(double r, double r2) {
 // every other instruction for one (tests/microbench/fp64_issue.cu), and the evaluation loop is
 // bound by exactly that port (profiles/r01_inner_maximize_v1.md).  So every instruction counts,
 // FP64 or not, and sqrt and exp are open-coded:
-//   sqrt : MUFU.RSQ64H seed y (SFU pipe), h = y/2 by an integer exponent decrement, one
-//          Goldschmidt step and one Newton correction; h is not refreshed (the last correction
-//          d*h is already 2^-44 small, h's 2^-22 accuracy suffices);
+//   sqrt : MUFU.RSQ64H seed y (SFU pipe, 2^-22), g = u2 y, then ONE third-order (Halley) step:
+//          with e = 1 - g y the root is g (1 - e)^(-1/2) = g (1 + e/2 + 3 e^2/8) + (5/16) e^3 g,
+//          i.e. e = fma(-g, y, 1); p = fma(e, 3/8, 1/2); u = fma(g, e p, g): 5 FP64 instructions
+//          like the Goldschmidt + Newton pair it replaces, but no y/2 (one integer instruction
+//          less) and no DFMA with three register sources (one issue cycle less); remainder
+//          (5/16) e^3 < 5e-18, rounding about one ulp;
 //   exp  : table-driven.  With N = 2^BQO_EXP_BITS table entries per octave,
 //          exp(-s) = 2^-(m div N) * 2^-((m mod N)/N) * exp(fr),  m = round(s N / ln2),
 //          |fr| <= ln2 / (2N).  The larger the table the shorter the polynomial for exp(fr):
@@ -138,9 +141,6 @@ static __constant__ double BQO_FC[6] = {
 // Degree-3 variant that skips the multiplication by -c: the polynomial is taken in d = u - m
 // itself, monic, with its three coefficients as uniform-register operands (one LDCU each per
 // training point), and the factor -c^3/6 goes into the table.
-#ifndef BQO_HALF_INT
-#define BQO_HALF_INT 1  // y/2 by an exponent decrement (1 issue cycle) instead of a DMUL (2)
-#endif
 #ifndef BQO_POLY_UR
 #define BQO_POLY_UR (BQO_EXP_DEGREE == 3)
 #endif
@@ -187,24 +187,21 @@ __device__ __forceinline__ void bqo_matern52_q_v(const double (&u2)[NV], Tab tab
         asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(u2[q]));
         // LOSRC: the seed's low word is taken from `losrc` (any value the caller has in a dying
         // register pair) instead of being zeroed -- one MOV less per evaluation.  The seed is
-        // then off by up to 2^-20 instead of 2^-22; after the Goldschmidt step and the Newton
-        // correction that is 1e-18 relative, far below half an ulp.
+        // then off by up to 2^-20 instead of 2^-22: e <= 2.4e-6 and the Halley remainder
+        // (5/16) e^3 < 5e-18, far below half an ulp.
         if (LOSRC) y = __hiloint2double(__double2hiint(y), __double2loint(losrc[q]));
         g[q] = u2[q] * y;
-#if BQO_HALF_INT
-        h[q] = __hiloint2double(__double2hiint(y) - 0x00100000, LOSRC ? __double2loint(y) : 0);  // y/2 on the integer pipe
-#else
-        h[q] = 0.5 * y;
-#endif
+        h[q] = y;
     }
+    // Halley step: with e = 1 - g y (= 1 - u2 y^2), sqrt(u2) = g (1 - e)^(-1/2) = g (1 + e/2 + 3 e^2/8) + O(e^3)
 #pragma unroll
-    for (int q = 0; q < NV; ++q) w[q] = fma(-h[q], g[q], 0.5);
+    for (int q = 0; q < NV; ++q) w[q] = fma(-g[q], h[q], 1.0);
 #pragma unroll
-    for (int q = 0; q < NV; ++q) g[q] = fma(g[q], w[q], g[q]);
+    for (int q = 0; q < NV; ++q) h[q] = fma(w[q], 0.375, 0.5);
 #pragma unroll
-    for (int q = 0; q < NV; ++q) w[q] = fma(-g[q], g[q], u2[q]);
+    for (int q = 0; q < NV; ++q) w[q] = w[q] * h[q];
 #pragma unroll
-    for (int q = 0; q < NV; ++q) g[q] = fma(w[q], h[q], g[q]);  // u = sqrt(u2)
+    for (int q = 0; q < NV; ++q) g[q] = fma(g[q], w[q], g[q]);  // u = sqrt(u2)
 #pragma unroll
     for (int q = 0; q < NV; ++q) {
         // One unsigned clamp of the HIGH word of u (u > 0, so the word is monotone in u) bounds

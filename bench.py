@@ -87,13 +87,14 @@ def issue_model(evals_per_launch, kernel_ms, clocks, dfma_peak_tflops=None):
     by the lanes; profiles/r02_inner_maximize.md) priced with
     the measured issue costs (FP64 2 cycles, 3 with three register sources, others 1), against
     the cycles the launch took at the sampled SM clock."""
-    fp64, fp64_3src, other = 182.0, 35.3, 111.7
+    fp64, fp64_3src, other = 182.0, 25.3, 101.9
     cyc = 2.0 * fp64 + fp64_3src + other
     out = {"fp64_instr_per_point": fp64, "other_instr_per_point": other,
            "issue_cycles_per_point": cyc, "fp64_3src_instr_per_point": fp64_3src,
            "source": "executed-instruction counts of the ncu captures in "
-           "profiles/r02_inner_maximize.md (293.7 warp instructions per point, 182 of them FP64; "
-           "the three-source share from profiles/r01_inner_maximize_final.md); "
+           "profiles/r02_inner_maximize.md (283.9 warp instructions per point, 182 of them FP64; "
+           "three-source DFMAs: the 35.3 of profiles/r01_inner_maximize_final.md less the ten of "
+           "the square root, which the Halley step does without); "
            "148 SMs x 4 sub-partitions"}
     mhz = (clocks or {}).get("sm_mhz")
     if mhz:
