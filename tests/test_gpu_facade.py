@@ -706,3 +706,28 @@ def test_sbo_optimize_resident_samples_against_advancing_chain():
             assert 0.0 <= xs[0] <= 1.0 and 0.0 <= xs[1] <= 1.0 and int(xs[2]) in range(T)
     se = (a - b).std(ddof=1) / np.sqrt(len(a))
     assert a.mean() >= b.mean() - 2.0 * se, (a.mean(), b.mean(), se)
+
+
+def test_bgo_loop_converges_on_a_toy_problem():
+    """Four iterations of the whole BO loop (data append, factor extension, chain advance,
+    acquisition maximisation, posterior-mean optimum) for BQO and for EI: the reported optimum lands
+    near the true one (tests/microbench/bgo_loop_check.py prints the same runs)."""
+    from bayesian_quadrature_optimization_b200.services.bgo import bgo
+
+    def g(x):
+        return [-(x[0] - 0.3) ** 2 - 0.5 * (x[1] - 0.6) ** 2]
+
+    def f(xw):
+        return [-(xw[0] - 0.3) ** 2 - 0.5 * (xw[1] - 0.6) ** 2 + (0.2 if int(xw[2]) == 0 else -0.2)]
+
+    sol = bgo(g, [(0.0, 1.0), (0.0, 1.0)], integrand_function=f, bounds_domain_w=[[0, 1]],
+              type_bounds=[0, 0, 1], name_method='bqo', n_iterations=4, random_seed=5, n_training=12,
+              thinning=2, n_burning=20, max_steps_out=20, n_restarts=4, n_samples_parameters=3,
+              maxepoch=5, n_samples_mc=3, n_restarts_mc=3, default_n_samples=6,
+              default_n_samples_parameters=5, n_restarts_mean=20)
+    assert np.max(np.abs(sol["optimal_solution"] - np.array([0.3, 0.6]))) < 0.1
+    assert abs(sol["optimal_value"]) < 0.02
+    sol = bgo(g, [(0.0, 1.0), (0.0, 1.0)], name_method='ei', n_iterations=4, random_seed=5,
+              n_training=8, thinning=2, n_burning=20, max_steps_out=20, n_restarts=4,
+              n_samples_parameters=3, maxepoch=5, n_restarts_mean=20)
+    assert np.max(np.abs(sol["optimal_solution"] - np.array([0.3, 0.6]))) < 0.1
