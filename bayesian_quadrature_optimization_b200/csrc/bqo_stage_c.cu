@@ -264,6 +264,9 @@ __device__ __forceinline__ void eval_ab_warp(const EvalPtrs& p, const UnitCtx<DX
     const int M = (MT > 0) ? MT : p.M;
     constexpr bool REC = PRE && WD && (DW > 0);
     constexpr int RECLD = (DX + 2) | 1;
+    // finite W: one kernel evaluation per training point, so the loop bookkeeping is a quarter of
+    // the non-FP64 work: two points per trip (the W-sample loop already fills a trip otherwise)
+#pragma unroll(DW == 0 ? 2 : 1)
     for (int j = lane; j < p.n; j += 32) {
         double dxl[DX];
         // keeps q2 a normal positive number for the fast sqrt (k(0) = 1); with the W-distance
